@@ -1,0 +1,215 @@
+"""Launch sequencing for the models: packed parameters, workspaces and the per-call kernel
+sequences.  Everything numeric happens in ``libswe_gnn_b200.so``; this module only decides which
+buffer each launch reads and writes.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Dict, List, Optional, Sequence, Tuple
+
+import torch
+import torch.nn as nn
+
+from . import lib
+from .lib import ACT_CODES, SweLayer, SweMlp
+from .models.models import activation_name_of
+from .plan import EdgeSet, GraphPlan
+
+SUPPORTED_F = (16, 32, 64)
+
+
+def padded_width(f: int) -> int:
+    for w in SUPPORTED_F:
+        if f <= w:
+            return w
+    raise NotImplementedError(f"hid_features={f} is wider than the largest kernel instantiation ({SUPPORTED_F[-1]})")
+
+
+def _round4(k: int) -> int:
+    return (k + 3) // 4 * 4
+
+
+class PackedMLP:
+    """Kernel-side image of a ``make_mlp`` Sequential: transposed (k-major) weights with the input
+    and output widths zero-padded to what the kernels expect, biases copied next to them, PReLU
+    slopes referenced in place.  Re-packed automatically when a parameter changed."""
+
+    def __init__(self, seq: nn.Sequential, in_blocks: Sequence[Tuple[int, int]], hidden_pad: Dict[int, int],
+                 first_k_pad: Optional[int] = None):
+        """in_blocks: (true width, padded width) of every column block of the first layer's
+        input; hidden_pad: true output width -> padded output width."""
+        self.linears: List[nn.Linear] = []
+        self.acts: List[Optional[nn.Module]] = []
+        mods = list(seq)
+        i = 0
+        while i < len(mods):
+            assert isinstance(mods[i], nn.Linear), "MLP layout must be (Linear, activation)*"
+            self.linears.append(mods[i])
+            if i + 1 < len(mods) and not isinstance(mods[i + 1], nn.Linear):
+                self.acts.append(mods[i + 1])
+                i += 2
+            else:
+                self.acts.append(None)
+                i += 1
+        if len(self.linears) > lib.SWE_MAX_LAYERS:
+            raise NotImplementedError(f"MLPs deeper than {lib.SWE_MAX_LAYERS} layers are not supported")
+        self.in_blocks = list(in_blocks)
+        self.hidden_pad = dict(hidden_pad)
+        self.first_k_pad = first_k_pad
+        self._stamp = None
+        self._buf = None
+        self._struct = SweMlp()
+
+    def _out_pad(self, n: int) -> int:
+        return self.hidden_pad.get(n, n)
+
+    def struct(self) -> SweMlp:
+        stamp = tuple((p.data_ptr(), p._version) for lin in self.linears for p in lin.parameters()) + \
+            tuple(a.weight.data_ptr() for a in self.acts if isinstance(a, nn.PReLU))
+        if stamp == self._stamp:
+            return self._struct
+        dev = self.linears[0].weight.device
+        # layout of the flat buffer
+        shapes = []
+        for li, lin in enumerate(self.linears):
+            n_out, k_in = lin.weight.shape
+            if li == 0:
+                assert sum(b[0] for b in self.in_blocks) == k_in, "input blocks do not match the first layer"
+                k_pad = sum(b[1] for b in self.in_blocks)
+                if self.first_k_pad:
+                    k_pad = max(k_pad, self.first_k_pad)
+                k_pad = _round4(k_pad)
+            else:
+                k_pad = _round4(self._out_pad(k_in))
+            shapes.append((k_pad, self._out_pad(n_out)))
+        total = sum(k * n + _round4(n) for k, n in shapes)
+        if self._buf is None or self._buf.numel() != total or self._buf.device != dev:
+            self._buf = torch.zeros(total, dtype=torch.float32, device=dev)
+        off = 0
+        st = self._struct
+        st.n_layers = len(self.linears)
+        with torch.no_grad():
+            for li, (lin, act) in enumerate(zip(self.linears, self.acts)):
+                k_pad, n_pad = shapes[li]
+                n_out, k_in = lin.weight.shape
+                w = lin.weight.detach()
+                if w.dtype != torch.float32:
+                    raise TypeError("kernels are fp32; cast the model with .float()")
+                need_pad = (n_pad != n_out) or (li == 0 and any(a != b for a, b in self.in_blocks)) or \
+                    (li > 0 and self._out_pad(k_in) != k_in)
+                if need_pad:
+                    wp = torch.zeros(n_pad, k_pad, dtype=torch.float32, device=dev)
+                    if li == 0:
+                        c_src = c_dst = 0
+                        for true_w, pad_w in self.in_blocks:
+                            wp[:n_out, c_dst:c_dst + true_w] = w[:, c_src:c_src + true_w]
+                            c_src += true_w
+                            c_dst += pad_w
+                    else:
+                        wp[:n_out, :k_in] = w
+                    w_src = wp
+                else:
+                    w_src = w.contiguous()
+                wt = self._buf[off:off + k_pad * n_pad]
+                lib.pack_linear(w_src, k_pad, wt.view(k_pad, n_pad))
+                L: SweLayer = st.layer[li]
+                L.wt = wt.data_ptr()
+                off += k_pad * n_pad
+                if lin.bias is not None:
+                    b = self._buf[off:off + n_pad]
+                    b.zero_()
+                    b[:n_out] = lin.bias.detach()
+                    L.bias = b.data_ptr()
+                else:
+                    L.bias = None
+                off += _round4(n_pad)
+                name = activation_name_of(act)
+                L.act = ACT_CODES[name]
+                L.slope = act.weight.data_ptr() if isinstance(act, nn.PReLU) else None
+                if isinstance(act, nn.PReLU) and act.weight.numel() != 1:
+                    raise NotImplementedError("per-channel PReLU is not supported")
+                L.k_in, L.n_out = k_pad, n_pad
+        self._stamp = stamp
+        return st
+
+
+class PackedFilters:
+    """Packed (transposed, padded) filter matrices W_0..W_K of one SWEGNN (gnn.py:381-384)."""
+
+    def __init__(self, linears: Sequence[nn.Linear], F: int, FP: int):
+        self.linears = list(linears)
+        self.F, self.FP = F, FP
+        self._stamp = None
+        self._buf = None
+
+    def tensors(self) -> List[torch.Tensor]:
+        stamp = tuple((l.weight.data_ptr(), l.weight._version) for l in self.linears)
+        if stamp != self._stamp:
+            dev = self.linears[0].weight.device
+            if self._buf is None or self._buf.device != dev:
+                self._buf = torch.zeros(len(self.linears), self.FP, self.FP, dtype=torch.float32, device=dev)
+            with torch.no_grad():
+                for i, lin in enumerate(self.linears):
+                    w = lin.weight.detach()
+                    if self.FP != self.F:
+                        wp = torch.zeros(self.FP, self.FP, dtype=torch.float32, device=dev)
+                        wp[:self.F, :self.F] = w
+                        w = wp
+                    lib.pack_linear(w.contiguous(), self.FP, self._buf[i])
+            self._stamp = stamp
+        return [self._buf[i] for i in range(len(self.linears))]
+
+
+class SweGnnLauncher:
+    """Kernel sequence of one ``SWEGNN.forward`` call (reference models/gnn.py:387-445) on a
+    destination-CSR edge set: gate once, W0, then K hops ping-ponging between two buffers."""
+
+    def __init__(self, module, F: int):
+        self.m = module
+        self.F = F
+        self.FP = padded_width(F)
+        nseg = 5 if module.edge_features > 0 else 4
+        if module.edge_features not in (0, F):
+            raise NotImplementedError("SWEGNN edge_features must be 0 or equal to the node width "
+                                      f"(got {module.edge_features} vs {F})")
+        two = {F: self.FP, 2 * F: 2 * self.FP}
+        self.mlp = PackedMLP(module.edge_mlp, [(F, self.FP)] * nseg, two)
+        self.filters = PackedFilters(list(module.filter_matrix), F, self.FP) if module.with_filter_matrix else None
+
+    def run(self, es: EdgeSet, xs, xd_src, xd_dst, a, s_buf, o_dst_rows_zero: bool, tmp_a, tmp_b, out,
+            addend=None, act_code: int = 0, act_slope=None):
+        """Writes rows [es.dst_lo, es.dst_lo+es.n_dst) of `out`.
+
+        xd_src: array holding x_d[row]; xd_dst: array holding x_d[col] or None when those rows are
+        zero (then the hop also treats o[col] as zero).  tmp_a / tmp_b: scratch [N, FP] arrays.
+        """
+        m, FP = self.m, self.FP
+        E = es.n_edges
+        lib.edge_gate_fwd(xs, xd_src, xd_dst, a, es.src, es.dst, E, self.mlp.struct(), m.normalize, s_buf, FP)
+        K = m.K
+        if m.with_filter_matrix:
+            W = self.filters.tensors()
+            # o_0 = x_d W0ᵀ on the destination rows and on every source row read by the hops
+            if xd_dst is not None:
+                lib.node_linear_fwd(xd_dst, es.dst_lo, es.n_dst, W[0], tmp_a, FP)
+                if es.src_lo != es.dst_lo:
+                    lib.node_linear_fwd(xd_src, es.src_lo, es.src_hi - es.src_lo, W[0], tmp_a, FP)
+                o_src, o_dst = tmp_a, tmp_a
+            else:
+                lib.node_linear_fwd(xd_src, es.src_lo, es.src_hi - es.src_lo, W[0], tmp_a, FP)
+                o_src, o_dst = tmp_a, None
+        else:
+            W = [None] * (K + 1)
+            o_src, o_dst = xd_src, xd_dst
+        if K == 0:
+            raise NotImplementedError("SWEGNN with K=0 hops")
+        if K > 1 and es.src_lo != es.dst_lo:
+            raise NotImplementedError("multi-hop propagation needs source and destination in the same node set")
+        bufs = [tmp_b, tmp_a] if o_src is tmp_a else [tmp_a, tmp_b]
+        for k in range(K):
+            last = k == K - 1
+            dst_buf = out if last else bufs[k % 2]
+            lib.propagate_hop_fwd(o_src, o_dst, s_buf, es.rowptr, es.src, es.dst_lo, es.n_dst, W[k + 1],
+                                  m.with_gradient, m.upwind_mode, addend if last else None,
+                                  act_code if last else 0, act_slope if last else None, dst_buf, FP)
+            o_src = o_dst = dst_buf

@@ -1,0 +1,191 @@
+"""ctypes binding of ``libswe_gnn_b200.so`` (C ABI in ``include/swe_gnn_b200.h``).
+
+This is the only place the package touches native code.  There is NO fallback: if the shared
+object is missing or a symbol declared in the header is not exported, loading raises; every
+wrapper converts a non-zero status into ``RuntimeError`` carrying ``swe_last_error()``.
+Tensors are passed as raw device pointers (``tensor.data_ptr()``) after dtype / device /
+contiguity checks; the CUDA stream is torch's current stream, so calls are captured by
+``torch.cuda.graph`` like any other launch.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+from typing import Optional, Sequence
+
+import torch
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "csrc", "libswe_gnn_b200.so")
+
+SWE_MAX_LAYERS = 8
+ACT_CODES = {None: 0, "prelu": 1, "relu": 2, "tanh": 3, "leakyrelu": 4, "elu": 5, "swish": 6, "sigmoid": 7}
+
+
+class SweLayer(C.Structure):
+    _fields_ = [("wt", C.c_void_p), ("bias", C.c_void_p), ("slope", C.c_void_p),
+                ("k_in", C.c_int32), ("n_out", C.c_int32), ("act", C.c_int32), ("_pad", C.c_int32)]
+
+
+class SweMlp(C.Structure):
+    _fields_ = [("n_layers", C.c_int32), ("_pad", C.c_int32), ("layer", SweLayer * SWE_MAX_LAYERS)]
+
+
+_p, _i32, _i64, _f32, _sz = C.c_void_p, C.c_int32, C.c_int64, C.c_float, C.c_size_t
+_mlp = C.POINTER(SweMlp)
+
+# name -> (restype, argtypes); mirrors include/swe_gnn_b200.h one to one
+SIGNATURES = {
+    "swe_abi_version": (C.c_int, []),
+    "swe_last_error": (C.c_char_p, []),
+    "swe_build_arch": (C.c_char_p, []),
+    "swe_pack_linear": (C.c_int, [_p, _i32, _i32, _i32, _p, _p]),
+    "swe_csr_build_ws_bytes": (_sz, [_i64, _i32]),
+    "swe_csr_build": (C.c_int, [_p, _p, _i64, _p, _i32, _i32, _i32, _i32, _i32, _p, _p, _p, _p, _p, _p, _sz, _p]),
+    "swe_node_encode_fwd": (C.c_int, [_p, _i32, _p, _i32, _i32, _i32, _i32, _mlp, _mlp, _p, _p, _i32, _p]),
+    "swe_edge_encode_fwd": (C.c_int, [_p, _i32, _p, _i64, _mlp, _p, _i32, _p]),
+    "swe_edge_gate_fwd": (C.c_int, [_p, _p, _p, _p, _p, _p, _i64, _mlp, _i32, _p, _i32, _p]),
+    "swe_node_linear_fwd": (C.c_int, [_p, _i32, _i32, _p, _p, _i32, _p]),
+    "swe_propagate_hop_fwd": (C.c_int, [_p, _p, _p, _p, _p, _i32, _i32, _p, _i32, _i32, _p, _i32, _p, _p, _i32, _p]),
+    "swe_pool_mean_fwd": (C.c_int, [_p, _p, _p, _i32, _i32, _p, _i32, _p]),
+    "swe_decode_head_fwd": (C.c_int, [_p, _i32, _p, _mlp, _p, _i32, _p, _i32, _i32, _i32, _p, _f32, _p, _p, _i64,
+                                      _p, _i32, _p]),
+    "swe_apply_bc": (C.c_int, [_p, _i32, _i32, _i32, _i32, _p, _i32, _p, _i32, _p, _p]),
+    "swe_step_advance": (C.c_int, [_p, _p]),
+}
+
+_lib = None
+
+
+def load(path: Optional[str] = None):
+    """Load the shared object and bind every declared symbol.  Raises if anything is missing."""
+    global _lib
+    if _lib is not None and path is None:
+        return _lib
+    path = path or LIB_PATH
+    if not os.path.exists(path):
+        raise RuntimeError(
+            f"{path} not found: the CUDA extension is not built. Run `python -c \"import __graft_entry__ as g; "
+            f"g.build()\"` (needs nvcc). There is no CPU fallback.")
+    lib = C.CDLL(path)
+    for name, (res, args) in SIGNATURES.items():
+        try:
+            fn = getattr(lib, name)
+        except AttributeError as e:
+            raise RuntimeError(f"{path} does not export `{name}` declared in include/swe_gnn_b200.h") from e
+        fn.restype, fn.argtypes = res, args
+    if lib.swe_abi_version() != 1:
+        raise RuntimeError(f"ABI version mismatch: library {lib.swe_abi_version()}, binding 1")
+    _lib = lib
+    return lib
+
+
+def _check(status: int, what: str):
+    if status != 0:
+        msg = load().swe_last_error().decode(errors="replace")
+        raise RuntimeError(f"{what} failed (status {status}): {msg}")
+
+
+def _stream() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+def ptr(t: Optional[torch.Tensor], dtype=torch.float32) -> Optional[int]:
+    """Device pointer of a contiguous CUDA tensor of the given dtype (None passes NULL)."""
+    if t is None:
+        return None
+    if not t.is_cuda:
+        raise RuntimeError("mswe_gnn_b200 kernels need CUDA tensors; got a %s tensor (no CPU fallback)" % t.device)
+    if t.dtype != dtype:
+        raise TypeError(f"expected {dtype}, got {t.dtype}")
+    if not t.is_contiguous():
+        raise ValueError("tensor must be contiguous")
+    return t.data_ptr()
+
+
+# ------------------------------------------------------------------------------------------------
+# thin wrappers (one per C entry point)
+# ------------------------------------------------------------------------------------------------
+def pack_linear(w: torch.Tensor, k_pad: int, out: torch.Tensor):
+    n_out, k_in = w.shape
+    _check(load().swe_pack_linear(ptr(w), n_out, k_in, k_pad, ptr(out), _stream()), "swe_pack_linear")
+
+
+def csr_build(row, col, node_map, dst_lo, n_dst, src_lo, src_hi, by_row=False):
+    """Returns (rowptr, src, dst, eid) int32 tensors; raises ValueError on out-of-range edges."""
+    lib = load()
+    E = int(row.numel())
+    dev = row.device
+    rowptr = torch.empty(n_dst + 1, dtype=torch.int32, device=dev)
+    src = torch.empty(max(E, 1), dtype=torch.int32, device=dev)
+    dst = torch.empty(max(E, 1), dtype=torch.int32, device=dev)
+    eid = torch.empty(max(E, 1), dtype=torch.int32, device=dev)
+    err = torch.zeros(1, dtype=torch.int32, device=dev)
+    ws_bytes = int(lib.swe_csr_build_ws_bytes(E, n_dst))
+    ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
+    _check(lib.swe_csr_build(ptr(row, torch.int64), ptr(col, torch.int64), E, ptr(node_map, torch.int32),
+                             dst_lo, n_dst, src_lo, src_hi, int(by_row), ptr(rowptr, torch.int32),
+                             ptr(src, torch.int32), ptr(dst, torch.int32), ptr(eid, torch.int32),
+                             ptr(err, torch.int32), ws.data_ptr(), ws_bytes, _stream()), "swe_csr_build")
+    n_bad = int(err.item())
+    if n_bad:
+        raise ValueError(f"{n_bad} edges have an endpoint outside the node range of their scale "
+                         f"(dst range [{dst_lo}, {dst_lo + n_dst}), src range [{src_lo}, {src_hi}))")
+    return rowptr, src[:E], dst[:E], eid[:E]
+
+
+def node_encode_fwd(x, perm, n_nodes, n_static_raw, with_wl, n_dyn_rows, mlp_s: SweMlp, mlp_d: SweMlp, xs, xd, F):
+    _check(load().swe_node_encode_fwd(ptr(x), x.shape[1], ptr(perm, torch.int32), n_nodes, n_static_raw, int(with_wl),
+                                      n_dyn_rows, C.byref(mlp_s), C.byref(mlp_d), ptr(xs), ptr(xd), F, _stream()),
+           "swe_node_encode_fwd")
+
+
+def edge_encode_fwd(edge_attr, eid, n_edges, mlp: SweMlp, a_out, F):
+    _check(load().swe_edge_encode_fwd(ptr(edge_attr), edge_attr.shape[1], ptr(eid, torch.int32), n_edges,
+                                      C.byref(mlp), ptr(a_out), F, _stream()), "swe_edge_encode_fwd")
+
+
+def edge_gate_fwd(xs, xd_src, xd_dst, a, src, dst, n_edges, mlp: SweMlp, normalize, s_out, F):
+    _check(load().swe_edge_gate_fwd(ptr(xs), ptr(xd_src), ptr(xd_dst), ptr(a), ptr(src, torch.int32),
+                                    ptr(dst, torch.int32), n_edges, C.byref(mlp), int(normalize), ptr(s_out), F,
+                                    _stream()), "swe_edge_gate_fwd")
+
+
+def node_linear_fwd(x, row_lo, n_rows, wt, out, F):
+    _check(load().swe_node_linear_fwd(ptr(x), row_lo, n_rows, ptr(wt), ptr(out), F, _stream()), "swe_node_linear_fwd")
+
+
+def propagate_hop_fwd(o_src, o_dst, s, rowptr, src, dst_lo, n_dst, wt, with_gradient, upwind, addend, act, slope,
+                      out, F):
+    _check(load().swe_propagate_hop_fwd(ptr(o_src), ptr(o_dst), ptr(s), ptr(rowptr, torch.int32),
+                                        ptr(src, torch.int32), dst_lo, n_dst, ptr(wt), int(with_gradient),
+                                        int(upwind), ptr(addend), act, ptr(slope), ptr(out), F, _stream()),
+           "swe_propagate_hop_fwd")
+
+
+def pool_mean_fwd(x, rowptr, fine, coarse_lo, n_coarse, out, F):
+    _check(load().swe_pool_mean_fwd(ptr(x), ptr(rowptr, torch.int32), ptr(fine, torch.int32), coarse_lo, n_coarse,
+                                    ptr(out), F, _stream()), "swe_pool_mean_fwd")
+
+
+def decode_head_fwd(h, act_in, slope_in, dec: SweMlp, x0, perm, n_nodes, previous_t, res_mode, res_w, eps, pred,
+                    step_ptr, pred_step_stride, x_next, F):
+    _check(load().swe_decode_head_fwd(ptr(h), act_in, ptr(slope_in), C.byref(dec), ptr(x0), x0.shape[1],
+                                      ptr(perm, torch.int32), n_nodes, previous_t, res_mode, ptr(res_w), float(eps),
+                                      ptr(pred), ptr(step_ptr, torch.int32), pred_step_stride, ptr(x_next), F,
+                                      _stream()), "swe_decode_head_fwd")
+
+
+def apply_bc(x, n_static_raw, previous_t, type_bc, node_bc, bc, step_ptr):
+    if type_bc == 3:
+        raise ValueError("Vector boundary conditions are not yet implemented.")
+    if type_bc not in (1, 2):
+        raise ValueError(f"BC_type={type_bc} is not a valid input. Please select either:\n"
+                         "1: Inflow water depth\n2: Inflow discharge")
+    _check(load().swe_apply_bc(ptr(x), x.shape[1], n_static_raw, previous_t, type_bc, ptr(node_bc, torch.int64),
+                               node_bc.numel(), ptr(bc), bc.shape[-1], ptr(step_ptr, torch.int32), _stream()),
+           "swe_apply_bc")
+
+
+def step_advance(step_ptr):
+    _check(load().swe_step_advance(ptr(step_ptr, torch.int32), _stream()), "swe_step_advance")

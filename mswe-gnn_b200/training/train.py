@@ -1,0 +1,148 @@
+"""Rollout and training-step drivers mirroring the reference's ``training/train.py``.
+
+``rollout_test(model, batch)`` keeps the reference signature and result (``[N, 2, T]``,
+``training/train.py:67-95``) but runs the whole autoregressive loop on the device: boundary
+injection, the model's kernel sequence and the window shift of one step are captured once in a
+CUDA graph and replayed for every time step, with a device-side step counter selecting the
+boundary value and the output slot — no host synchronisation inside the loop.
+The Lightning wrapper itself (``LightningTrainer``) is orchestration and is not rebuilt.
+"""
+from __future__ import annotations
+
+import os
+from typing import Optional
+
+import torch
+
+from .. import lib
+from ..utils.data import Batch, Data
+from ..utils.dataset import NUM_WATER_VARS, apply_boundary_condition, check_type_BC, use_prediction
+
+
+def _is_batch(obj) -> bool:
+    return isinstance(obj, Batch) or type(obj).__name__.endswith("Batch")
+
+
+def update_batch_multiscale(batch):
+    """Regroup the edges / inter-scale edges of a PyG-collated multiscale batch per scale across
+    graphs and make ``node_ptr`` a cumulative ``[G, S+1]`` table (reference
+    ``training/train.py:31-65``)."""
+    G = int(batch.num_graphs)
+    eptr = batch.edge_ptr.reshape(G, -1).clone()
+    iptr = batch.intra_edge_ptr.reshape(G, -1).clone()
+    nptr = batch.node_ptr.reshape(G, -1).clone()
+    for table in (eptr, iptr, nptr):
+        for g in range(1, G):
+            table[g] += table[g - 1].max()
+    S = iptr.shape[1]
+    e_lo, e_hi = eptr[:, :-1].tolist(), eptr[:, 1:].tolist()
+    i_lo, i_hi = iptr[:, :-1].tolist(), iptr[:, 1:].tolist()
+    ei = [torch.cat([batch.edge_index[:, e_lo[g][s]:e_hi[g][s]] for g in range(G)], 1) for s in range(S)]
+    ea = [torch.cat([batch.edge_attr[e_lo[g][s]:e_hi[g][s]] for g in range(G)]) for s in range(S)]
+    ie = [torch.cat([batch.intra_mesh_edge_index[:, i_lo[g][s]:i_hi[g][s]] for g in range(G)], 1)
+          for s in range(S - 1)]
+    dev = batch.edge_index.device
+    batch.node_ptr = nptr
+    batch.edge_index = torch.cat(ei, 1).contiguous()
+    batch.edge_attr = torch.cat(ea).contiguous()
+    batch.edge_ptr = torch.tensor([0] + [e.shape[1] for e in ei]).cumsum(0)
+    batch.intra_edge_ptr = torch.tensor([0] + [e.shape[1] for e in ie]).cumsum(0)
+    batch.intra_mesh_edge_index = torch.cat(ie, 1).contiguous() if ie else torch.zeros(2, 0, dtype=torch.long, device=dev)
+
+
+def adapt_batch_training(batch):
+    """Reference ``training/train.py:14-29``: offset ``node_BC`` per graph, collapse the per-graph
+    scalars, and regroup multiscale batches."""
+    assert _is_batch(batch), "This function requires a Batch object as input"
+    temp = batch.clone()
+    G = int(temp.num_graphs)
+    temp.node_BC = torch.cat([temp.ptr[i].to(batch[i].node_BC.device) + batch[i].node_BC for i in range(G)]) \
+        .to(temp.x.device)
+    for name in ("temporal_res", "type_BC", "previous_t"):
+        v = getattr(temp, name, None)
+        if v is not None and not isinstance(v, (int, float)):
+            setattr(temp, name, int(v[0]))
+    if "edge_ptr" in temp.keys():
+        update_batch_multiscale(temp)
+        lo, hi = temp.node_ptr[:, 0], temp.node_ptr[:, -1]
+        temp.node_BC_ptr = torch.tensor([int(torch.where((lo <= n) & (n <= hi))[0][0]) for n in temp.node_BC.cpu()])
+    else:
+        temp.node_BC_ptr = torch.tensor([int(torch.where((temp.ptr[:-1].cpu() <= n) & (n < temp.ptr[1:].cpu()))[0][0])
+                                         for n in temp.node_BC.cpu()])
+    return temp
+
+
+class RolloutRunner:
+    """Device-resident autoregressive loop for one (model, graph) pair."""
+
+    def __init__(self, model, graph, n_steps: int, use_cuda_graph: Optional[bool] = None):
+        model._check_input(graph)
+        self.model, self.graph, self.T = model, graph, int(n_steps)
+        multiscale = model.type_model == "MSGNN"
+        self.plan = model._plans.get(graph, getattr(model, "num_scales", 1), multiscale)
+        dev = graph.x.device
+        N = self.plan.n_nodes
+        self.x = graph.x.detach().clone().contiguous()
+        self.preds = torch.empty(self.T, N, NUM_WATER_VARS, dtype=torch.float32, device=dev)
+        self.step = torch.zeros(1, dtype=torch.int32, device=dev)
+        self.type_BC = int(graph.type_BC)
+        check_type_BC(self.type_BC)
+        self.node_BC = graph.node_BC.to(dev, torch.int64).contiguous()
+        self.bc = graph.BC.to(dev, torch.float32).contiguous()
+        if self.bc.shape[-1] < self.T:
+            raise ValueError(f"BC holds {self.bc.shape[-1]} time steps, rollout needs {self.T}")
+        self.n_static_raw = self.x.shape[1] - model.previous_t * NUM_WATER_VARS
+        if use_cuda_graph is None:
+            use_cuda_graph = os.environ.get("MSWE_CUDA_GRAPH", "1") != "0"
+        self.use_cuda_graph = use_cuda_graph and self.T > 2
+        self._graph = None
+
+    def _one_step(self):
+        m = self.model
+        lib.apply_bc(self.x, self.n_static_raw, m.previous_t, self.type_BC, self.node_BC, self.bc, self.step)
+        m._launch(self.plan, self.graph, self.x, self.preds, step_ptr=self.step,
+                  pred_stride=self.preds.shape[1] * NUM_WATER_VARS, x_next=self.x)
+        lib.step_advance(self.step)
+
+    def reset(self, x: Optional[torch.Tensor] = None):
+        self.x.copy_(self.graph.x if x is None else x)
+        self.step.zero_()
+
+    def run(self, n_steps: Optional[int] = None):
+        """Advance `n_steps` (default: all remaining) steps; returns the prediction buffer
+        ``[T, N, 2]`` (slot t holds step t)."""
+        n = self.T if n_steps is None else n_steps
+        done = 0
+        if self.use_cuda_graph and self._graph is None and n > 1:
+            self._one_step()                     # eager: lazy packing / allocation happen here
+            done = 1
+            g = torch.cuda.CUDAGraph()
+            torch.cuda.synchronize()
+            with torch.cuda.graph(g):
+                self._one_step()
+            self._graph = g
+        for _ in range(done, n):
+            if self._graph is not None:
+                self._graph.replay()
+            else:
+                self._one_step()
+        return self.preds
+
+
+@torch.no_grad()
+def rollout_test(model, batch, use_cuda_graph: Optional[bool] = None):
+    '''
+    Tests a model and returns the rollout prediction ``[N, 2, T]`` (reference
+    ``training/train.py:67-95``).
+    ------
+    model: GNN or MSGNN from ``mswe_gnn_b200.models.gnn``
+    batch: a single graph (``Data``) or several graphs stacked in a ``Batch``
+    '''
+    temp = adapt_batch_training(batch) if _is_batch(batch) else batch.clone()
+    dynamic_vars = model.previous_t * model.NUM_WATER_VARS
+    assert temp.x.shape[-1] >= dynamic_vars, \
+        "The number of dynamic variables is greater than the number of node features"
+    final_step = batch.y.shape[-1]
+    runner = RolloutRunner(model, temp, final_step, use_cuda_graph)
+    preds = runner.run()
+    return preds.permute(1, 2, 0)

@@ -1,0 +1,112 @@
+"""CPU: host-side logic and the C-ABI surface (no compute calls)."""
+import os
+import re
+
+import numpy as np
+import pytest
+import torch
+
+import mswe_gnn_b200  # noqa: F401
+from helpers import REF_CONFIG_MODELS
+from mswe_gnn_b200 import lib
+from mswe_gnn_b200.utils.data import Batch
+from mswe_gnn_b200.utils.synthetic import make_single_scale_mesh, make_tri_mesh, tri_level_sizes
+from oracle import plan_oracle as P
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_library_exports_every_declared_symbol():
+    header = open(os.path.join(ROOT, "include", "swe_gnn_b200.h")).read()
+    declared = set(re.findall(r"\b(swe_[a-z0-9_]+)\s*\(", header))
+    assert declared, "no declarations parsed"
+    l = lib.load()
+    for name in declared:
+        assert hasattr(l, name), f"{name} declared in the header but not exported"
+    assert declared == set(lib.SIGNATURES), (declared ^ set(lib.SIGNATURES))
+    assert l.swe_abi_version() == 1 and l.swe_build_arch() == b"sm_100a"
+
+
+def test_missing_library_fails_loudly(tmp_path):
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        lib.load(str(tmp_path / "nope.so"))
+
+
+def test_models_refuse_cpu_tensors():
+    from mswe_gnn_b200.models.gnn import MSGNN
+    m = MSGNN(num_node_features=8, num_edge_features=1, num_scales=3, previous_t=3, **{**REF_CONFIG_MODELS, "hid_features": 16})
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        with torch.no_grad():
+            m(make_tri_mesh(8, 4, 3))
+
+
+def test_unsupported_options_raise():
+    from mswe_gnn_b200.models.gnn import GNN, MSGNN
+    from mswe_gnn_b200.models.models import activation_functions, make_mlp
+    with pytest.raises(NotImplementedError):
+        MSGNN(8, 1, 3, learned_pooling=True, previous_t=3)
+    with pytest.raises(NotImplementedError):
+        GNN(8, 1, type_GNN="GAT", previous_t=3)
+    with pytest.raises(ValueError):
+        GNN(8, 1, type_GNN="nonsense", previous_t=3)
+    with pytest.raises(NotImplementedError):
+        make_mlp(4, 4, layer_norm=True)
+    with pytest.raises(AttributeError):
+        activation_functions("gelu")
+    with pytest.raises(AssertionError):
+        MSGNN(8, 1, 3, K=[1, 2], previous_t=3)
+
+
+def test_synthetic_mesh_sizes_match_survey():
+    d = make_tri_mesh(32, 24, 4)
+    assert d.x.shape[0] == 2044 and d.edge_index.shape[1] == 5914
+    assert d.node_ptr.tolist() == [0, 1537, 1922, 2019, 2044]
+    assert [s[0] for s in tri_level_sizes(712, 712, 4)] == [1013889, 253473, 63369, 15843]
+    assert sum(s[1] for s in tri_level_sizes(712, 712, 4)) == 4034374
+    assert sum(s[0] for s in tri_level_sizes(2832, 2832, 4)) == 21303724
+    ei = d.edge_index[:, :4496]
+    fwd = set(map(tuple, ei.t().tolist()))
+    assert all((b, a) in fwd for a, b in fwd)                       # undirected part is symmetric
+    assert d.edge_index[:, 4496].tolist() == [1536, 0]              # ghost -> face 0
+    key = ei[0] * 10000 + ei[1]
+    assert bool((key[1:] > key[:-1]).all())                         # (row, col) sorted
+    c, f = d.intra_mesh_edge_index[:, :1536]
+    assert bool((c[1:] >= c[:-1]).all()) and torch.bincount(c - 1537).tolist() == [4] * 384
+
+
+def test_plan_oracle_loops_vs_numpy():
+    rng = np.random.default_rng(0)
+    row = rng.integers(0, 40, 300)
+    col = rng.integers(10, 30, 300)
+    a = P.stable_dst_csr(row, col, None, 10, 20)
+    b = P.stable_dst_csr_loops(row.tolist(), col.tolist(), 10, 20)
+    for x, y in zip(a, b):
+        assert x.tolist() == list(y)
+    # stable order == scatter_add_ order: sequential in-segment sums reproduce it bit for bit
+    vals = torch.randn(300, 4)
+    ref = torch.zeros(20, 4).scatter_add_(0, torch.from_numpy(col - 10).view(-1, 1).expand(-1, 4), vals)
+    rowptr, _, _, eid = a
+    out = torch.zeros(20, 4)
+    for i in range(20):
+        acc = torch.zeros(4)
+        for p in range(rowptr[i], rowptr[i + 1]):
+            acc = acc + vals[eid[p]]
+        out[i] = acc
+    assert torch.equal(out, ref)
+
+
+def test_batch_collation_and_permutation():
+    graphs = [make_tri_mesh(8, 8, 3, seed=s) for s in range(3)]
+    b = Batch.from_data_list(graphs)
+    n = [g.x.shape[0] for g in graphs]
+    assert b.ptr.tolist() == [0, n[0], n[0] + n[1], sum(n)]
+    assert torch.equal(b.edge_index[:, graphs[0].edge_index.shape[1]:][:, :5], graphs[1].edge_index[:, :5] + n[0])
+    assert torch.equal(b.node_ptr[:4], graphs[0].node_ptr)          # *_ptr are NOT shifted by collation
+    from mswe_gnn_b200.training.train import adapt_batch_training
+    t = adapt_batch_training(b)
+    assert t.node_ptr.shape == (3, 4) and int(t.node_ptr[-1, -1]) == sum(n)
+    perm, inv = P.batch_permutation(t.node_ptr.numpy())
+    assert sorted(perm.tolist()) == list(range(sum(n)))
+    s0 = graphs[0].node_ptr[1].item()
+    assert perm[:s0].tolist() == list(range(s0)) and perm[s0] == n[0]        # scale-major, graph-minor
+    assert t.node_BC.tolist() == [s0 - 1, n[0] + s0 - 1, n[0] + n[1] + s0 - 1]
