@@ -1,0 +1,355 @@
+#!/usr/bin/env python
+"""Benchmark of the mSWE-GNN rollout hot path (contract: see the task statement / DESIGN.md §5).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload cfg3]
+
+One "step" = one autoregressive rollout step (boundary injection, full MSGNN forward, window
+shift) of the default config.yaml mSWE-GNN (K=4, F=64, 3-layer MLPs, 4 scales) on a synthetic
+triangular mesh.  N=1: cfg3 = tri(712,712), 1,346,574 nodes (BASELINE.json configs[2], the
+single-GPU configuration the rollout metric is quoted on).  Metric: node-steps/s.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import torch  # noqa: E402
+
+MODEL_CFG = dict(hid_features=64, mlp_layers=3, seed=666, learned_residuals=True, mlp_activation="prelu",
+                 gnn_activation="tanh", edge_mlp=True, normalize=True, with_filter_matrix=True, with_gradient=True,
+                 with_WL=True, K=4, learned_pooling=False, skip_connections=True)      # config.yaml:42-58
+CTOR = dict(num_node_features=8, num_edge_features=1, num_scales=4, previous_t=3, **MODEL_CFG)
+WORKLOADS = {"cfg1": (32, 24), "cfg5": (224, 224), "cfg3": (712, 712), "cfg4": (2832, 2832), "cpu_sample": (192, 192)}
+F, K_HOPS, S = 64, 4, 4
+
+
+def peaks():
+    try:
+        p = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        return dict(hbm=p["hbm_gbs"], hbm_src="measured", bf16=p["bf16_tflops_sustained"], bf16_burst=p["bf16_tflops"])
+    except Exception:
+        return dict(hbm=6650.0, hbm_src="fallback", bf16=1400.0, bf16_burst=1590.0)
+
+
+def algorithmic_bytes(nx, ny):
+    """per-forward algorithmic bytes (fp32 features, int32 CSR, neighbour gathers
+    L2-served, s_ij written once per SWEGNN call and re-read every hop)."""
+    from mswe_gnn_b200.utils.synthetic import tri_level_sizes
+    sz = tri_level_sizes(nx, ny, S)
+    N = [s[0] for s in sz]; E = [s[1] for s in sz]; I = [s[2] for s in sz]
+    gate = lambda s: 4 * F * (2 * N[s] + 2 * E[s]) + 4 * (E[s] + N[s] + 1)
+    hop = lambda s: 4 * F * (E[s] + 2 * N[s]) + 4 * (E[s] + N[s] + 1)
+    calls = list(range(S - 1)) + list(range(S - 1, -1, -1))
+    total = sum(gate(s) + K_HOPS * hop(s) for s in calls)
+    Nt, Et = sum(N), sum(E)
+    total += 4 * (Et * (1 + F) + Nt * (9 + 2 * F) + Nt * (F + 2))
+    for s in range(S - 1):
+        total += 4 * F * (2 * (N[s] + N[s + 1]) + 2 * N[s]) + 8 * I[s] + 4 * F * (N[s] + N[s + 1]) + 4 * I[s]
+    return dict(total=total, gate=[gate(s) for s in range(S)], hop=[hop(s) for s in range(S)], N=N, E=E, I=I)
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled during the timed region."""
+    Q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
+        "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, index=0):
+        self.rows, self.proc, self.index = [], None, index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm, mx, reasons = [], None, set()
+        for r in self.rows:
+            parts = [p.strip() for p in r.split(",")]
+            if len(parts) < 7:
+                continue
+            try:
+                sm.append(float(parts[0])); mx = float(parts[1])
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), parts[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+# --------------------------------------------------------------------------------------------------
+# reference arm / CPU baseline: the oracle port of the reference's PyG path on the host cores
+# --------------------------------------------------------------------------------------------------
+def cpu_reference_rate(steps, warmup, threads=None):
+    """node-steps/s of the reference CPU path (oracle/swe_oracle.py: per-hop masks, compaction and
+    K× edge-MLP evaluation exactly as /root/reference/models/gnn.py does) on a bounded sample."""
+    from oracle import swe_oracle as O
+    from mswe_gnn_b200.models.gnn import MSGNN
+    from mswe_gnn_b200.utils.synthetic import make_tri_mesh
+    threads = threads or os.cpu_count()
+    torch.set_num_threads(threads)
+    nx, ny = WORKLOADS["cpu_sample"]
+    data = make_tri_mesh(nx, ny, S, rollout_steps=steps + warmup)
+    sd = MSGNN(**CTOR).state_dict()
+    spec = O.ModelSpec("MSGNN", **CTOR)
+    n = data.x.shape[0]
+    t = O._Bag(**{k: (getattr(data, k).clone() if torch.is_tensor(getattr(data, k)) else getattr(data, k)) for k in data.keys()})
+    times = []
+    with torch.no_grad():
+        for i in range(warmup + steps):
+            t0 = time.perf_counter()
+            t.x[:, -6:] = O.apply_boundary_condition(t.x[:, -6:], t.BC[:, :, i], t.node_BC, t.type_BC)
+            p = O.forward(sd, spec, t)
+            t.x = O.use_prediction(t.x, p, 3)
+            times.append(time.perf_counter() - t0)
+    timed = times[warmup:]
+    sec = sum(timed) / len(timed)
+    return dict(value=n / sec, ms_per_step=sec * 1e3, cores=threads, nodes=n,
+                sample=f"{steps} rollout steps of the same model on tri({nx},{ny}) 4-scale ({n} nodes), torch {torch.__version__} CPU, {threads} threads")
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    steps, warmup = min(args.steps, 3), min(args.warmup, 1)
+    r = cpu_reference_rate(steps, warmup)
+    nx, ny = WORKLOADS[args.workload or "cfg3"]
+    line = {"impl": "reference", "metric": "mSWE-GNN rollout node-steps/sec", "value": r["value"], "unit": "node-steps/s",
+            "n_gpus": args.gpus, "steps": steps, "warmup": warmup, "ms_per_step": r["ms_per_step"],
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": f"{args.workload or 'cfg3'}: default config.yaml mSWE-GNN (K4,F64,S4) rollout on tri({nx},{ny}); "
+                                   f"CPU arm timed on a bounded sample: {r['sample']}"},
+            "cpu_baseline": {"value": r["value"], "unit": "node-steps/s", "cores": r["cores"], "kind": "port", "sample": r["sample"]},
+            "e2e": {"value": r["value"], "unit": "node-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+
+
+# --------------------------------------------------------------------------------------------------
+# our arm
+# --------------------------------------------------------------------------------------------------
+def run_ours(args):
+    import torch.distributed as dist
+    import mswe_gnn_b200  # noqa: F401
+    from mswe_gnn_b200 import lib
+    from mswe_gnn_b200.models.gnn import MSGNN
+    from mswe_gnn_b200.training.train import RolloutRunner, rollout_test
+    from mswe_gnn_b200.utils.synthetic import make_tri_mesh
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    lib.load()
+    wl = args.workload or "cfg3"
+    nx, ny = WORKLOADS[wl]
+    K, W = args.steps, max(args.warmup, 3)
+    model = MSGNN(**CTOR).to(dev)
+    host = make_tri_mesh(nx, ny, S, rollout_steps=K + W, seed=rank)      # one simulation per rank (replicas)
+    N_nodes = host.x.shape[0]
+    data = host.to(dev)
+    runner = RolloutRunner(model, data, K + W, use_cuda_graph=True)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    runner.run(W)                                                          # warm-up (includes graph capture)
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    barrier()
+    l0 = lib.launch_count
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev0.record()
+    runner.run(K)
+    ev1.record()
+    barrier()
+    ms = ev0.elapsed_time(ev1)
+    clocks = sampler.stop() if rank == 0 else None
+    per_step_launches = runner.launches_per_step
+    if world > 1:
+        t = torch.tensor([ms], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+    value = N_nodes * world * K / (ms * 1e-3)
+
+    # ---- end-to-end through the public API with HOST (pinned) inputs: rollout_test(model, host_graph)
+    host_p = host.clone()
+    for k in host_p.keys():
+        v = getattr(host_p, k)
+        if torch.is_tensor(v):
+            setattr(host_p, k, v.pin_memory())
+    host_p.y = torch.empty(0, 2, K)                     # only its last dimension (number of steps) is read
+    h2d = sum(getattr(host_p, k).numel() * getattr(host_p, k).element_size() for k in host_p.keys()
+              if torch.is_tensor(getattr(host_p, k)) and k != "y")
+    out_host = torch.empty(N_nodes, 2, K, dtype=torch.float32).pin_memory()
+
+    def e2e_call():
+        g = host_p.to(dev, non_blocking=True)
+        pred = rollout_test(model, g)
+        out_host.copy_(pred, non_blocking=True)
+        torch.cuda.synchronize()
+
+    e2e_call()                                          # warm (plan build for the new tensors)
+    barrier()
+    t0 = time.perf_counter()
+    e2e_call()
+    barrier()
+    e2e_s = time.perf_counter() - t0
+    if world > 1:
+        t = torch.tensor([e2e_s], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        e2e_s = float(t.item())
+    e2e_value = N_nodes * world * K / e2e_s
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    # ---- per-kernel timing of one eager step with CUDA events (roofline of the dominant kernel)
+    alg = algorithmic_bytes(nx, ny)
+    kern = profile_kernels(runner, alg)
+    pk = peaks()
+    dom = max(kern.values(), key=lambda r: r["ms_per_step"])
+    if dom["bound"] == "hbm":
+        roof = {"bound": "hbm", "kernel": dom["name"], "achieved": dom["gbs"], "peak": pk["hbm"], "unit": "GB/s",
+                "frac": dom["gbs"] / pk["hbm"], "traffic": None, "peak_source": pk["hbm_src"]}
+    else:
+        roof = {"bound": "tensor", "kernel": dom["name"], "achieved": dom["tflops"], "peak": pk["bf16"], "unit": "TFLOP/s",
+                "frac": dom["tflops"] / pk["bf16"], "traffic": None, "peak_source": pk["hbm_src"] + " (sustained bf16)"}
+    step_gbs = alg["total"] / (ms * 1e-3 / K) / 1e9
+
+    cpu = None
+    if world == 1 and not args.no_cpu_baseline:
+        r = cpu_reference_rate(2, 1)
+        cpu = {"value": r["value"], "unit": "node-steps/s", "cores": r["cores"], "kind": "port", "sample": r["sample"]}
+
+    line = {"metric": "mSWE-GNN rollout node-steps/sec", "value": value, "unit": "node-steps/s", "n_gpus": world,
+            "steps": K, "warmup": W, "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": f"{wl}: default config.yaml mSWE-GNN (K=4,F=64,mlp_layers=3,S=4) autoregressive rollout on "
+                                   f"tri({nx},{ny}) = {N_nodes} nodes per GPU; random-init weights seed 666; 30% wet nodes",
+                       "l2": f"working set {alg['total'] / 1e9:.1f} GB per step >> 126 MB L2 (inputs larger than L2, no flush needed)",
+                       "multi_gpu": "independent simulations per rank (replicas, no collective)" if world > 1 else "single GPU",
+                       "cuda_graph": True},
+            "clocks": clocks,
+            "e2e": {"value": e2e_value, "unit": "node-steps/s", "h2d_bytes_per_step": h2d // K, "d2h_bytes_per_step": N_nodes * 8,
+                    "what": "rollout_test(model, host_graph): pinned host graph -> device, plan build, K steps, predictions -> pinned host"},
+            "gpu_launches": per_step_launches * K,
+            "roofline": roof,
+            "hbm_fraction_whole_step": {"algorithmic_GB_per_step": alg["total"] / 1e9, "achieved_GBps": step_gbs,
+                                        "frac_of_peak": step_gbs / pk["hbm"], "peak_source": pk["hbm_src"]},
+            "kernels": sorted(kern.values(), key=lambda r: -r["ms_per_step"]),
+            "cpu_baseline": cpu}
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def profile_kernels(runner, alg):
+    """One eager (non-graph) step with a CUDA-event pair around every C-ABI launch, grouped by
+    kernel.  Events are recorded on torch's current stream, the stream the kernels launch on."""
+    from mswe_gnn_b200 import lib
+    records = []
+    orig = {}
+    names = ["node_encode_fwd", "edge_gate_fwd", "node_linear_fwd", "propagate_hop_fwd", "pool_mean_fwd",
+             "decode_head_fwd", "edge_encode_fwd", "apply_bc", "step_advance"]
+
+    def wrap(name):
+        fn = getattr(lib, name)
+        orig[name] = fn
+
+        def inner(*a, **k):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            r = fn(*a, **k)
+            e1.record()
+            meta = None
+            if name == "propagate_hop_fwd":
+                meta = ("hop", int(a[6]), a[7] is not None)          # n_dst, has filter
+            elif name == "edge_gate_fwd":
+                meta = ("gate", int(a[6]), a[3] is not None)         # n_edges, has edge features
+            records.append((name, e0, e1, meta))
+            return r
+        setattr(lib, name, inner)
+
+    for n in names:
+        wrap(n)
+    try:
+        reps = 3
+        for _ in range(reps):
+            runner._one_step()
+        torch.cuda.synchronize()
+    finally:
+        for n, fn in orig.items():
+            setattr(lib, n, fn)
+    out = {}
+    N, E = alg["N"], alg["E"]
+    for name, e0, e1, meta in records:
+        r = out.setdefault(name, dict(name="swe_" + name, ms_per_step=0.0, launches_per_step=0, bytes_per_step=0.0,
+                                      flops_per_step=0.0, bound="hbm"))
+        r["ms_per_step"] += e0.elapsed_time(e1) / reps
+        r["launches_per_step"] += 1.0 / reps
+        if meta and meta[0] == "hop" and meta[2]:
+            s = min(range(S), key=lambda i: abs(N[i] - meta[1]))
+            r["bytes_per_step"] += alg["hop"][s] / reps
+        if meta and meta[0] == "gate":
+            nseg = 5 if meta[2] else 3
+            r["flops_per_step"] += 2.0 * meta[1] * (nseg * F * 2 * F + 2 * F * 2 * F + 2 * F * F) / reps
+            r["bound"] = "tensor"
+    for r in out.values():
+        sec = r["ms_per_step"] * 1e-3
+        r["gbs"] = r["bytes_per_step"] / sec / 1e9 if sec > 0 else 0.0
+        r["tflops"] = r["flops_per_step"] / sec / 1e12 if sec > 0 else 0.0
+    tot = sum(r["ms_per_step"] for r in out.values())
+    for r in out.values():
+        r["share"] = r["ms_per_step"] / tot if tot else 0.0
+    return out
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default=None, choices=[None, *WORKLOADS])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -80,7 +80,13 @@ def load(path: Optional[str] = None):
     return lib
 
 
+launch_count = 0          # C-ABI calls issued so far (each is one kernel launch; csr_build is several)
+_launch_log = None        # when a list: (name, meta) of every call is appended (bench instrumentation)
+
+
 def _check(status: int, what: str):
+    global launch_count
+    launch_count += 1
     if status != 0:
         msg = load().swe_last_error().decode(errors="replace")
         raise RuntimeError(f"{what} failed (status {status}): {msg}")

@@ -96,8 +96,14 @@ class RolloutRunner:
             use_cuda_graph = os.environ.get("MSWE_CUDA_GRAPH", "1") != "0"
         self.use_cuda_graph = use_cuda_graph and self.T > 2
         self._graph = None
+        self.launches_per_step = 0
 
     def _one_step(self):
+        c0 = lib.launch_count
+        self._step_body()
+        self.launches_per_step = lib.launch_count - c0
+
+    def _step_body(self):
         m = self.model
         lib.apply_bc(self.x, self.n_static_raw, m.previous_t, self.type_BC, self.node_BC, self.bc, self.step)
         m._launch(self.plan, self.graph, self.x, self.preds, step_ptr=self.step,
