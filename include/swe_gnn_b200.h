@@ -127,6 +127,29 @@ int swe_edge_gate_fwd(const float* xs, const float* xd_src, const float* xd_dst,
                       const int32_t* src, const int32_t* dst, int64_t n_edges, const swe_mlp_t* mlp,
                       int32_t normalize, float* s_out, int32_t F, void* stream);
 
+/* ---------------------------------------------------------------------------------------------
+ * Edge gate on tcgen05 tensor cores (F = 64, 3-layer edge MLP 5F|4F -> 2F -> 2F -> F: the default
+ * config.yaml model).  Same contract and reference span as swe_edge_gate_fwd (models/gnn.py:414-426);
+ * products are 3xTF32 (error-free hi/lo splits, fp32 accumulation in TMEM), see DESIGN.md.
+ * ------------------------------------------------------------------------------------------- */
+
+/* Bytes of the packed weight image for a first layer with k1 input columns (256 or 320). */
+size_t swe_gate_tc_image_bytes(int32_t k1);
+
+/* Packs edge_mlp.{0,2,4}.{weight,bias} (torch Linear layout [n_out, k_in]) into the image the
+ * kernel streams: per 32-column K-chunk a hi tile and a lo tile in the UMMA K-major SWIZZLE_128B
+ * shared-memory layout, followed by the three bias vectors. */
+int swe_gate_tc_pack(const float* w1, int32_t k1, const float* b1, const float* w2, const float* b2,
+                     const float* w3, const float* b3, void* image, void* stream);
+
+/* act3: HOST array of 3 activation codes; slope3: HOST array of 3 DEVICE pointers to the PReLU
+ * parameters (NULL for other activations).  dbg: NULL, or a device buffer of 128*128*2 + 128*64
+ * floats receiving the raw accumulators of the first tile (tests only). */
+int swe_edge_gate_tc_fwd(const float* xs, const float* xd_src, const float* xd_dst, const float* a,
+                         const int32_t* src, const int32_t* dst, int64_t n_edges, const void* image,
+                         int32_t k1, const int32_t* act3, const float* const* slope3, int32_t normalize,
+                         float* s_out, float* dbg, void* stream);
+
 /* out[dst_lo + i] = x[dst_lo + i] · Wᵀ for i < n_rows.  Replaces models/gnn.py:401-402
  * (filter_matrix[0]).  wt is the packed (k-major) F×F weight. */
 int swe_node_linear_fwd(const float* x, int32_t row_lo, int32_t n_rows, const float* wt, float* out,

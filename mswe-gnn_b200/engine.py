@@ -160,6 +160,52 @@ class PackedFilters:
         return [self._buf[i] for i in range(len(self.linears))]
 
 
+class PackedGateTC:
+    """Weight image of a 3-layer edge MLP for the tcgen05 gate kernel (swe_gate_tc_pack)."""
+
+    def __init__(self, seq: nn.Sequential):
+        self.linears = [m for m in seq if isinstance(m, nn.Linear)]
+        self.acts = [m for m in seq if not isinstance(m, nn.Linear)]
+        self._stamp = None
+        self._img = None
+
+    @staticmethod
+    def eligible(seq: nn.Sequential, F: int) -> bool:
+        lins = [m for m in seq if isinstance(m, nn.Linear)]
+        acts = [m for m in seq if not isinstance(m, nn.Linear)]
+        if F != 64 or len(lins) != 3 or len(acts) != 3:
+            return False
+        shapes = [tuple(l.weight.shape) for l in lins]
+        return shapes[0][0] == 128 and shapes[0][1] in (256, 320) and shapes[1] == (128, 128) and shapes[2] == (64, 128)
+
+    def image(self):
+        stamp = tuple((p.data_ptr(), p._version) for l in self.linears for p in l.parameters())
+        if stamp != self._stamp:
+            l1, l2, l3 = self.linears
+            k1 = l1.weight.shape[1]
+            dev = l1.weight.device
+            n = lib.gate_tc_image_bytes(k1)
+            if self._img is None or self._img.numel() != n or self._img.device != dev:
+                self._img = torch.empty(n, dtype=torch.uint8, device=dev)
+            with torch.no_grad():
+                lib.gate_tc_pack(l1.weight.detach().contiguous(), None if l1.bias is None else l1.bias.detach(),
+                                 l2.weight.detach().contiguous(), None if l2.bias is None else l2.bias.detach(),
+                                 l3.weight.detach().contiguous(), None if l3.bias is None else l3.bias.detach(), self._img)
+            self._stamp = stamp
+        return self._img
+
+    def acts_and_slopes(self):
+        codes = [ACT_CODES[activation_name_of(a)] for a in self.acts]
+        slopes = [a.weight if isinstance(a, nn.PReLU) else None for a in self.acts]
+        return codes, slopes
+
+
+def gate_backend() -> str:
+    """'tc' (tcgen05 3xTF32, default where eligible) or 'ffma' (exact-fp32 CUDA cores)."""
+    import os
+    return os.environ.get("MSWE_GATE", "tc")
+
+
 class SweGnnLauncher:
     """Kernel sequence of one ``SWEGNN.forward`` call (reference models/gnn.py:387-445) on a
     destination-CSR edge set: gate once, W0, then K hops ping-ponging between two buffers."""
@@ -175,6 +221,18 @@ class SweGnnLauncher:
         two = {F: self.FP, 2 * F: 2 * self.FP}
         self.mlp = PackedMLP(module.edge_mlp, [(F, self.FP)] * nseg, two)
         self.filters = PackedFilters(list(module.filter_matrix), F, self.FP) if module.with_filter_matrix else None
+        self.tc = PackedGateTC(module.edge_mlp) if PackedGateTC.eligible(module.edge_mlp, F) else None
+
+    def gate(self, es, xs, xd_src, xd_dst, a, s_buf, dbg=None):
+        m = self.m
+        if self.tc is not None and gate_backend() == "tc":
+            codes, slopes = self.tc.acts_and_slopes()
+            k1 = self.tc.linears[0].weight.shape[1]
+            lib.edge_gate_tc_fwd(xs, xd_src, xd_dst, a, es.src, es.dst, es.n_edges, self.tc.image(), k1, codes, slopes,
+                                 m.normalize, s_buf, dbg)
+        else:
+            lib.edge_gate_fwd(xs, xd_src, xd_dst, a, es.src, es.dst, es.n_edges, self.mlp.struct(), m.normalize,
+                              s_buf, self.FP)
 
     def run(self, es: EdgeSet, xs, xd_src, xd_dst, a, s_buf, o_dst_rows_zero: bool, tmp_a, tmp_b, out,
             addend=None, act_code: int = 0, act_slope=None):
@@ -185,7 +243,7 @@ class SweGnnLauncher:
         """
         m, FP = self.m, self.FP
         E = es.n_edges
-        lib.edge_gate_fwd(xs, xd_src, xd_dst, a, es.src, es.dst, E, self.mlp.struct(), m.normalize, s_buf, FP)
+        self.gate(es, xs, xd_src, xd_dst, a, s_buf)
         K = m.K
         if m.with_filter_matrix:
             W = self.filters.tensors()

@@ -45,6 +45,10 @@ SIGNATURES = {
     "swe_node_encode_fwd": (C.c_int, [_p, _i32, _p, _i32, _i32, _i32, _i32, _mlp, _mlp, _p, _p, _i32, _p]),
     "swe_edge_encode_fwd": (C.c_int, [_p, _i32, _p, _i64, _mlp, _p, _i32, _p]),
     "swe_edge_gate_fwd": (C.c_int, [_p, _p, _p, _p, _p, _p, _i64, _mlp, _i32, _p, _i32, _p]),
+    "swe_gate_tc_image_bytes": (_sz, [_i32]),
+    "swe_gate_tc_pack": (C.c_int, [_p, _i32, _p, _p, _p, _p, _p, _p, _p]),
+    "swe_edge_gate_tc_fwd": (C.c_int, [_p, _p, _p, _p, _p, _p, _i64, _p, _i32, C.POINTER(C.c_int32),
+                                       C.POINTER(C.c_void_p), _i32, _p, _p, _p]),
     "swe_node_linear_fwd": (C.c_int, [_p, _i32, _i32, _p, _p, _i32, _p]),
     "swe_propagate_hop_fwd": (C.c_int, [_p, _p, _p, _p, _p, _i32, _i32, _p, _i32, _i32, _p, _i32, _p, _p, _i32, _p]),
     "swe_pool_mean_fwd": (C.c_int, [_p, _p, _p, _i32, _i32, _p, _i32, _p]),
@@ -155,6 +159,23 @@ def edge_gate_fwd(xs, xd_src, xd_dst, a, src, dst, n_edges, mlp: SweMlp, normali
     _check(load().swe_edge_gate_fwd(ptr(xs), ptr(xd_src), ptr(xd_dst), ptr(a), ptr(src, torch.int32),
                                     ptr(dst, torch.int32), n_edges, C.byref(mlp), int(normalize), ptr(s_out), F,
                                     _stream()), "swe_edge_gate_fwd")
+
+
+def gate_tc_image_bytes(k1: int) -> int:
+    return int(load().swe_gate_tc_image_bytes(k1))
+
+
+def gate_tc_pack(w1, b1, w2, b2, w3, b3, image):
+    _check(load().swe_gate_tc_pack(ptr(w1), w1.shape[1], ptr(b1), ptr(w2), ptr(b2), ptr(w3), ptr(b3),
+                                   image.data_ptr(), _stream()), "swe_gate_tc_pack")
+
+
+def edge_gate_tc_fwd(xs, xd_src, xd_dst, a, src, dst, n_edges, image, k1, acts, slopes, normalize, s_out, dbg=None):
+    act3 = (C.c_int32 * 3)(*acts)
+    slope3 = (C.c_void_p * 3)(*[None if s is None else ptr(s) for s in slopes])
+    _check(load().swe_edge_gate_tc_fwd(ptr(xs), ptr(xd_src), ptr(xd_dst), ptr(a), ptr(src, torch.int32),
+                                       ptr(dst, torch.int32), n_edges, image.data_ptr(), k1, act3, slope3,
+                                       int(normalize), ptr(s_out), ptr(dbg), _stream()), "swe_edge_gate_tc_fwd")
 
 
 def node_linear_fwd(x, row_lo, n_rows, wt, out, F):

@@ -1,0 +1,103 @@
+"""GPU: the tcgen05 (3xTF32) edge-gate kernel, stage by stage against fp64 and against the exact-fp32
+CUDA-core gate kernel.  Tolerance: every layer within rel 1e-5 (north_star) of the fp64 result."""
+import os
+
+import pytest
+import torch
+
+import mswe_gnn_b200  # noqa: F401
+from mswe_gnn_b200 import lib
+from mswe_gnn_b200.engine import PackedGateTC, PackedMLP
+from mswe_gnn_b200.models.models import make_mlp
+from mswe_gnn_b200.utils.synthetic import make_single_scale_mesh
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+
+
+def _setup(n_edge_feat, seed=0, nx=12, ny=9):
+    torch.manual_seed(seed)
+    d = make_single_scale_mesh(nx, ny, seed=seed)
+    n = d.x.shape[0]
+    row, col = d.edge_index.to(DEV)
+    rowptr, src, dst, eid = lib.csr_build(row, col, None, 0, n, 0, n)
+    E = int(src.numel())
+    xs = torch.randn(n, 64, device=DEV)
+    xd = torch.randn(n, 64, device=DEV) * (torch.rand(n, 1, device=DEV) < 0.6)
+    a = torch.randn(E, 64, device=DEV) if n_edge_feat else None
+    k1 = 256 + n_edge_feat
+    mlp = make_mlp(k1, 64, hidden_size=128, n_layers=3, bias=True, activation="prelu").to(DEV)
+    with torch.no_grad():
+        for m in mlp:
+            if isinstance(m, torch.nn.PReLU):
+                m.weight.fill_(0.1 + 0.2 * torch.rand(1).item())
+    return n, E, src, dst, xs, xd, a, mlp, k1
+
+
+@pytest.mark.parametrize("n_edge_feat,drop_dst", [(64, False), (0, False), (0, True)])
+def test_gate_tc_stagewise_vs_fp64(n_edge_feat, drop_dst):
+    n, E, src, dst, xs, xd, a, mlp, k1 = _setup(n_edge_feat)
+    tc = PackedGateTC(mlp)
+    assert PackedGateTC.eligible(mlp, 64)
+    codes, slopes = tc.acts_and_slopes()
+    s = torch.full((E, 64), float("nan"), device=DEV)
+    dbg = torch.zeros(128 * 128 * 2 + 128 * 64, device=DEV)
+    lib.edge_gate_tc_fwd(xs, xd, None if drop_dst else xd, a, src, dst, E, tc.image(), k1, codes, slopes, True, s, dbg)
+    torch.cuda.synchronize()
+    # fp64 reference of the first tile, stage by stage
+    sl, dl = src.long(), dst.long()
+    xdd = torch.zeros_like(xd) if drop_dst else xd
+    parts = [xs[sl], xs[dl], xd[sl], xdd[dl]] + ([a] if a is not None else [])
+    z = torch.cat(parts, 1).double()
+    lins = [m for m in mlp if isinstance(m, torch.nn.Linear)]
+    prl = [m for m in mlp if isinstance(m, torch.nn.PReLU)]
+    T = min(128, E)
+    pre1 = (z @ lins[0].weight.double().T).detach()
+    d1 = dbg[:128 * 128].view(128, 128)[:T].double()
+    err1 = float((d1 - pre1[:T]).abs().max() / pre1[:T].abs().max())
+    print('stage errors:', err1); assert err1 < 3e-6, f"layer-0 accumulators (SS path) off by {err1:.3e}"
+    h1 = torch.nn.functional.prelu(pre1 + lins[0].bias.double(), prl[0].weight.double()).detach()
+    pre2 = (h1 @ lins[1].weight.double().T).detach()
+    d2 = dbg[128 * 128:2 * 128 * 128].view(128, 128)[:T].double()
+    err2 = float((d2 - pre2[:T]).abs().max() / pre2[:T].abs().max())
+    print('stage2', err2); assert err2 < 4e-6, f"layer-1 accumulators (TS path) off by {err2:.3e}"
+    h2 = torch.nn.functional.prelu(pre2 + lins[1].bias.double(), prl[1].weight.double()).detach()
+    pre3 = (h2 @ lins[2].weight.double().T).detach()
+    d3 = dbg[2 * 128 * 128:].view(128, 64)[:T].double()
+    err3 = float((d3 - pre3[:T]).abs().max() / pre3[:T].abs().max())
+    print('stage3', err3); assert err3 < 6e-6, f"layer-2 accumulators (TS, N=64) off by {err3:.3e}"
+    u = torch.nn.functional.prelu(pre3 + lins[2].bias.double(), prl[2].weight.double()).detach()
+    ref = u / u.norm(dim=1, keepdim=True)
+    err = float((s.double() - ref).abs().max()); print('final', err)
+    assert err < 1e-5, f"normalised gate off by {err:.3e} (all tiles)"
+
+
+def test_gate_tc_matches_exact_fp32_kernel_on_many_tiles():
+    n, E, src, dst, xs, xd, a, mlp, k1 = _setup(64, seed=3, nx=60, ny=40)      # 14k edges -> 111 tiles
+    tc = PackedGateTC(mlp)
+    codes, slopes = tc.acts_and_slopes()
+    s_tc = torch.empty(E, 64, device=DEV)
+    s_ff = torch.empty(E, 64, device=DEV)
+    lib.edge_gate_tc_fwd(xs, xd, xd, a, src, dst, E, tc.image(), k1, codes, slopes, True, s_tc, None)
+    pk = PackedMLP(mlp, [(64, 64)] * 5, {})
+    lib.edge_gate_fwd(xs, xd, xd, a, src, dst, E, pk.struct(), True, s_ff, 64)
+    torch.cuda.synchronize()
+    assert bool(torch.isfinite(s_tc).all())
+    assert float((s_tc - s_ff).abs().max()) < 1e-5
+    # deterministic
+    s2 = torch.empty_like(s_tc)
+    lib.edge_gate_tc_fwd(xs, xd, xd, a, src, dst, E, tc.image(), k1, codes, slopes, True, s2, None)
+    assert torch.equal(s_tc, s2)
+
+
+def test_gate_tc_zero_rows_give_zero_gate_not_nan():
+    """An all-zero MLP output row normalises to 0/0 -> NaN -> 0 (gnn.py:425-426)."""
+    n, E, src, dst, xs, xd, a, mlp, k1 = _setup(0, seed=5)
+    with torch.no_grad():
+        lins = [m for m in mlp if isinstance(m, torch.nn.Linear)]
+        lins[2].weight.zero_(); lins[2].bias.zero_()
+    tc = PackedGateTC(mlp)
+    codes, slopes = tc.acts_and_slopes()
+    s = torch.full((E, 64), float("nan"), device=DEV)
+    lib.edge_gate_tc_fwd(xs, xd, xd, None, src, dst, E, tc.image(), k1, codes, slopes, True, s, None)
+    assert float(s.abs().max()) == 0.0

@@ -1,0 +1,37 @@
+"""Times the edge-gate kernels alone on a cfg3-sized finest level (3.04 M edges)."""
+import os, sys, time
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch
+import mswe_gnn_b200  # noqa
+from mswe_gnn_b200 import lib
+from mswe_gnn_b200.engine import PackedGateTC, PackedMLP
+from mswe_gnn_b200.models.models import make_mlp
+from mswe_gnn_b200.utils.synthetic import make_tri_mesh
+
+DEV = "cuda:0"
+nx = int(os.environ.get("NX", "712"))
+d = make_tri_mesh(nx, nx, 1)
+n = d.x.shape[0]
+row, col = d.edge_index.to(DEV)
+rowptr, src, dst, eid = lib.csr_build(row, col, None, 0, n, 0, n)
+E = int(src.numel())
+torch.manual_seed(0)
+xs = torch.randn(n, 64, device=DEV); xd = torch.randn(n, 64, device=DEV); a = torch.randn(E, 64, device=DEV)
+mlp = make_mlp(320, 64, hidden_size=128, n_layers=3, bias=True, activation="prelu").to(DEV)
+tc = PackedGateTC(mlp); codes, slopes = tc.acts_and_slopes(); img = tc.image()
+pk = PackedMLP(mlp, [(64, 64)] * 5, {}); st = pk.struct()
+s = torch.empty(E, 64, device=DEV)
+which = os.environ.get("WHICH", "tc,ffma").split(",")
+for name in which:
+    fn = (lambda: lib.edge_gate_tc_fwd(xs, xd, xd, a, src, dst, E, img, 320, codes, slopes, True, s, None)) if name == "tc" \
+        else (lambda: lib.edge_gate_fwd(xs, xd, xd, a, src, dst, E, st, True, s, 64))
+    for _ in range(2): fn()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    reps = int(os.environ.get("REPS", "5"))
+    for _ in range(reps): fn()
+    e1.record(); torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / reps
+    flops = 2.0 * E * (320 * 128 + 128 * 128 + 128 * 64)
+    print(f"{name}: E={E} {ms:.3f} ms  {flops / ms / 1e9:.1f} TFLOP/s (algorithmic)  {ms * 1e3 / ((E + 127) // 128 / 148):.2f} us/tile/SM")
