@@ -7,18 +7,18 @@
 //     A·W ≈ A_hi·W_hi + A_lo·W_hi + A_hi·W_lo          (dropped term |A_lo·W_lo| <= 2^-22 |A||W|)
 // accumulated in fp32 in TMEM — per-layer relative error ≈ 1e-6.
 //
-// One CTA = one 128-edge tile at a time (persistent over tiles), 192 threads:
-//   warps 0-3  row workers : gather the layer-0 input K-chunks (x_s[r], x_s[c], x_d[r], x_d[c], a_e),
+// One CTA works on 128-edge tiles (persistent, two tiles in flight), 320 threads:
+//   warps 0-7  row workers : gather the layer-0 input K-chunks (x_s[r], x_s[c], x_d[r], x_d[c], a_e),
 //                            split hi/lo, store them to shared memory in the UMMA K-major SWIZZLE_128B
 //                            layout; later the epilogues (one thread = one TMEM lane = one edge):
 //                            tcgen05.ld accumulators -> bias + PReLU -> split -> tcgen05.st as the next
 //                            layer's A operand (A stays in TMEM, never touches shared memory) and
 //                            finally L2-normalise + store s_ij.
-//   warp 4     weight loader: streams pre-packed weight chunk images (already swizzled, hi|lo) from
+//   warp 8     weight loader: streams pre-packed weight chunk images (already swizzled, hi|lo) from
 //                            global/L2 into a shared-memory ring with cp.async.bulk + mbarrier tx.
-//   warp 5     MMA issuer   : one thread issues tcgen05.mma (SS for layer 0, TS for layers 1-2) and
+//   warp 9     MMA issuer   : one thread issues tcgen05.mma (SS for layer 0, TS for layers 1-2) and
 //                            tcgen05.commit to release ring slots / publish accumulators.
-// TMEM (512 columns): [0,128) A_hi, [128,256) A_lo, [256,384) D_a (layer 0 / layer 2), [384,512) D_b.
+// TMEM (512 columns): [0,128) A_hi, [128,256) A_lo, [256,384) D_a (layer 0), [384,512) D_b (layers 1, 2).
 #include "swe_tc.cuh"
 
 namespace swe {
@@ -32,20 +32,19 @@ constexpr int TILE16K = TILE_ROWS * 128;  // bytes of a [128 x 32] tf32 tile
 constexpr int SLOT_BYTES = 2 * TILE16K;   // hi tile + lo tile
 constexpr int A_STAGES = 3;
 constexpr int W_STAGES = 3;
-constexpr int N_ROW_THREADS = 128;
-constexpr int N_THREADS = 192;
+constexpr int N_ROW_THREADS = 256;        // warps 0-7
+constexpr int N_THREADS = 320;            // + loader warp 8 + MMA warp 9
 constexpr uint32_t COL_A_HI = 0, COL_A_LO = 128, COL_D_A = 256, COL_D_B = 384;
 
 struct __align__(8) Barriers {
     uint64_t a_full[A_STAGES], a_empty[A_STAGES];
     uint64_t w_full[W_STAGES], w_empty[W_STAGES];
     uint64_t d_full[3];        // accumulators of layer 0/1/2 complete (tcgen05.commit)
-    uint64_t a_ready[2];       // next layer's A operand written to TMEM (128 arrivals)
-    uint64_t d_free;           // last accumulator drained, next tile may start (128 arrivals)
+    uint64_t a_ready[2];       // next layer's A operand written to TMEM (256 arrivals)
 };
 
 constexpr size_t GATE_TC_SMEM = 1024 /*align slack*/ + (size_t)(A_STAGES + W_STAGES) * SLOT_BYTES +
-                                sizeof(float) * 320 + sizeof(int32_t) * 2 * TILE_ROWS + sizeof(Barriers) + 16;
+                                sizeof(float) * 320 + sizeof(int32_t) * 4 * TILE_ROWS + sizeof(Barriers) + 16;
 
 // image layout of the packed weights (bytes)
 __host__ __device__ constexpr size_t img_l1_off(int chunk) { return (size_t)chunk * SLOT_BYTES; }
@@ -100,199 +99,255 @@ __device__ __forceinline__ int l1_chunk_segment(int i, bool has_xd_dst) {
     return sg < 3 ? sg : ((sg == 3 && has_xd_dst) ? 3 : 4);
 }
 
+// "leaky family" activations (none / relu / leakyrelu / prelu) are v > 0 ? v : slope * v
+template <bool GENERIC>
+__device__ __forceinline__ float gate_act(int act, float v, float slope) {
+    if (GENERIC) return act_apply(act, v, slope);
+    return fmaxf(v, 0.f) + slope * fminf(v, 0.f);
+}
+__device__ __forceinline__ float leaky_slope(int act, const float* slope_p) {
+    switch (act) {
+        case SWE_ACT_PRELU:     return slope_p ? __ldg(slope_p) : 0.25f;
+        case SWE_ACT_RELU:      return 0.f;
+        case SWE_ACT_LEAKYRELU: return 0.1f;
+        case SWE_ACT_NONE:      return 1.f;
+        default:                return (act == SWE_ACT_PRELU && slope_p) ? __ldg(slope_p) : 0.f;
+    }
+}
+
+// Tile schedule shared by the three roles (tiles t_0 .. t_{n-1} of this CTA, h = n_l1 / 2):
+//   L1(t_0) ;  for i: { L2(t_i) ; L1(t_{i+1})[0,h) ; L3(t_i) ; L1(t_{i+1})[h,n_l1) }
+// row workers:  G(t_0) ;  for i: { E1(t_i) ; G(t_{i+1})[0,h) ; E2(t_i) ; G(t_{i+1})[h,n_l1) ; E3(t_i) }
+// so the tensor pipe works on the next tile's layer 0 while the row workers run this tile's
+// epilogues, and on this tile's layers 1-2 while they gather the next tile's inputs.
+template <bool GENERIC>
 __global__ void __launch_bounds__(N_THREADS, 1) edge_gate_tc_kernel(const __grid_constant__ GateTcParams p) {
     extern __shared__ unsigned char smem_raw[];
     unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
     unsigned char* a_ring = smem;
     unsigned char* w_ring = smem + (size_t)A_STAGES * SLOT_BYTES;
     float* s_bias = reinterpret_cast<float*>(w_ring + (size_t)W_STAGES * SLOT_BYTES);
-    int32_t* s_src = reinterpret_cast<int32_t*>(s_bias + 320);
-    int32_t* s_dst = s_src + TILE_ROWS;
-    Barriers* bar = reinterpret_cast<Barriers*>(s_dst + TILE_ROWS);
+    int32_t* s_ids = reinterpret_cast<int32_t*>(s_bias + 320);            // [2 tiles][src 128 | dst 128]
+    Barriers* bar = reinterpret_cast<Barriers*>(s_ids + 4 * TILE_ROWS);
     uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(bar + 1);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const bool has_xd_dst = p.xd_dst != nullptr, has_a = p.a != nullptr;
     const int n_l1 = 2 * (3 + (has_xd_dst ? 1 : 0) + (has_a ? 1 : 0));      // active layer-0 chunks
-    const long long n_tiles = (p.n_edges + TILE_ROWS - 1) / TILE_ROWS;
+    const int h_l1 = n_l1 / 2;
+    const long long n_tiles_all = (p.n_edges + TILE_ROWS - 1) / TILE_ROWS;
+    const int n_my = (int)((n_tiles_all - blockIdx.x + gridDim.x - 1) / gridDim.x);   // tiles of this CTA
 
     if (threadIdx.x == 0) {
         for (int i = 0; i < A_STAGES; ++i) { mbar_init(&bar->a_full[i], N_ROW_THREADS); mbar_init(&bar->a_empty[i], 1); }
         for (int i = 0; i < W_STAGES; ++i) { mbar_init(&bar->w_full[i], 1); mbar_init(&bar->w_empty[i], 1); }
         for (int i = 0; i < 3; ++i) mbar_init(&bar->d_full[i], 1);
         for (int i = 0; i < 2; ++i) mbar_init(&bar->a_ready[i], N_ROW_THREADS);
-        mbar_init(&bar->d_free, N_ROW_THREADS);
         fence_barrier_init();
     }
     {
         const float* gb = reinterpret_cast<const float*>(p.img + img_bias_off(p.n_l1_img));
         for (int i = threadIdx.x; i < 320; i += N_THREADS) s_bias[i] = gb[i];
     }
-    if (warp == 4) tmem_alloc(tmem_holder, 512);
+    if (warp == 8) tmem_alloc(tmem_holder, 512);
     tc_fence_before_sync();
     __syncthreads();
     tc_fence_after_sync();
     const uint32_t tmem_base = *tmem_holder;
 
-    if (warp < 4) {
+    if (warp < 8) {
         // =====================================================================================
-        // row workers: producer of layer-0 A chunks, then epilogues
+        // row workers
         // =====================================================================================
-        const int row = threadIdx.x;                                  // TMEM lane / edge within the tile
-        const uint32_t lane_addr = tmem_base + ((uint32_t)(warp * 32) << 16);
-        const float sl0 = (p.act[0] == SWE_ACT_PRELU && p.slope[0]) ? __ldg(p.slope[0]) : 0.f;
-        const float sl1 = (p.act[1] == SWE_ACT_PRELU && p.slope[1]) ? __ldg(p.slope[1]) : 0.f;
-        const float sl2 = (p.act[2] == SWE_ACT_PRELU && p.slope[2]) ? __ldg(p.slope[2]) : 0.f;
-        uint32_t a_cnt = 0;                                           // A-ring uses so far
-        uint32_t it = 0;
-        for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
-            const long long e0 = tile * TILE_ROWS;
-            {   // edge endpoints of this tile (previous tile's gathers have all completed: they are
-                // synchronous register loads issued before the a_full arrivals)
-                long long e = e0 + row;
+        const int q = warp & 3, hf = warp >> 2;
+        const int row = q * 32 + lane;                                // TMEM lane / edge within the tile
+        const uint32_t lane_addr = tmem_base + ((uint32_t)(q * 32) << 16);
+        float sl[3];
+#pragma unroll
+        for (int l = 0; l < 3; ++l) sl[l] = GENERIC ? ((p.act[l] == SWE_ACT_PRELU && p.slope[l]) ? __ldg(p.slope[l]) : 0.f)
+                                                    : leaky_slope(p.act[l], p.slope[l]);
+        uint32_t a_cnt = 0;
+        const int piece = threadIdx.x & 7, r0 = threadIdx.x >> 3;     // gather: 4 rows r0 + 32 i, one 16-B piece
+        const uint32_t g_off0 = sw128_offset(r0, piece * 4);          // + i * 4096 for row r0 + 32 i
+
+        auto load_ids = [&](int i) {                                  // endpoints of tile t_i -> s_ids[i & 1]
+            const long long e0 = ((long long)blockIdx.x + (long long)i * gridDim.x) * TILE_ROWS;
+            int32_t* ids = s_ids + (i & 1) * 2 * TILE_ROWS;
+            if (threadIdx.x < TILE_ROWS) {
+                long long e = e0 + threadIdx.x;
                 if (e >= p.n_edges) e = p.n_edges - 1;
-                asm volatile("bar.sync 1, 128;" ::: "memory");        // everyone done reading old ids
-                s_src[row] = __ldg(p.src + e);
-                s_dst[row] = __ldg(p.dst + e);
-                asm volatile("bar.sync 1, 128;" ::: "memory");
+                ids[threadIdx.x] = __ldg(p.src + e);
+            } else {
+                long long e = e0 + threadIdx.x - TILE_ROWS;
+                if (e >= p.n_edges) e = p.n_edges - 1;
+                ids[threadIdx.x] = __ldg(p.dst + e);                  // ids[128 + r]
             }
-            // ---------------- layer-0 input chunks
-            const int piece = row & 7, r0 = row >> 3;
-            for (int c = 0; c < n_l1; ++c, ++a_cnt) {
+            asm volatile("bar.sync 1, 256;" ::: "memory");
+        };
+        auto gather = [&](int i, int c_lo, int c_hi) {                // layer-0 input chunks [c_lo, c_hi) of tile t_i
+            const long long e0 = ((long long)blockIdx.x + (long long)i * gridDim.x) * TILE_ROWS;
+            const int32_t* ids = s_ids + (i & 1) * 2 * TILE_ROWS;
+#pragma unroll 1
+            for (int c = c_lo; c < c_hi; ++c, ++a_cnt) {
                 const int sg = l1_chunk_segment(c, has_xd_dst);
                 const int koff = (c & 1) * KC + piece * 4;
-                float4 v[8];
+                float4 v[4];
+                if (sg == 4) {
 #pragma unroll
-                for (int i = 0; i < 8; ++i) {
-                    const int r = r0 + 16 * i;
-                    const float* srcp;
-                    if (sg == 4) {
-                        long long e = e0 + r;
+                    for (int j = 0; j < 4; ++j) {
+                        long long e = e0 + r0 + 32 * j;
                         if (e >= p.n_edges) e = p.n_edges - 1;
-                        srcp = p.a + e * GF;
-                    } else {
-                        const long long node = (sg & 1) ? s_dst[r] : s_src[r];
-                        srcp = (sg < 2 ? p.xs : (sg == 2 ? p.xd_src : p.xd_dst)) + node * GF;
+                        v[j] = ldg4_stream(p.a + e * GF + koff);
                     }
-                    v[i] = (sg == 4) ? ldg4_stream(srcp + koff) : ldg4(srcp + koff);
+                } else {
+                    const float* base = sg < 2 ? p.xs : (sg == 2 ? p.xd_src : p.xd_dst);
+                    const int32_t* idp = ids + ((sg & 1) ? TILE_ROWS : 0) + r0;
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) v[j] = ldg4(base + (long long)idp[32 * j] * GF + koff);
                 }
                 const uint32_t slot = a_cnt % A_STAGES;
                 mbar_wait(&bar->a_empty[slot], ((a_cnt / A_STAGES) & 1) ^ 1);
-                unsigned char* hi_t = a_ring + (size_t)slot * SLOT_BYTES;
-                unsigned char* lo_t = hi_t + TILE16K;
+                unsigned char* hi_t = a_ring + (size_t)slot * SLOT_BYTES + g_off0;
 #pragma unroll
-                for (int i = 0; i < 8; ++i) {
-                    const int r = r0 + 16 * i;
-                    float4 h, l;
-                    split_tf32(v[i].x, h.x, l.x); split_tf32(v[i].y, h.y, l.y);
-                    split_tf32(v[i].z, h.z, l.z); split_tf32(v[i].w, h.w, l.w);
-                    const uint32_t off = sw128_offset(r, piece * 4);
-                    *reinterpret_cast<float4*>(hi_t + off) = h;
-                    *reinterpret_cast<float4*>(lo_t + off) = l;
+                for (int j = 0; j < 4; ++j) {
+                    float4 hh, ll;
+                    split_tf32(v[j].x, hh.x, ll.x); split_tf32(v[j].y, hh.y, ll.y);
+                    split_tf32(v[j].z, hh.z, ll.z); split_tf32(v[j].w, hh.w, ll.w);
+                    *reinterpret_cast<float4*>(hi_t + j * 4096) = hh;
+                    *reinterpret_cast<float4*>(hi_t + TILE16K + j * 4096) = ll;
                 }
                 fence_proxy_async_smem();
                 mbar_arrive(&bar->a_full[slot]);
             }
-            const uint32_t ph = it & 1;
-            // ---------------- epilogue of layer 0 and 1: D -> bias, activation -> hi/lo -> TMEM A operand
-#pragma unroll 1
-            for (int layer = 0; layer < 2; ++layer) {
-                mbar_wait(&bar->d_full[layer], ph);
-                tc_fence_after_sync();
-                const uint32_t dcol = layer == 0 ? COL_D_A : COL_D_B;
-                const float* bias = s_bias + layer * 128;
-                const int act = p.act[layer];
-                const float sl = layer == 0 ? sl0 : sl1;
-#pragma unroll 1
-                for (int cb = 0; cb < 4; ++cb) {
-                    uint32_t v[32], hi[32], lo[32];
-                    tmem_ld32(lane_addr + dcol + cb * 32, v);
-                    tmem_wait_ld();
-                    if (p.dbg && tile == 0) {
-                        float* d = p.dbg + (size_t)layer * 128 * 128 + (size_t)row * 128 + cb * 32;
+        };
+        // D -> bias, activation -> hi/lo -> TMEM A operand; this thread owns 64 columns of its lane
+        auto epilogue_mid = [&](int layer, uint32_t ph, bool dump) {
+            mbar_wait(&bar->d_full[layer], ph);
+            tc_fence_after_sync();
+            const uint32_t dcol = (layer == 0 ? COL_D_A : COL_D_B) + hf * 64;
+            const float* bias = s_bias + layer * 128 + hf * 64;
+            const int act = p.act[layer];
+            const float slope = sl[layer];
 #pragma unroll
-                        for (int j = 0; j < 32; ++j) d[j] = __uint_as_float(v[j]);
-                    }
-#pragma unroll
-                    for (int j = 0; j < 32; ++j) {
-                        const float y = act_apply(act, __uint_as_float(v[j]) + bias[cb * 32 + j], sl);
-                        float h, l;
-                        split_tf32(y, h, l);
-                        hi[j] = __float_as_uint(h);
-                        lo[j] = __float_as_uint(l);
-                    }
-                    tmem_st32(lane_addr + COL_A_HI + cb * 32, hi);
-                    tmem_st32(lane_addr + COL_A_LO + cb * 32, lo);
-                }
-                tmem_wait_st();
-                tc_fence_before_sync();
-                mbar_arrive(&bar->a_ready[layer]);
-            }
-            // ---------------- final epilogue: bias, activation, L2 normalise, store s_ij
-            {
-                mbar_wait(&bar->d_full[2], ph);
-                tc_fence_after_sync();
-                uint32_t v0[32], v1[32];
-                tmem_ld32(lane_addr + COL_D_A, v0);
-                tmem_ld32(lane_addr + COL_D_A + 32, v1);
+            for (int cb = 0; cb < 2; ++cb) {
+                uint32_t v[32];
+                tmem_ld32(lane_addr + dcol + cb * 32, v);
                 tmem_wait_ld();
-                tc_fence_before_sync();
-                mbar_arrive(&bar->d_free);                            // accumulator drained
-                if (p.dbg && tile == 0) {
-                    float* d = p.dbg + (size_t)2 * 128 * 128 + (size_t)row * 64;
+                if (dump) {
+                    float* d = p.dbg + (size_t)layer * 128 * 128 + (size_t)row * 128 + hf * 64 + cb * 32;
 #pragma unroll
-                    for (int j = 0; j < 32; ++j) { d[j] = __uint_as_float(v0[j]); d[32 + j] = __uint_as_float(v1[j]); }
+                    for (int j = 0; j < 32; ++j) d[j] = __uint_as_float(v[j]);
                 }
-                const float* bias = s_bias + 256;
-                float y[64];
-                float ss = 0.f;
+                uint32_t lo[32];
 #pragma unroll
-                for (int j = 0; j < 32; ++j) {
-                    y[j] = act_apply(p.act[2], __uint_as_float(v0[j]) + bias[j], sl2);
-                    y[32 + j] = act_apply(p.act[2], __uint_as_float(v1[j]) + bias[32 + j], sl2);
-                }
-                if (p.normalize) {
+                for (int j = 0; j < 32; j += 4) {
+                    const float4 b4 = *reinterpret_cast<const float4*>(bias + cb * 32 + j);
+                    const float bb[4] = {b4.x, b4.y, b4.z, b4.w};
 #pragma unroll
-                    for (int j = 0; j < 64; ++j) ss = fmaf(y[j], y[j], ss);
-                    const float nrm = sqrtf(ss);
-#pragma unroll
-                    for (int j = 0; j < 64; ++j) {
-                        const float q = __fdiv_rn(y[j], nrm);         // s / ||s||   (gnn.py:425)
-                        y[j] = (q != q) ? 0.f : q;                    // NaN -> 0    (gnn.py:426)
+                    for (int u = 0; u < 4; ++u) {
+                        const float y = gate_act<GENERIC>(act, __uint_as_float(v[j + u]) + bb[u], slope);
+                        const float hh = round_tf32(y);
+                        v[j + u] = __float_as_uint(hh);
+                        lo[j + u] = __float_as_uint(round_tf32(y - hh));
                     }
                 }
-                const long long e = e0 + row;
-                if (e < p.n_edges) {
-                    float* o = p.s_out + e * GF;
+                tmem_st32(lane_addr + COL_A_HI + hf * 64 + cb * 32, v);
+                tmem_st32(lane_addr + COL_A_LO + hf * 64 + cb * 32, lo);
+            }
+            tmem_wait_st();
+            tc_fence_before_sync();
+            mbar_arrive(&bar->a_ready[layer]);
+        };
+        auto epilogue_final = [&](int i, uint32_t ph, bool dump) {    // warps 0-3: 64 columns each
+            if (hf != 0) return;
+            mbar_wait(&bar->d_full[2], ph);
+            tc_fence_after_sync();
+            uint32_t v0[32], v1[32];
+            tmem_ld32(lane_addr + COL_D_B, v0);
+            tmem_ld32(lane_addr + COL_D_B + 32, v1);
+            tmem_wait_ld();
+            tc_fence_before_sync();
+            if (dump) {
+                float* d = p.dbg + (size_t)2 * 128 * 128 + (size_t)row * 64;
 #pragma unroll
-                    for (int j = 0; j < 64; j += 4) stg4(o + j, make_float4(y[j], y[j + 1], y[j + 2], y[j + 3]));
+                for (int j = 0; j < 32; ++j) { d[j] = __uint_as_float(v0[j]); d[32 + j] = __uint_as_float(v1[j]); }
+            }
+            const float* bias = s_bias + 256;
+            float ss = 0.f;
+#pragma unroll
+            for (int j = 0; j < 32; j += 4) {
+                const float4 b0 = *reinterpret_cast<const float4*>(bias + j), b1 = *reinterpret_cast<const float4*>(bias + 32 + j);
+                const float bb0[4] = {b0.x, b0.y, b0.z, b0.w}, bb1[4] = {b1.x, b1.y, b1.z, b1.w};
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    const float y0 = gate_act<GENERIC>(p.act[2], __uint_as_float(v0[j + u]) + bb0[u], sl[2]);
+                    const float y1 = gate_act<GENERIC>(p.act[2], __uint_as_float(v1[j + u]) + bb1[u], sl[2]);
+                    ss = fmaf(y0, y0, ss); ss = fmaf(y1, y1, ss);
+                    v0[j + u] = __float_as_uint(y0); v1[j + u] = __float_as_uint(y1);
                 }
             }
+            float inv = 1.f;
+            if (p.normalize) inv = 1.f / sqrtf(ss);                   // ss == 0 -> inf -> 0*inf = NaN -> 0 below
+            const long long e = ((long long)blockIdx.x + (long long)i * gridDim.x) * TILE_ROWS + row;
+            if (e < p.n_edges) {
+                float* o = p.s_out + e * GF;
+#pragma unroll
+                for (int j = 0; j < 32; j += 4) {
+                    float4 r;
+                    r.x = __uint_as_float(v0[j]) * inv; r.y = __uint_as_float(v0[j + 1]) * inv;
+                    r.z = __uint_as_float(v0[j + 2]) * inv; r.w = __uint_as_float(v0[j + 3]) * inv;
+                    r.x = (r.x != r.x) ? 0.f : r.x; r.y = (r.y != r.y) ? 0.f : r.y;      // NaN -> 0 (gnn.py:426)
+                    r.z = (r.z != r.z) ? 0.f : r.z; r.w = (r.w != r.w) ? 0.f : r.w;
+                    stg4(o + j, r);
+                }
+#pragma unroll
+                for (int j = 0; j < 32; j += 4) {
+                    float4 r;
+                    r.x = __uint_as_float(v1[j]) * inv; r.y = __uint_as_float(v1[j + 1]) * inv;
+                    r.z = __uint_as_float(v1[j + 2]) * inv; r.w = __uint_as_float(v1[j + 3]) * inv;
+                    r.x = (r.x != r.x) ? 0.f : r.x; r.y = (r.y != r.y) ? 0.f : r.y;
+                    r.z = (r.z != r.z) ? 0.f : r.z; r.w = (r.w != r.w) ? 0.f : r.w;
+                    stg4(o + 32 + j, r);
+                }
+            }
+        };
+
+        if (n_my > 0) { load_ids(0); gather(0, 0, n_l1); }
+#pragma unroll 1
+        for (int i = 0; i < n_my; ++i) {
+            const uint32_t ph = i & 1;
+            const bool dump = p.dbg != nullptr && i == 0 && blockIdx.x == 0;
+            const bool more = i + 1 < n_my;
+            epilogue_mid(0, ph, dump);
+            if (more) { load_ids(i + 1); gather(i + 1, 0, h_l1); }
+            epilogue_mid(1, ph, dump);
+            if (more) gather(i + 1, h_l1, n_l1);
+            epilogue_final(i, ph, dump);
         }
-    } else if (warp == 4) {
+    } else if (warp == 8) {
         // =====================================================================================
-        // weight loader
+        // weight loader (same chunk order as the MMA issuer)
         // =====================================================================================
         if (lane == 0) {
             uint32_t w_cnt = 0;
-            for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-                for (int c = 0; c < n_l1 + 8; ++c, ++w_cnt) {
-                    const unsigned char* srcp;
-                    uint32_t bytes = SLOT_BYTES;
-                    if (c < n_l1) {
-                        const int sg = l1_chunk_segment(c, has_xd_dst);
-                        srcp = p.img + img_l1_off(2 * sg + (c & 1));
-                    } else if (c < n_l1 + 4) {
-                        srcp = p.img + img_l2_off(p.n_l1_img, c - n_l1);
-                    } else {
-                        srcp = p.img + img_l3_off(p.n_l1_img, c - n_l1 - 4);
-                        bytes = SLOT_BYTES / 2;
-                    }
-                    const uint32_t slot = w_cnt % W_STAGES;
-                    mbar_wait(&bar->w_empty[slot], ((w_cnt / W_STAGES) & 1) ^ 1);
-                    mbar_arrive_expect_tx(&bar->w_full[slot], bytes);
-                    bulk_g2s(w_ring + (size_t)slot * SLOT_BYTES, srcp, bytes, &bar->w_full[slot]);
-                }
+            auto load = [&](const unsigned char* srcp, uint32_t bytes) {
+                const uint32_t slot = w_cnt % W_STAGES;
+                mbar_wait(&bar->w_empty[slot], ((w_cnt / W_STAGES) & 1) ^ 1);
+                mbar_arrive_expect_tx(&bar->w_full[slot], bytes);
+                bulk_g2s(w_ring + (size_t)slot * SLOT_BYTES, srcp, bytes, &bar->w_full[slot]);
+                ++w_cnt;
+            };
+            auto load_l1 = [&](int c_lo, int c_hi) {
+                for (int c = c_lo; c < c_hi; ++c)
+                    load(p.img + img_l1_off(2 * l1_chunk_segment(c, has_xd_dst) + (c & 1)), SLOT_BYTES);
+            };
+            if (n_my > 0) load_l1(0, n_l1);
+            for (int i = 0; i < n_my; ++i) {
+                const bool more = i + 1 < n_my;
+                for (int c = 0; c < 4; ++c) load(p.img + img_l2_off(p.n_l1_img, c), SLOT_BYTES);
+                if (more) load_l1(0, h_l1);
+                for (int c = 0; c < 4; ++c) load(p.img + img_l3_off(p.n_l1_img, c), SLOT_BYTES / 2);
+                if (more) load_l1(h_l1, n_l1);
             }
         }
     } else {
@@ -302,12 +357,10 @@ __global__ void __launch_bounds__(N_THREADS, 1) edge_gate_tc_kernel(const __grid
         if (lane == 0) {
             const uint32_t idesc128 = make_idesc_tf32(128, 128), idesc64 = make_idesc_tf32(128, 64);
             const uint32_t a_ring_u32 = smem_u32(a_ring), w_ring_u32 = smem_u32(w_ring);
-            uint32_t a_cnt = 0, w_cnt = 0, it = 0;
-            for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
-                const uint32_t ph = it & 1;
-                if (it > 0) { mbar_wait(&bar->d_free, (it - 1) & 1); tc_fence_after_sync(); }
-                // ---------------- layer 0 (SS): D_a = Σ_chunks A_chunk · W_chunkᵀ
-                for (int c = 0; c < n_l1; ++c, ++a_cnt, ++w_cnt) {
+            uint32_t a_cnt = 0, w_cnt = 0;
+            // layer 0 (SS): D_a (+)= A_chunk · W_chunkᵀ for chunks [c_lo, c_hi)
+            auto mma_l1 = [&](int c_lo, int c_hi, bool last) {
+                for (int c = c_lo; c < c_hi; ++c, ++a_cnt, ++w_cnt) {
                     const uint32_t sa = a_cnt % A_STAGES, sw = w_cnt % W_STAGES;
                     mbar_wait(&bar->a_full[sa], (a_cnt / A_STAGES) & 1);
                     mbar_wait(&bar->w_full[sw], (w_cnt / W_STAGES) & 1);
@@ -325,38 +378,45 @@ __global__ void __launch_bounds__(N_THREADS, 1) edge_gate_tc_kernel(const __grid
                     mma_commit(&bar->a_empty[sa]);
                     mma_commit(&bar->w_empty[sw]);
                 }
-                mma_commit(&bar->d_full[0]);
-                // ---------------- layers 1 and 2 (TS): A from TMEM
-#pragma unroll 1
-                for (int layer = 1; layer < 3; ++layer) {
-                    mbar_wait(&bar->a_ready[layer - 1], ph);
+                if (last) mma_commit(&bar->d_full[0]);
+            };
+            // layers 1 / 2 (TS): A from TMEM, D_b (layer 1: 128 columns, layer 2: 64 columns)
+            auto mma_ts = [&](int layer, uint32_t ph) {
+                mbar_wait(&bar->a_ready[layer - 1], ph);
+                tc_fence_after_sync();
+                const uint32_t idesc = layer == 1 ? idesc128 : idesc64;
+                const uint32_t lo_off = layer == 1 ? TILE16K : TILE16K / 2;           // lo tile follows hi tile
+                for (int c = 0; c < 4; ++c, ++w_cnt) {
+                    const uint32_t sw = w_cnt % W_STAGES;
+                    mbar_wait(&bar->w_full[sw], (w_cnt / W_STAGES) & 1);
                     tc_fence_after_sync();
-                    const uint32_t dcol = layer == 1 ? COL_D_B : COL_D_A;
-                    const uint32_t idesc = layer == 1 ? idesc128 : idesc64;
-                    const uint32_t lo_off = layer == 1 ? TILE16K : TILE16K / 2;       // lo tile follows hi tile
-                    for (int c = 0; c < 4; ++c, ++w_cnt) {
-                        const uint32_t sw = w_cnt % W_STAGES;
-                        mbar_wait(&bar->w_full[sw], (w_cnt / W_STAGES) & 1);
-                        tc_fence_after_sync();
-                        const uint32_t w_hi = w_ring_u32 + sw * SLOT_BYTES, w_lo = w_hi + lo_off;
+                    const uint32_t w_hi = w_ring_u32 + sw * SLOT_BYTES, w_lo = w_hi + lo_off;
 #pragma unroll
-                        for (int ks = 0; ks < KC / 8; ++ks) {
-                            const uint32_t kcol = c * KC + ks * 8;
-                            const uint64_t dwh = make_desc_sw128(w_hi + ks * 32), dwl = make_desc_sw128(w_lo + ks * 32);
-                            mma_tf32_ts(tmem_base + dcol, tmem_base + COL_A_LO + kcol, dwh, idesc, (c | ks) ? 1u : 0u);
-                            mma_tf32_ts(tmem_base + dcol, tmem_base + COL_A_HI + kcol, dwl, idesc, 1u);
-                            mma_tf32_ts(tmem_base + dcol, tmem_base + COL_A_HI + kcol, dwh, idesc, 1u);
-                        }
-                        mma_commit(&bar->w_empty[sw]);
+                    for (int ks = 0; ks < KC / 8; ++ks) {
+                        const uint32_t kcol = c * KC + ks * 8;
+                        const uint64_t dwh = make_desc_sw128(w_hi + ks * 32), dwl = make_desc_sw128(w_lo + ks * 32);
+                        mma_tf32_ts(tmem_base + COL_D_B, tmem_base + COL_A_LO + kcol, dwh, idesc, (c | ks) ? 1u : 0u);
+                        mma_tf32_ts(tmem_base + COL_D_B, tmem_base + COL_A_HI + kcol, dwl, idesc, 1u);
+                        mma_tf32_ts(tmem_base + COL_D_B, tmem_base + COL_A_HI + kcol, dwh, idesc, 1u);
                     }
-                    mma_commit(&bar->d_full[layer]);
+                    mma_commit(&bar->w_empty[sw]);
                 }
+                mma_commit(&bar->d_full[layer]);
+            };
+            if (n_my > 0) mma_l1(0, n_l1, true);
+            for (int i = 0; i < n_my; ++i) {
+                const uint32_t ph = i & 1;
+                const bool more = i + 1 < n_my;
+                mma_ts(1, ph);
+                if (more) mma_l1(0, h_l1, false);
+                mma_ts(2, ph);
+                if (more) mma_l1(h_l1, n_l1, true);
             }
         }
     }
     tc_fence_before_sync();
     __syncthreads();
-    if (warp == 4) tmem_dealloc(tmem_base, 512);
+    if (warp == 8) tmem_dealloc(tmem_base, 512);
 }
 
 }  // namespace tc
@@ -390,14 +450,13 @@ extern "C" int swe_edge_gate_tc_fwd(const float* xs, const float* xd_src, const 
     p.img = (const unsigned char*)image; p.n_l1_img = k1 / tc::KC;
     for (int i = 0; i < 3; ++i) { p.act[i] = act3[i]; p.slope[i] = slope3[i]; }
     p.normalize = normalize; p.s_out = s_out; p.dbg = dbg;
-    static bool attr_done = false;
-    if (!attr_done) {
-        cudaError_t e = cudaFuncSetAttribute(tc::edge_gate_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                             (int)tc::GATE_TC_SMEM);
-        if (e != cudaSuccess) { set_error("edge_gate_tc smem opt-in (%zu B): %s", tc::GATE_TC_SMEM, cudaGetErrorString(e)); return (int)e; }
-        attr_done = true;
-    }
+    bool generic = false;
+    for (int i = 0; i < 3; ++i)
+        generic |= !(act3[i] == SWE_ACT_NONE || act3[i] == SWE_ACT_PRELU || act3[i] == SWE_ACT_RELU || act3[i] == SWE_ACT_LEAKYRELU);
+    auto kern = generic ? tc::edge_gate_tc_kernel<true> : tc::edge_gate_tc_kernel<false>;
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc::GATE_TC_SMEM);
+    if (e != cudaSuccess) { set_error("edge_gate_tc smem opt-in (%zu B): %s", tc::GATE_TC_SMEM, cudaGetErrorString(e)); return (int)e; }
     const long long n_tiles = (n_edges + tc::TILE_ROWS - 1) / tc::TILE_ROWS;
-    tc::edge_gate_tc_kernel<<<grid_for(n_tiles, 1), tc::N_THREADS, tc::GATE_TC_SMEM, (cudaStream_t)stream>>>(p);
+    kern<<<grid_for(n_tiles, 1), tc::N_THREADS, tc::GATE_TC_SMEM, (cudaStream_t)stream>>>(p);
     return check_launch("edge_gate_tc_fwd");
 }

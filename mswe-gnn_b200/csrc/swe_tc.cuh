@@ -149,7 +149,7 @@ __device__ __forceinline__ float round_tf32(float x) {
 __host__ __device__ __forceinline__ void split_tf32(float x, float& hi, float& lo) {
 #ifdef __CUDA_ARCH__
     hi = round_tf32(x);
-    lo = (fabsf(x) <= 3.402823466e38f) ? round_tf32(x - hi) : 0.f;      // inf/nan stay in hi only
+    lo = round_tf32(x - hi);
 #else
     hi = x; lo = 0.f;
 #endif
