@@ -281,7 +281,7 @@ def profile_kernels(runner, alg):
     from mswe_gnn_b200 import lib
     records = []
     orig = {}
-    names = ["node_encode_fwd", "edge_gate_fwd", "node_linear_fwd", "propagate_hop_fwd", "pool_mean_fwd",
+    names = ["node_encode_fwd", "edge_gate_fwd", "edge_gate_tc_fwd", "node_linear_fwd", "propagate_hop_fwd", "pool_mean_fwd",
              "decode_head_fwd", "edge_encode_fwd", "apply_bc", "step_advance"]
 
     def wrap(name):
@@ -296,7 +296,7 @@ def profile_kernels(runner, alg):
             meta = None
             if name == "propagate_hop_fwd":
                 meta = ("hop", int(a[6]), a[7] is not None)          # n_dst, has filter
-            elif name == "edge_gate_fwd":
+            elif name in ("edge_gate_fwd", "edge_gate_tc_fwd"):
                 meta = ("gate", int(a[6]), a[3] is not None)         # n_edges, has edge features
             records.append((name, e0, e1, meta))
             return r
@@ -323,7 +323,7 @@ def profile_kernels(runner, alg):
             s = min(range(S), key=lambda i: abs(N[i] - meta[1]))
             r["bytes_per_step"] += alg["hop"][s] / reps
         if meta and meta[0] == "gate":
-            nseg = 5 if meta[2] else 3
+            nseg = (5 if meta[2] else 3)
             r["flops_per_step"] += 2.0 * meta[1] * (nseg * F * 2 * F + 2 * F * 2 * F + 2 * F * F) / reps
             r["bound"] = "tensor"
     for r in out.values():

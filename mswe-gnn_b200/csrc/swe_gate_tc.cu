@@ -30,8 +30,8 @@ constexpr int KC = 32;                    // K elements per chunk = one 128-byte
 constexpr int TILE_ROWS = 128;
 constexpr int TILE16K = TILE_ROWS * 128;  // bytes of a [128 x 32] tf32 tile
 constexpr int SLOT_BYTES = 2 * TILE16K;   // hi tile + lo tile
-constexpr int A_STAGES = 3;
-constexpr int W_STAGES = 3;
+constexpr int A_STAGES = 2;
+constexpr int W_STAGES = 4;
 constexpr int N_ROW_THREADS = 256;        // warps 0-7
 constexpr int N_THREADS = 320;            // + loader warp 8 + MMA warp 9
 constexpr uint32_t COL_A_HI = 0, COL_A_LO = 128, COL_D_A = 256, COL_D_B = 384;
@@ -91,6 +91,7 @@ struct GateTcParams {
     int normalize;
     float* s_out;
     float* dbg;                 // optional [128*128 + 128*128 + 128*64] raw accumulators of tile 0
+    long long* trace;           // optional [3 roles][16 tiles][8 events] clock64 stamps of CTA 0 (profiling aid)
 };
 
 __device__ __forceinline__ int l1_chunk_segment(int i, bool has_xd_dst) {
@@ -187,11 +188,9 @@ __global__ void __launch_bounds__(N_THREADS, 1) edge_gate_tc_kernel(const __grid
         auto gather = [&](int i, int c_lo, int c_hi) {                // layer-0 input chunks [c_lo, c_hi) of tile t_i
             const long long e0 = ((long long)blockIdx.x + (long long)i * gridDim.x) * TILE_ROWS;
             const int32_t* ids = s_ids + (i & 1) * 2 * TILE_ROWS;
-#pragma unroll 1
-            for (int c = c_lo; c < c_hi; ++c, ++a_cnt) {
+            auto issue = [&](int c, float4 (&v)[4]) {                 // 4 independent 16-B loads per thread
                 const int sg = l1_chunk_segment(c, has_xd_dst);
                 const int koff = (c & 1) * KC + piece * 4;
-                float4 v[4];
                 if (sg == 4) {
 #pragma unroll
                     for (int j = 0; j < 4; ++j) {
@@ -205,19 +204,27 @@ __global__ void __launch_bounds__(N_THREADS, 1) edge_gate_tc_kernel(const __grid
 #pragma unroll
                     for (int j = 0; j < 4; ++j) v[j] = ldg4(base + (long long)idp[32 * j] * GF + koff);
                 }
+            };
+            float4 cur[4], nxt[4];
+            issue(c_lo, cur);
+#pragma unroll 1
+            for (int c = c_lo; c < c_hi; ++c, ++a_cnt) {
+                if (c + 1 < c_hi) issue(c + 1, nxt);                  // next chunk's loads fly while this one is packed
                 const uint32_t slot = a_cnt % A_STAGES;
                 mbar_wait(&bar->a_empty[slot], ((a_cnt / A_STAGES) & 1) ^ 1);
                 unsigned char* hi_t = a_ring + (size_t)slot * SLOT_BYTES + g_off0;
 #pragma unroll
                 for (int j = 0; j < 4; ++j) {
                     float4 hh, ll;
-                    split_tf32(v[j].x, hh.x, ll.x); split_tf32(v[j].y, hh.y, ll.y);
-                    split_tf32(v[j].z, hh.z, ll.z); split_tf32(v[j].w, hh.w, ll.w);
+                    split_tf32(cur[j].x, hh.x, ll.x); split_tf32(cur[j].y, hh.y, ll.y);
+                    split_tf32(cur[j].z, hh.z, ll.z); split_tf32(cur[j].w, hh.w, ll.w);
                     *reinterpret_cast<float4*>(hi_t + j * 4096) = hh;
                     *reinterpret_cast<float4*>(hi_t + TILE16K + j * 4096) = ll;
                 }
                 fence_proxy_async_smem();
                 mbar_arrive(&bar->a_full[slot]);
+#pragma unroll
+                for (int j = 0; j < 4; ++j) cur[j] = nxt[j];
             }
         };
         // D -> bias, activation -> hi/lo -> TMEM A operand; this thread owns 64 columns of its lane
@@ -248,7 +255,7 @@ __global__ void __launch_bounds__(N_THREADS, 1) edge_gate_tc_kernel(const __grid
                         const float y = gate_act<GENERIC>(act, __uint_as_float(v[j + u]) + bb[u], slope);
                         const float hh = round_tf32(y);
                         v[j + u] = __float_as_uint(hh);
-                        lo[j + u] = __float_as_uint(round_tf32(y - hh));
+                        lo[j + u] = __float_as_uint(y - hh);
                     }
                 }
                 tmem_st32(lane_addr + COL_A_HI + hf * 64 + cb * 32, v);
@@ -312,18 +319,28 @@ __global__ void __launch_bounds__(N_THREADS, 1) edge_gate_tc_kernel(const __grid
             }
         };
 
+        const bool tr = p.trace != nullptr && blockIdx.x == 0 && lane == 0 && (warp == 0 || warp == 4);
+        long long* trp = p.trace + (warp == 0 ? 0 : 1) * 128;
+#define SWE_STAMP(i_, ev_) do { if (tr && (i_) < 16) trp[(i_) * 8 + (ev_)] = clock64(); } while (0)
         if (n_my > 0) { load_ids(0); gather(0, 0, n_l1); }
 #pragma unroll 1
         for (int i = 0; i < n_my; ++i) {
             const uint32_t ph = i & 1;
             const bool dump = p.dbg != nullptr && i == 0 && blockIdx.x == 0;
             const bool more = i + 1 < n_my;
+            SWE_STAMP(i, 0);
             epilogue_mid(0, ph, dump);
+            SWE_STAMP(i, 1);
             if (more) { load_ids(i + 1); gather(i + 1, 0, h_l1); }
+            SWE_STAMP(i, 2);
             epilogue_mid(1, ph, dump);
+            SWE_STAMP(i, 3);
             if (more) gather(i + 1, h_l1, n_l1);
+            SWE_STAMP(i, 4);
             epilogue_final(i, ph, dump);
+            SWE_STAMP(i, 5);
         }
+#undef SWE_STAMP
     } else if (warp == 8) {
         // =====================================================================================
         // weight loader (same chunk order as the MMA issuer)
@@ -403,15 +420,24 @@ __global__ void __launch_bounds__(N_THREADS, 1) edge_gate_tc_kernel(const __grid
                 }
                 mma_commit(&bar->d_full[layer]);
             };
+            const bool tr = p.trace != nullptr && blockIdx.x == 0;
+            long long* trp = p.trace + 2 * 128;
+#define SWE_STAMP(i_, ev_) do { if (tr && (i_) < 16) trp[(i_) * 8 + (ev_)] = clock64(); } while (0)
             if (n_my > 0) mma_l1(0, n_l1, true);
             for (int i = 0; i < n_my; ++i) {
                 const uint32_t ph = i & 1;
                 const bool more = i + 1 < n_my;
+                SWE_STAMP(i, 0);
                 mma_ts(1, ph);
+                SWE_STAMP(i, 1);
                 if (more) mma_l1(0, h_l1, false);
+                SWE_STAMP(i, 2);
                 mma_ts(2, ph);
+                SWE_STAMP(i, 3);
                 if (more) mma_l1(h_l1, n_l1, true);
+                SWE_STAMP(i, 4);
             }
+#undef SWE_STAMP
         }
     }
     tc_fence_before_sync();
@@ -423,6 +449,10 @@ __global__ void __launch_bounds__(N_THREADS, 1) edge_gate_tc_kernel(const __grid
 }  // namespace swe
 
 using namespace swe;
+
+extern "C" int swe_edge_gate_tc_fwd_traced(const float*, const float*, const float*, const float*, const int32_t*,
+                                           const int32_t*, int64_t, const void*, int32_t, const int32_t*,
+                                           const float* const*, int32_t, float*, float*, long long*, void*);
 
 extern "C" size_t swe_gate_tc_image_bytes(int32_t k1) { return tc::img_bytes(k1 / tc::KC); }
 
@@ -439,6 +469,16 @@ extern "C" int swe_edge_gate_tc_fwd(const float* xs, const float* xd_src, const 
                                     const int32_t* src, const int32_t* dst, int64_t n_edges, const void* image,
                                     int32_t k1, const int32_t* act3, const float* const* slope3, int32_t normalize,
                                     float* s_out, float* dbg, void* stream) {
+    return swe_edge_gate_tc_fwd_traced(xs, xd_src, xd_dst, a, src, dst, n_edges, image, k1, act3, slope3, normalize,
+                                       s_out, dbg, nullptr, stream);
+}
+
+// same as swe_edge_gate_tc_fwd plus an optional device buffer of 3*16*8 int64 receiving clock64 stamps of
+// the phase boundaries of CTA 0 (row workers warp 0 / warp 4, MMA issuer) — a profiling aid, not part of the ABI
+extern "C" int swe_edge_gate_tc_fwd_traced(const float* xs, const float* xd_src, const float* xd_dst, const float* a,
+                                           const int32_t* src, const int32_t* dst, int64_t n_edges, const void* image,
+                                           int32_t k1, const int32_t* act3, const float* const* slope3,
+                                           int32_t normalize, float* s_out, float* dbg, long long* trace, void* stream) {
     SWE_REQUIRE(xs && xd_src && src && dst && s_out && image && act3 && slope3 && n_edges >= 0, SWE_E_INVAL,
                 "edge_gate_tc: bad arguments");
     SWE_REQUIRE(aligned16(xs) && aligned16(xd_src) && aligned16(s_out) && aligned16(image) && (!a || aligned16(a)) &&
@@ -449,7 +489,7 @@ extern "C" int swe_edge_gate_tc_fwd(const float* xs, const float* xd_src, const 
     p.xs = xs; p.xd_src = xd_src; p.xd_dst = xd_dst; p.a = a; p.src = src; p.dst = dst; p.n_edges = n_edges;
     p.img = (const unsigned char*)image; p.n_l1_img = k1 / tc::KC;
     for (int i = 0; i < 3; ++i) { p.act[i] = act3[i]; p.slope[i] = slope3[i]; }
-    p.normalize = normalize; p.s_out = s_out; p.dbg = dbg;
+    p.normalize = normalize; p.s_out = s_out; p.dbg = dbg; p.trace = trace;
     bool generic = false;
     for (int i = 0; i < 3; ++i)
         generic |= !(act3[i] == SWE_ACT_NONE || act3[i] == SWE_ACT_PRELU || act3[i] == SWE_ACT_RELU || act3[i] == SWE_ACT_LEAKYRELU);

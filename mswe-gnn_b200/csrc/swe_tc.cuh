@@ -139,20 +139,20 @@ __device__ __forceinline__ void mma_commit(uint64_t* bar) {
 __host__ __device__ constexpr uint32_t sw128_offset(uint32_t row, uint32_t k) {
     return (row >> 3) * 1024u + (row & 7u) * 128u + ((((k >> 2) ^ (row & 7u)) & 7u) << 4) + ((k & 3u) << 2);
 }
-// split an fp32 value into a tf32-exact high part and a tf32-exact remainder, both round-to-nearest
-// (cvt.rna), so the split error is unbiased and <= 2^-24 |x| and the tensor core reads exact operands
-__device__ __forceinline__ float round_tf32(float x) {
-    uint32_t r;
-    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
-    return __uint_as_float(r);
+// Error-free split x = hi + lo for 3xTF32: hi = x rounded to nearest tf32 (integer add of half an ulp,
+// then clear the 13 low mantissa bits: 2 ALU ops instead of the ~5-instruction cvt.rna.tf32 sequence),
+// lo = x - hi exactly (|lo| <= 2^-12 |x|, 12 significant bits; the tensor core drops its last bit,
+// a 2^-23 |x| effect).  inf stays inf, NaN stays NaN.
+__host__ __device__ __forceinline__ float round_tf32(float x) {
+#ifdef __CUDA_ARCH__
+    return __uint_as_float((__float_as_uint(x) + 0x1000u) & 0xFFFFE000u);
+#else
+    union { float f; uint32_t u; } c; c.f = x; c.u = (c.u + 0x1000u) & 0xFFFFE000u; return c.f;
+#endif
 }
 __host__ __device__ __forceinline__ void split_tf32(float x, float& hi, float& lo) {
-#ifdef __CUDA_ARCH__
     hi = round_tf32(x);
-    lo = round_tf32(x - hi);
-#else
-    hi = x; lo = 0.f;
-#endif
+    lo = x - hi;
 }
 
 }  // namespace tc

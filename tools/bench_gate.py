@@ -35,3 +35,22 @@ for name in which:
     ms = e0.elapsed_time(e1) / reps
     flops = 2.0 * E * (320 * 128 + 128 * 128 + 128 * 64)
     print(f"{name}: E={E} {ms:.3f} ms  {flops / ms / 1e9:.1f} TFLOP/s (algorithmic)  {ms * 1e3 / ((E + 127) // 128 / 148):.2f} us/tile/SM")
+
+if os.environ.get("TRACE"):
+    import ctypes as C
+    l = lib.load()
+    fn = l.swe_edge_gate_tc_fwd_traced
+    fn.restype = C.c_int
+    fn.argtypes = [C.c_void_p] * 6 + [C.c_int64, C.c_void_p, C.c_int32, C.POINTER(C.c_int32), C.POINTER(C.c_void_p), C.c_int32,
+                                       C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+    trace = torch.zeros(3 * 128, dtype=torch.int64, device=DEV)
+    act3 = (C.c_int32 * 3)(*codes); sl3 = (C.c_void_p * 3)(*[None if t is None else t.data_ptr() for t in slopes])
+    rc = fn(xs.data_ptr(), xd.data_ptr(), xd.data_ptr(), a.data_ptr(), src.data_ptr(), dst.data_ptr(), E, img.data_ptr(), 320,
+            act3, sl3, 1, s.data_ptr(), None, trace.data_ptr(), torch.cuda.current_stream().cuda_stream)
+    torch.cuda.synchronize()
+    t = trace.cpu().view(3, 16, 8)
+    t0 = int(t[0, 2, 0])
+    names = ["rowA(w0)", "rowB(w4)", "mma"]
+    for tile in range(2, 8):
+        for r in range(3):
+            print(tile, names[r], [(int(v) - t0) if int(v) else None for v in t[r, tile, :6]])
