@@ -202,6 +202,141 @@ int swe_apply_bc(float* x, int32_t n_cols, int32_t n_static_raw, int32_t previou
 /* *step_ptr += 1 (end of one rollout step, training/train.py:87). */
 int swe_step_advance(int32_t* step_ptr, void* stream);
 
+
+/* ---------------------------------------------------------------------------------------------
+ * Training path (forward that keeps what the backward needs + backward kernels).
+ * The reference has no hand-written backward: it is whatever torch.autograd derives for
+ * models/gnn.py:387-445 etc. inside LightningTrainer.training_step (training/train.py:125-145).
+ * The kernels below are that derivative, written out; parity is checked
+ * against torch.autograd run on the oracle.  Every reduction is a fixed-order sum (per-CTA
+ * partials reduced in CTA order, CSR segments in edge order): no atomics, bit-reproducible.
+ * ------------------------------------------------------------------------------------------- */
+
+/* Row provider: X[r, :] = concat_j act_j( base_j[(idx_j ? idx_j[r] : r) * ld_j + (0..width_j)) ),
+ * every block zero-padded to a multiple of 4 columns (<= 128). */
+typedef struct swe_seg {
+    const float*   base;
+    const int32_t* idx;     /* NULL = identity */
+    const float*   slope;   /* PReLU parameter (device) or NULL */
+    int32_t ld;
+    int32_t width;
+    int32_t act;            /* enum swe_act applied on load */
+    int32_t _pad;
+} swe_seg_t;
+
+#define SWE_MAX_SEGS 5
+typedef struct swe_rows {
+    int32_t n_seg;
+    int32_t _pad;
+    swe_seg_t seg[SWE_MAX_SEGS];
+} swe_rows_t;
+
+/* pre[r, 0:n_out) = X[r, :] · Wᵀ + bias  (one Linear of a make_mlp stack, models/models.py:133-145,
+ * WITHOUT its activation: the consumer applies it through its row provider, so the saved tensor
+ * is the pre-activation the backward needs).  wt: packed k-major weight (swe_pack_linear) whose
+ * row blocks follow the padded segment widths.  n_out in {16, 32, 64, 128}. */
+int swe_mlp_layer_fwd(const swe_rows_t* X, int64_t n_rows, const float* wt, const float* bias, int32_t n_out,
+                      float* pre, void* stream);
+
+/* Backward of one Linear+activation w.r.t. its input:
+ *   delta = dh ⊙ act'(pre)            (skipped when pre == NULL: dh already holds delta)
+ *   dx[r, 0:KO) (+)= delta[r, :] · W[:, k_off : k_off + KO)      (columns >= k_valid give 0)
+ * dh: [n_rows, n] in/out (overwritten with delta when write_delta); W: torch Linear.weight layout
+ * [n, w_ld] row-major; KO in {16, 32, 64, 128}; dx: [n_rows, KO] or NULL (then only delta and
+ * the partial sums are produced).  part: NULL or [grid_ctas][n + 1] per-CTA partial sums of
+ * delta (bias gradient) and of dh·min(pre,0)-style PReLU slope gradient (last slot); reduce them
+ * with swe_reduce_partials.  Returns the number of CTAs through *grid_out. */
+int swe_mlp_layer_bwd_dx(float* dh, const float* pre, int32_t act, const float* slope, int64_t n_rows, int32_t n,
+                         const float* w, int32_t w_ld, int32_t k_off, int32_t k_valid, int32_t ko,
+                         float* dx, int32_t accumulate, int32_t write_delta, float* part, int32_t* grid_out,
+                         void* stream);
+int swe_mlp_layer_bwd_dx_grid(int64_t n_rows);
+
+/* Weight gradient of one Linear: part[cta][n_i * KO + k] = Σ_{rows of this CTA} delta[r, n_i] · X[r, k]
+ * (X: provider with ONE segment, zero-padded to KO).  Reduce with swe_reduce_partials. */
+int swe_mlp_layer_bwd_dw(const float* delta, int64_t n_rows, int32_t n, const swe_rows_t* X, int32_t ko,
+                         float* part, int32_t* grid_out, void* stream);
+int swe_mlp_layer_bwd_dw_grid(int64_t n_rows);
+
+/* out[(j / ko) * ld_out + k_off + j % ko] += Σ_{c < n_parts, in order} part[c * part_stride + item_off + j]
+ * for j < n_items with (j % ko) < k_valid. */
+int swe_reduce_partials(const float* part, int32_t n_parts, int64_t part_stride, int32_t item_off, int32_t n_items,
+                        int32_t ko, int32_t k_valid, float* out, int32_t ld_out, int32_t k_off, void* stream);
+
+/* s = act(pre3) / ||act(pre3)||₂, NaN -> 0 (models/gnn.py:425-426); F-wide rows. */
+int swe_gate_norm_fwd(const float* pre3, int32_t act, const float* slope, int32_t normalize, int64_t n_edges,
+                      float* s_out, int32_t F, void* stream);
+/* ds (in place) -> du = (ds − s (s·ds)) / ||u||  (0 where ||u|| = 0); normalize == 0: unchanged. */
+int swe_gate_norm_bwd(float* ds, const float* pre3, int32_t act, const float* slope, int32_t normalize,
+                      int64_t n_edges, int32_t F, void* stream);
+
+/* y = act(x) and its backward g ⊙ act'(x) over rows [row_lo, row_lo + n_rows) of [*, F] arrays
+ * (gnn_activation, models/gnn.py:135-136,332-336).  slope_part: NULL or [grid] per-CTA PReLU
+ * slope-gradient partials. */
+int swe_act_fwd(const float* x, int32_t row_lo, int32_t n_rows, int32_t act, const float* slope, float* y,
+                int32_t F, void* stream);
+int swe_act_bwd(const float* g, const float* x, int32_t row_lo, int32_t n_rows, int32_t act, const float* slope,
+                float* gx, float* slope_part, int32_t* grid_out, int32_t F, void* stream);
+
+/* swe_propagate_hop_fwd that also stores agg (the filter's input) for the backward. */
+int swe_propagate_hop_train_fwd(const float* o_src, const float* o_dst, const float* s, const int32_t* rowptr,
+                                const int32_t* src, int32_t dst_lo, int32_t n_dst, const float* wt,
+                                int32_t with_gradient, int32_t upwind, const float* addend, float* agg_out,
+                                float* out, int32_t F, void* stream);
+
+/* flags[i] = (Σ_f o[i, f] != 0) for rows [row_lo, row_lo + n_rows): the reference's per-hop wet-node
+ * mask (models/gnn.py:408), which the backward needs to reproduce autograd's input gradients. */
+int swe_row_flags(const float* o, int32_t row_lo, int32_t n_rows, uint8_t* flags, int32_t F, void* stream);
+
+/* Backward of one hop, destination-centric part (models/gnn.py:428-443 differentiated):
+ *   act_p = wet_dst[c] | wet_src[src[p]]
+ *   with_gradient: ds[p] (+)= act_p · da[c] ⊙ (o_dst[c] − o_src[src[p]]);  g_part[c] = g_next[c] + da[c] ⊙ Σ_p act_p s[p]
+ *   otherwise    : ds[p] (+)= act_p · da[c] ⊙ o_src[src[p]]                (g_part untouched)
+ * wet_dst / o_dst may be NULL (destination rows identically zero). */
+int swe_hop_bwd_dst(const float* da, const float* o_src, const float* o_dst, const float* s, float* ds,
+                    int32_t accumulate_ds, const int32_t* rowptr, const int32_t* src, const uint8_t* wet_src,
+                    const uint8_t* wet_dst, int32_t dst_lo, int32_t n_dst, int32_t with_gradient,
+                    const float* g_next, float* g_part, int32_t F, void* stream);
+/* Source-centric part over the transposed CSR (t_rowptr over source nodes, t_pos = position of the
+ * edge in destination-CSR order):  acc = Σ_q act · s[p] ⊙ da[dst[p]], p = t_pos[q];
+ *   with_gradient: g_io[n] −= acc;   otherwise: g_io[n] (+)= acc (accumulate flag). */
+int swe_hop_bwd_src(const float* da, const float* s, const int32_t* t_rowptr, const int32_t* t_pos,
+                    const int32_t* dst, const uint8_t* wet_src, const uint8_t* wet_dst, int32_t src_lo,
+                    int32_t n_src, int32_t with_gradient, int32_t accumulate, float* g_io, int32_t F, void* stream);
+
+/* out[node_lo + i] (+)= Σ_{q in segment i} e[pos ? pos[q] : q]   (edge -> node sums of the gate's input
+ * gradients over a CSR; fixed order). */
+int swe_edge_to_node_sum(const float* e, const int32_t* rowptr, const int32_t* pos, int32_t node_lo, int32_t n_nodes,
+                         float* out, int32_t accumulate, int32_t F, void* stream);
+
+/* Backward of swe_pool_mean_fwd: dx[fine_lo + i] (+)= Σ_{q in fine segment i} g[coarse[q]] / max(1, count(coarse[q])),
+ * count from the pooling CSR rowptr (keyed by coarse node, first key coarse_lo). */
+int swe_pool_mean_bwd(const float* g, const int32_t* f_rowptr, const int32_t* coarse, int32_t fine_lo, int32_t n_fine,
+                      const int32_t* pool_rowptr, int32_t coarse_lo, float* dx, int32_t accumulate, int32_t F,
+                      void* stream);
+
+/* Encoder inputs of the training path: xin_s[i] = [x[perm[i], 0:n_static_raw], WL, 0..] (ks columns),
+ * and the scatter of their gradients back into dx (original row order, accumulated):
+ *   dx[perm[i], c] += dxin_s[i, c] (c < n_static_raw); WL: dx[.., n_static_raw-1] and dx[.., n_cols-2];
+ *   dx[perm[i], n_static_raw + c] += dxin_d[i, c] for i < n_dyn_rows. */
+int swe_static_inputs_fwd(const float* x, int32_t n_cols, const int32_t* perm, int32_t n_nodes, int32_t n_static_raw,
+                          int32_t with_wl, float* xin_s, int32_t ks, void* stream);
+int swe_node_inputs_bwd(const float* dxin_s, int32_t ks, const float* dxin_d, int32_t kd, int32_t n_cols,
+                        const int32_t* perm, int32_t n_nodes, int32_t n_dyn_rows, int32_t n_static_raw,
+                        int32_t with_wl, float* dx, void* stream);
+
+/* Head of the training path: pred from the decoder's last pre-activation (models/gnn.py:339-348,
+ * models/models.py:50-91) and its backward.  pre3: [n_nodes, ldp] (first two columns used).
+ *   dh3[i, 0:2] = dpred[perm[i]] ⊙ masks ⊙ relu'  (other columns 0), dx0[perm[i], window] += residual path,
+ *   res_part[cta][2*previous_t]: per-CTA partials of d residual_weights laid out [t][var]. */
+int swe_head_fwd(const float* pre3, int32_t ldp, int32_t act, const float* slope, const float* x0, int32_t n_cols,
+                 const int32_t* perm, int32_t n_nodes, int32_t previous_t, int32_t res_mode, const float* res_w,
+                 float eps, float* pred, void* stream);
+int swe_head_bwd(const float* dpred, const float* pre3, int32_t ldp, int32_t act, const float* slope, const float* x0,
+                 int32_t n_cols, const int32_t* perm, int32_t n_nodes, int32_t previous_t, int32_t res_mode,
+                 const float* res_w, float eps, float* dh3, float* dx0, float* res_part, int32_t* grid_out,
+                 void* stream);
+
 #ifdef __cplusplus
 }
 #endif

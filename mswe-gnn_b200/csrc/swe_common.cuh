@@ -64,7 +64,7 @@ __device__ __forceinline__ float act_apply(int act, float v, float slope) {
 // d act(v) / d v expressed with the pre-activation v (backward kernels)
 __device__ __forceinline__ float act_grad(int act, float v, float slope) {
     switch (act) {
-        case SWE_ACT_PRELU:     return v >= 0.f ? 1.f : slope;          // torch: grad at 0 is 1 for x>=0? see note
+        case SWE_ACT_PRELU:     return v > 0.f ? 1.f : slope;           // torch: input > 0 ? grad : weight * grad
         case SWE_ACT_RELU:      return v > 0.f ? 1.f : 0.f;
         case SWE_ACT_TANH:      { float t = tanhf(v); return 1.f - t * t; }
         case SWE_ACT_LEAKYRELU: return v > 0.f ? 1.f : 0.1f;

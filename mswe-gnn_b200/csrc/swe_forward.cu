@@ -360,7 +360,7 @@ __global__ void __launch_bounds__(NT, FILTER ? 3 : 4) hop_kernel(
     const float* __restrict__ o_src, const float* __restrict__ o_dst, const float* __restrict__ s,
     const int32_t* __restrict__ rowptr, const int32_t* __restrict__ src, int dst_lo, int n_dst,
     const float* __restrict__ wt, int with_gradient, int upwind, const float* __restrict__ addend,
-    int act, const float* __restrict__ slope_p, float* __restrict__ out) {
+    int act, const float* __restrict__ slope_p, float* __restrict__ out, float* __restrict__ agg_out) {
     extern __shared__ __align__(16) float smem[];
     constexpr int QPR = F / 4, NG = NT / QPR, LDA = F + 4;
     float* agg = smem;
@@ -393,7 +393,10 @@ __global__ void __launch_bounds__(NT, FILTER ? 3 : 4) hop_kernel(
                     stg4(out + c * F + 4 * q, v);
                 }
             }
-            if (FILTER) stg4(agg + i * LDA + 4 * q, acc);
+            if (FILTER) {
+                stg4(agg + i * LDA + 4 * q, acc);
+                if (agg_out && c_rel < n_dst) stg4(agg_out + ((long long)dst_lo + c_rel) * F + 4 * q, acc);
+            }
         }
         if (FILTER) {
             cp_async_wait<0>();
@@ -699,14 +702,15 @@ extern "C" int swe_node_linear_fwd(const float* x, int32_t row_lo, int32_t n_row
     return check_launch("node_linear_fwd");
 }
 
-extern "C" int swe_propagate_hop_fwd(const float* o_src, const float* o_dst, const float* s, const int32_t* rowptr,
-                                     const int32_t* src, int32_t dst_lo, int32_t n_dst, const float* wt,
-                                     int32_t with_gradient, int32_t upwind, const float* addend, int32_t act,
-                                     const float* slope, float* out, int32_t F, void* stream) {
+static int hop_launch(const float* o_src, const float* o_dst, const float* s, const int32_t* rowptr,
+                      const int32_t* src, int32_t dst_lo, int32_t n_dst, const float* wt, int32_t with_gradient,
+                      int32_t upwind, const float* addend, int32_t act, const float* slope, float* out,
+                      float* agg_out, int32_t F, void* stream) {
     SWE_REQUIRE(o_src && s && rowptr && src && out && dst_lo >= 0 && n_dst >= 0, SWE_E_INVAL, "hop: bad arguments");
     SWE_REQUIRE(!(with_gradient && !o_dst), SWE_E_INVAL, "hop: with_gradient needs the destination rows");
     SWE_REQUIRE(aligned16(o_src) && aligned16(s) && aligned16(out) && (!o_dst || aligned16(o_dst)) &&
-                (!wt || aligned16(wt)) && (!addend || aligned16(addend)), SWE_E_ALIGN, "hop: unaligned buffer");
+                (!wt || aligned16(wt)) && (!addend || aligned16(addend)) && (!agg_out || aligned16(agg_out)),
+                SWE_E_ALIGN, "hop: unaligned buffer");
     SWE_REQUIRE(out != o_src && out != o_dst, SWE_E_INVAL, "hop: output must not alias the hop input");
     if (n_dst == 0) return 0;
     SWE_DISPATCH_F(F, {
@@ -714,14 +718,30 @@ extern "C" int swe_propagate_hop_fwd(const float* o_src, const float* o_dst, con
             auto k = hop_kernel<FF, true>;
             if (int r = opt_in_smem(k, HopSmem<FF>::bytes)) return r;
             k<<<grid_for((n_dst + TM - 1) / TM, 3), NT, HopSmem<FF>::bytes, (cudaStream_t)stream>>>(
-                o_src, o_dst, s, rowptr, src, dst_lo, n_dst, wt, with_gradient, upwind, addend, act, slope, out);
+                o_src, o_dst, s, rowptr, src, dst_lo, n_dst, wt, with_gradient, upwind, addend, act, slope, out, agg_out);
         } else {
             auto k = hop_kernel<FF, false>;
             k<<<grid_for((n_dst + TM - 1) / TM, 4), NT, 0, (cudaStream_t)stream>>>(
-                o_src, o_dst, s, rowptr, src, dst_lo, n_dst, nullptr, with_gradient, upwind, addend, act, slope, out);
+                o_src, o_dst, s, rowptr, src, dst_lo, n_dst, nullptr, with_gradient, upwind, addend, act, slope, out, nullptr);
         }
     });
     return check_launch("propagate_hop_fwd");
+}
+
+extern "C" int swe_propagate_hop_fwd(const float* o_src, const float* o_dst, const float* s, const int32_t* rowptr,
+                                     const int32_t* src, int32_t dst_lo, int32_t n_dst, const float* wt,
+                                     int32_t with_gradient, int32_t upwind, const float* addend, int32_t act,
+                                     const float* slope, float* out, int32_t F, void* stream) {
+    return hop_launch(o_src, o_dst, s, rowptr, src, dst_lo, n_dst, wt, with_gradient, upwind, addend, act, slope, out,
+                      nullptr, F, stream);
+}
+
+extern "C" int swe_propagate_hop_train_fwd(const float* o_src, const float* o_dst, const float* s, const int32_t* rowptr,
+                                           const int32_t* src, int32_t dst_lo, int32_t n_dst, const float* wt,
+                                           int32_t with_gradient, int32_t upwind, const float* addend, float* agg_out,
+                                           float* out, int32_t F, void* stream) {
+    return hop_launch(o_src, o_dst, s, rowptr, src, dst_lo, n_dst, wt, with_gradient, upwind, addend, SWE_ACT_NONE,
+                      nullptr, out, agg_out, F, stream);
 }
 
 extern "C" int swe_pool_mean_fwd(const float* x, const int32_t* rowptr, const int32_t* fine, int32_t coarse_lo,

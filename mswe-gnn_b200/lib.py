@@ -31,8 +31,22 @@ class SweMlp(C.Structure):
     _fields_ = [("n_layers", C.c_int32), ("_pad", C.c_int32), ("layer", SweLayer * SWE_MAX_LAYERS)]
 
 
+SWE_MAX_SEGS = 5
+
+
+class SweSeg(C.Structure):
+    _fields_ = [("base", C.c_void_p), ("idx", C.c_void_p), ("slope", C.c_void_p),
+                ("ld", C.c_int32), ("width", C.c_int32), ("act", C.c_int32), ("_pad", C.c_int32)]
+
+
+class SweRows(C.Structure):
+    _fields_ = [("n_seg", C.c_int32), ("_pad", C.c_int32), ("seg", SweSeg * SWE_MAX_SEGS)]
+
+
 _p, _i32, _i64, _f32, _sz = C.c_void_p, C.c_int32, C.c_int64, C.c_float, C.c_size_t
 _mlp = C.POINTER(SweMlp)
+_rows = C.POINTER(SweRows)
+_pi32 = C.POINTER(C.c_int32)
 
 # name -> (restype, argtypes); mirrors include/swe_gnn_b200.h one to one
 SIGNATURES = {
@@ -56,6 +70,28 @@ SIGNATURES = {
                                       _p, _i32, _p]),
     "swe_apply_bc": (C.c_int, [_p, _i32, _i32, _i32, _i32, _p, _i32, _p, _i32, _p, _p]),
     "swe_step_advance": (C.c_int, [_p, _p]),
+    # training path
+    "swe_mlp_layer_fwd": (C.c_int, [_rows, _i64, _p, _p, _i32, _p, _p]),
+    "swe_mlp_layer_bwd_dx": (C.c_int, [_p, _p, _i32, _p, _i64, _i32, _p, _i32, _i32, _i32, _i32, _p, _i32, _i32, _p,
+                                       _pi32, _p]),
+    "swe_mlp_layer_bwd_dx_grid": (C.c_int, [_i64]),
+    "swe_mlp_layer_bwd_dw": (C.c_int, [_p, _i64, _i32, _rows, _i32, _p, _pi32, _p]),
+    "swe_mlp_layer_bwd_dw_grid": (C.c_int, [_i64]),
+    "swe_reduce_partials": (C.c_int, [_p, _i32, _i64, _i32, _i32, _i32, _i32, _p, _i32, _i32, _p]),
+    "swe_gate_norm_fwd": (C.c_int, [_p, _i32, _p, _i32, _i64, _p, _i32, _p]),
+    "swe_gate_norm_bwd": (C.c_int, [_p, _p, _i32, _p, _i32, _i64, _i32, _p]),
+    "swe_act_fwd": (C.c_int, [_p, _i32, _i32, _i32, _p, _p, _i32, _p]),
+    "swe_act_bwd": (C.c_int, [_p, _p, _i32, _i32, _i32, _p, _p, _p, _pi32, _i32, _p]),
+    "swe_propagate_hop_train_fwd": (C.c_int, [_p, _p, _p, _p, _p, _i32, _i32, _p, _i32, _i32, _p, _p, _p, _i32, _p]),
+    "swe_row_flags": (C.c_int, [_p, _i32, _i32, _p, _i32, _p]),
+    "swe_hop_bwd_dst": (C.c_int, [_p, _p, _p, _p, _p, _i32, _p, _p, _p, _p, _i32, _i32, _i32, _p, _p, _i32, _p]),
+    "swe_hop_bwd_src": (C.c_int, [_p, _p, _p, _p, _p, _p, _p, _i32, _i32, _i32, _i32, _p, _i32, _p]),
+    "swe_edge_to_node_sum": (C.c_int, [_p, _p, _p, _i32, _i32, _p, _i32, _i32, _p]),
+    "swe_pool_mean_bwd": (C.c_int, [_p, _p, _p, _i32, _i32, _p, _i32, _p, _i32, _i32, _p]),
+    "swe_static_inputs_fwd": (C.c_int, [_p, _i32, _p, _i32, _i32, _i32, _p, _i32, _p]),
+    "swe_node_inputs_bwd": (C.c_int, [_p, _i32, _p, _i32, _i32, _p, _i32, _i32, _i32, _i32, _p, _p]),
+    "swe_head_fwd": (C.c_int, [_p, _i32, _i32, _p, _p, _i32, _p, _i32, _i32, _i32, _p, _f32, _p, _p]),
+    "swe_head_bwd": (C.c_int, [_p, _p, _i32, _i32, _p, _p, _i32, _p, _i32, _i32, _i32, _p, _f32, _p, _p, _p, _pi32, _p]),
 }
 
 _lib = None
@@ -102,8 +138,8 @@ def _stream() -> int:
 
 def ptr(t: Optional[torch.Tensor], dtype=torch.float32) -> Optional[int]:
     """Device pointer of a contiguous CUDA tensor of the given dtype (None passes NULL)."""
-    if t is None:
-        return None
+    if t is None or isinstance(t, int):
+        return t
     if not t.is_cuda:
         raise RuntimeError("mswe_gnn_b200 kernels need CUDA tensors; got a %s tensor (no CPU fallback)" % t.device)
     if t.dtype != dtype:
@@ -216,3 +252,147 @@ def apply_bc(x, n_static_raw, previous_t, type_bc, node_bc, bc, step_ptr):
 
 def step_advance(step_ptr):
     _check(load().swe_step_advance(ptr(step_ptr, torch.int32), _stream()), "swe_step_advance")
+
+
+# ------------------------------------------------------------------------------------------------
+# training path
+# ------------------------------------------------------------------------------------------------
+def vptr(t: torch.Tensor, row_lo: int = 0) -> int:
+    """Address of a *virtual* full-size array whose rows [row_lo, row_lo + len(t)) are backed by `t`
+    (the kernels only touch the row range they are given)."""
+    ptr(t)
+    return t.data_ptr() - row_lo * t.shape[1] * t.element_size()
+
+
+def make_rows(segs) -> SweRows:
+    """segs: sequence of (tensor_or_address, idx or None, ld, width, act_code, slope tensor or None)."""
+    r = SweRows()
+    r.n_seg = len(segs)
+    for j, (base, idx, ld, width, act, slope) in enumerate(segs):
+        sg = r.seg[j]
+        sg.base = base if isinstance(base, int) else ptr(base)
+        sg.idx = ptr(idx, torch.int32)
+        sg.slope = ptr(slope)
+        sg.ld, sg.width, sg.act = int(ld), int(width), int(act)
+    return r
+
+
+def _addr(t):
+    return t if (t is None or isinstance(t, int)) else ptr(t)
+
+
+def mlp_layer_fwd(rows: SweRows, n_rows, wt, bias, n_out, pre):
+    _check(load().swe_mlp_layer_fwd(C.byref(rows), n_rows, _addr(wt), _addr(bias), n_out, _addr(pre), _stream()),
+           "swe_mlp_layer_fwd")
+
+
+def mlp_layer_bwd_dx(dh, pre, act, slope, n_rows, n, w, w_ld, k_off, k_valid, ko, dx, accumulate, write_delta, part):
+    g = C.c_int32(0)
+    _check(load().swe_mlp_layer_bwd_dx(_addr(dh), _addr(pre), act, ptr(slope), n_rows, n, _addr(w), w_ld, k_off, k_valid,
+                                       ko, _addr(dx), int(accumulate), int(write_delta), _addr(part), C.byref(g),
+                                       _stream()), "swe_mlp_layer_bwd_dx")
+    return g.value
+
+
+def mlp_layer_bwd_dx_grid(n_rows) -> int:
+    return int(load().swe_mlp_layer_bwd_dx_grid(n_rows))
+
+
+def mlp_layer_bwd_dw(delta, n_rows, n, rows: SweRows, ko, part):
+    g = C.c_int32(0)
+    _check(load().swe_mlp_layer_bwd_dw(_addr(delta), n_rows, n, C.byref(rows), ko, _addr(part), C.byref(g), _stream()),
+           "swe_mlp_layer_bwd_dw")
+    return g.value
+
+
+def mlp_layer_bwd_dw_grid(n_rows) -> int:
+    return int(load().swe_mlp_layer_bwd_dw_grid(n_rows))
+
+
+def reduce_partials(part, n_parts, part_stride, item_off, n_items, ko, k_valid, out, ld_out, k_off):
+    _check(load().swe_reduce_partials(_addr(part), n_parts, part_stride, item_off, n_items, ko, k_valid, _addr(out),
+                                      ld_out, k_off, _stream()), "swe_reduce_partials")
+
+
+def gate_norm_fwd(pre3, act, slope, normalize, n_edges, s_out, F):
+    _check(load().swe_gate_norm_fwd(ptr(pre3), act, ptr(slope), int(normalize), n_edges, ptr(s_out), F, _stream()),
+           "swe_gate_norm_fwd")
+
+
+def gate_norm_bwd(ds, pre3, act, slope, normalize, n_edges, F):
+    _check(load().swe_gate_norm_bwd(ptr(ds), ptr(pre3), act, ptr(slope), int(normalize), n_edges, F, _stream()),
+           "swe_gate_norm_bwd")
+
+
+def act_fwd(x, row_lo, n_rows, act, slope, y, F):
+    _check(load().swe_act_fwd(_addr(x), row_lo, n_rows, act, ptr(slope), _addr(y), F, _stream()), "swe_act_fwd")
+
+
+def act_bwd(g, x, row_lo, n_rows, act, slope, gx, slope_part, F):
+    gr = C.c_int32(0)
+    _check(load().swe_act_bwd(_addr(g), _addr(x), row_lo, n_rows, act, ptr(slope), _addr(gx), _addr(slope_part),
+                              C.byref(gr), F, _stream()), "swe_act_bwd")
+    return gr.value
+
+
+def propagate_hop_train_fwd(o_src, o_dst, s, rowptr, src, dst_lo, n_dst, wt, with_gradient, upwind, addend, agg_out,
+                            out, F):
+    _check(load().swe_propagate_hop_train_fwd(_addr(o_src), _addr(o_dst), ptr(s), ptr(rowptr, torch.int32),
+                                              ptr(src, torch.int32), dst_lo, n_dst, ptr(wt), int(with_gradient),
+                                              int(upwind), _addr(addend), _addr(agg_out), _addr(out), F, _stream()),
+           "swe_propagate_hop_train_fwd")
+
+
+def row_flags(o, row_lo, n_rows, flags, F):
+    _check(load().swe_row_flags(_addr(o), row_lo, n_rows, ptr(flags, torch.uint8), F, _stream()), "swe_row_flags")
+
+
+def hop_bwd_dst(da, o_src, o_dst, s, ds, accumulate_ds, rowptr, src, wet_src, wet_dst, dst_lo, n_dst, with_gradient,
+                g_next, g_part, F):
+    _check(load().swe_hop_bwd_dst(_addr(da), _addr(o_src), _addr(o_dst), ptr(s), ptr(ds), int(accumulate_ds),
+                                  ptr(rowptr, torch.int32), ptr(src, torch.int32), ptr(wet_src, torch.uint8),
+                                  ptr(wet_dst, torch.uint8), dst_lo, n_dst, int(with_gradient), _addr(g_next),
+                                  _addr(g_part), F, _stream()), "swe_hop_bwd_dst")
+
+
+def hop_bwd_src(da, s, t_rowptr, t_pos, dst, wet_src, wet_dst, src_lo, n_src, with_gradient, accumulate, g_io, F):
+    _check(load().swe_hop_bwd_src(_addr(da), ptr(s), ptr(t_rowptr, torch.int32), ptr(t_pos, torch.int32),
+                                  ptr(dst, torch.int32), ptr(wet_src, torch.uint8), ptr(wet_dst, torch.uint8), src_lo,
+                                  n_src, int(with_gradient), int(accumulate), _addr(g_io), F, _stream()),
+           "swe_hop_bwd_src")
+
+
+def edge_to_node_sum(e, rowptr, pos, node_lo, n_nodes, out, accumulate, F):
+    _check(load().swe_edge_to_node_sum(ptr(e), ptr(rowptr, torch.int32), ptr(pos, torch.int32), node_lo, n_nodes,
+                                       _addr(out), int(accumulate), F, _stream()), "swe_edge_to_node_sum")
+
+
+def pool_mean_bwd(g, f_rowptr, coarse, fine_lo, n_fine, pool_rowptr, coarse_lo, dx, accumulate, F):
+    _check(load().swe_pool_mean_bwd(_addr(g), ptr(f_rowptr, torch.int32), ptr(coarse, torch.int32), fine_lo, n_fine,
+                                    ptr(pool_rowptr, torch.int32), coarse_lo, _addr(dx), int(accumulate), F, _stream()),
+           "swe_pool_mean_bwd")
+
+
+def static_inputs_fwd(x, perm, n_nodes, n_static_raw, with_wl, xin_s):
+    _check(load().swe_static_inputs_fwd(ptr(x), x.shape[1], ptr(perm, torch.int32), n_nodes, n_static_raw, int(with_wl),
+                                        ptr(xin_s), xin_s.shape[1], _stream()), "swe_static_inputs_fwd")
+
+
+def node_inputs_bwd(dxin_s, dxin_d, n_cols, perm, n_nodes, n_dyn_rows, n_static_raw, with_wl, dx):
+    _check(load().swe_node_inputs_bwd(ptr(dxin_s), dxin_s.shape[1], ptr(dxin_d), dxin_d.shape[1], n_cols,
+                                      ptr(perm, torch.int32), n_nodes, n_dyn_rows, n_static_raw, int(with_wl), ptr(dx),
+                                      _stream()), "swe_node_inputs_bwd")
+
+
+def head_fwd(pre3, act, slope, x0, perm, n_nodes, previous_t, res_mode, res_w, eps, pred):
+    _check(load().swe_head_fwd(ptr(pre3), pre3.shape[1], act, ptr(slope), ptr(x0), x0.shape[1], ptr(perm, torch.int32),
+                               n_nodes, previous_t, res_mode, ptr(res_w), float(eps), ptr(pred), _stream()),
+           "swe_head_fwd")
+
+
+def head_bwd(dpred, pre3, act, slope, x0, perm, n_nodes, previous_t, res_mode, res_w, eps, dh3, dx0, res_part):
+    g = C.c_int32(0)
+    _check(load().swe_head_bwd(ptr(dpred), ptr(pre3), pre3.shape[1], act, ptr(slope), ptr(x0), x0.shape[1],
+                               ptr(perm, torch.int32), n_nodes, previous_t, res_mode, ptr(res_w), float(eps), ptr(dh3),
+                               ptr(dx0), ptr(res_part), C.byref(g), _stream()), "swe_head_bwd")
+    return g.value

@@ -1,0 +1,177 @@
+"""GPU parity of the training path (forward that saves pre-activations + hand-written backward
+kernels) against torch.autograd run on the oracle (which restates the reference's forward; the
+reference's backward IS torch.autograd on that forward, training/train.py:125-145).
+
+Tolerances: gradients are compared in relative L2 norm per tensor against the fp64 oracle; the
+fp32 oracle's own distance to fp64 on the same quantity is the yard-stick (we must be within a
+small multiple of it, with a floor of 2e-4 for tiny-norm tensors dominated by cancellation).
+"""
+import copy
+
+import pytest
+import torch
+
+from helpers import REF_CONFIG_MODELS, rel_l2
+from mswe_gnn_b200 import lib
+from mswe_gnn_b200.utils.synthetic import make_single_scale_mesh, make_tri_mesh
+from oracle import swe_oracle as O
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda"
+
+
+def _sd_grad(model, dtype):
+    return {k: v.detach().cpu().to(dtype).clone().requires_grad_(True) for k, v in model.state_dict().items()}
+
+
+def _check_grads(ours: dict, ref64: dict, ref32: dict, floor=2e-4, mult=20.0):
+    worst = ("", 0.0)
+    for k, g64 in ref64.items():
+        if g64 is None:
+            continue
+        g = ours[k]
+        assert g is not None, f"no gradient for {k}"
+        if float(g64.norm()) == 0.0:
+            assert float(g.norm()) < 1e-6, k
+            continue
+        e = rel_l2(g.cpu(), g64)
+        yard = rel_l2(ref32[k], g64) if ref32.get(k) is not None else 0.0
+        assert e <= max(floor, mult * yard), f"{k}: rel-L2 {e:.3e} (fp32 oracle yard-stick {yard:.3e})"
+        if e > worst[1]:
+            worst = (k, e)
+    return worst
+
+
+@pytest.mark.parametrize("kw", [
+    dict(edge_features=16, K=2, normalize=True, with_filter_matrix=True, with_gradient=True),
+    dict(edge_features=16, K=3, normalize=False, with_filter_matrix=True, with_gradient=True),
+    dict(edge_features=0, K=1, normalize=True, with_filter_matrix=False, with_gradient=False),
+    dict(edge_features=16, K=1, normalize=True, with_filter_matrix=False, with_gradient=True),
+])
+def test_swegnn_operator_backward_vs_oracle_autograd(kw):
+    from mswe_gnn_b200.models.gnn import SWEGNN
+    torch.manual_seed(3)
+    F = 16
+    d = make_single_scale_mesh(14, 9, seed=2)
+    n, e = d.x.shape[0], d.edge_index.shape[1]
+    xs = torch.randn(n, F)
+    xd = torch.randn(n, F)
+    xd[torch.rand(n) < 0.4] = 0.0                       # dry nodes: exercises the wet-edge mask in the backward
+    ea = torch.randn(e, F)
+    R = torch.randn(n, F)
+    op = SWEGNN(F, F, n_layers=2, activation="prelu", bias=True, **kw).to(DEV)
+    has_e = kw["edge_features"] > 0
+    # ours
+    xs_g, xd_g = xs.to(DEV).requires_grad_(True), xd.to(DEV).requires_grad_(True)
+    ea_g = ea.to(DEV).requires_grad_(True) if has_e else None
+    out = op(xs_g, xd_g, d.edge_index.to(DEV), ea_g)
+    (out * R.to(DEV)).sum().backward()
+    ours = {"x_s": xs_g.grad, "x_d": xd_g.grad}
+    if has_e:
+        ours["edge_attr"] = ea_g.grad
+    ours.update({"p::" + k: p.grad for k, p in op.named_parameters()})
+    # oracle in fp64 and fp32
+    refs = []
+    for dt in (torch.float64, torch.float32):
+        sd = {"op." + k: v.detach().cpu().to(dt).requires_grad_(True) for k, v in op.state_dict().items()}
+        a, b = xs.to(dt).requires_grad_(True), xd.to(dt).requires_grad_(True)
+        c = ea.to(dt).requires_grad_(True) if has_e else None
+        o = O.swegnn(sd, "op", a, b, d.edge_index, c, kw["K"], 2, "prelu", kw["edge_features"], kw["normalize"],
+                     kw["with_filter_matrix"], kw["with_gradient"])
+        (o * R.to(dt)).sum().backward()
+        r = {"x_s": a.grad, "x_d": b.grad}
+        if has_e:
+            r["edge_attr"] = c.grad
+        r.update({"p::" + k[3:]: v.grad for k, v in sd.items()})
+        refs.append(r)
+        if dt == torch.float64:
+            assert rel_l2(out.detach().cpu(), o.detach()) < 1e-5
+    _check_grads(ours, refs[0], refs[1])
+
+
+def _train_compare(model_type, ctor, data, rollout_steps):
+    from mswe_gnn_b200.models.gnn import GNN, MSGNN
+    from mswe_gnn_b200.utils.dataset import use_prediction
+    cls = MSGNN if model_type == "MSGNN" else GNN
+    model = cls(**ctor).to(DEV)
+    g = data.to(DEV)
+    n_dyn = model.previous_t * 2
+    # ours: the reference's training_step loop (train.py:125-145) around our model
+    x = g.x.clone()
+    losses = []
+    for i in range(rollout_steps):
+        xd = x[:, -n_dyn:].clone()
+        xd[g.node_BC, (int(g.type_BC) - 1)::2] = g.BC[:, :, i]
+        g.x = torch.cat((x[:, :-n_dyn], xd), 1)
+        p = model(g)
+        x = use_prediction(g.x, p, model.previous_t)
+        losses.append(_loss(p, g.y[:, :, i], g))
+    loss = torch.stack(losses).mean()
+    loss.backward()
+    ours = {k: p.grad for k, p in model.named_parameters()}
+    spec = O.ModelSpec(model_type, **ctor)
+    refs, ref_loss = [], None
+    for dt in (torch.float64, torch.float32):
+        sd = _sd_grad(model, dt)
+        dd = data.clone()
+        for k in dd.keys():
+            v = getattr(dd, k)
+            if torch.is_tensor(v) and v.is_floating_point():
+                setattr(dd, k, v.to(dt))
+        l = O.training_step(sd, spec, dd, rollout_steps, hoisted=False)
+        l.backward()
+        refs.append({k: v.grad for k, v in sd.items()})
+        if dt == torch.float64:
+            ref_loss = float(l)
+    assert abs(float(loss) - ref_loss) <= 2e-5 * max(1.0, abs(ref_loss)), (float(loss), ref_loss)
+    return _check_grads(ours, refs[0], refs[1])
+
+
+def _loss(preds, real, graph):
+    """training/loss.py:76-118 (conservation = 0) in torch on the [N, 2] predictions — the loss stays
+    PyTorch (SURVEY.md §8f 'next'); autograd hands d loss / d pred to the backward kernels."""
+    diff = preds - real
+    if hasattr(graph, "node_ptr") and graph.node_ptr is not None:
+        ptr = graph.node_ptr.reshape(-1, graph.node_ptr.shape[-1])
+        diff = torch.cat([diff[int(ptr[k, 0]):int(ptr[k, 1])] for k in range(ptr.shape[0])])
+    diff = diff[(diff != 0).any(1)]
+    per_var = diff.pow(2).mean(0).sqrt()
+    w = torch.tensor([1.0, 7.0], device=diff.device)
+    return torch.dot(per_var, w) / w.sum()
+
+
+def test_msgnn_training_step_two_rollout_steps_vs_oracle():
+    ctor = dict(num_node_features=8, num_edge_features=1, num_scales=3, previous_t=3, hid_features=32, mlp_layers=2,
+                seed=11, learned_residuals=True, mlp_activation="prelu", gnn_activation="tanh", with_WL=True, K=2)
+    data = make_tri_mesh(16, 12, 3, rollout_steps=2, seed=4)
+    _train_compare("MSGNN", ctor, data, 2)
+
+
+def test_msgnn_default_config_training_step_vs_oracle():
+    ctor = dict(num_node_features=8, num_edge_features=1, num_scales=4, previous_t=3, **REF_CONFIG_MODELS)
+    data = make_tri_mesh(16, 16, 4, rollout_steps=1, seed=5)
+    _train_compare("MSGNN", ctor, data, 1)
+
+
+def test_gnn_training_step_vs_oracle():
+    ctor = dict(num_node_features=8, num_edge_features=1, previous_t=3, hid_features=32, K=3, n_GNN_layers=2,
+                mlp_layers=2, seed=7, learned_residuals="all", mlp_activation="prelu", gnn_activation="prelu",
+                with_WL=True)
+    data = make_single_scale_mesh(18, 14, rollout_steps=2, seed=6)
+    _train_compare("GNN", ctor, data, 2)
+
+
+def test_backward_is_deterministic():
+    from mswe_gnn_b200.models.gnn import MSGNN
+    ctor = dict(num_node_features=8, num_edge_features=1, num_scales=3, previous_t=3, hid_features=32, mlp_layers=2,
+                seed=11, learned_residuals=True, with_WL=True, K=2)
+    data = make_tri_mesh(24, 16, 3, rollout_steps=1, seed=9).to(DEV)
+    model = MSGNN(**ctor).to(DEV)
+    runs = []
+    for _ in range(2):
+        model.zero_grad(set_to_none=True)
+        p = model(data)
+        (p * p).sum().backward()
+        runs.append([q.grad.clone() for q in model.parameters()])
+    for a, b in zip(*runs):
+        assert torch.equal(a, b)
