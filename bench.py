@@ -281,7 +281,7 @@ def profile_kernels(runner, alg):
     from mswe_gnn_b200 import lib
     records = []
     orig = {}
-    names = ["node_encode_fwd", "edge_gate_fwd", "edge_gate_tc_fwd", "node_linear_fwd", "propagate_hop_fwd", "pool_mean_fwd",
+    names = ["node_encode_fwd", "edge_gate_fwd", "edge_gate_tc_fwd", "node_linear_fwd", "propagate_hop_fwd", "propagate_hop_tc_fwd", "pool_mean_fwd",
              "decode_head_fwd", "edge_encode_fwd", "apply_bc", "step_advance"]
 
     def wrap(name):
@@ -294,7 +294,7 @@ def profile_kernels(runner, alg):
             r = fn(*a, **k)
             e1.record()
             meta = None
-            if name == "propagate_hop_fwd":
+            if name in ("propagate_hop_fwd", "propagate_hop_tc_fwd"):
                 meta = ("hop", int(a[6]), a[7] is not None)          # n_dst, has filter
             elif name in ("edge_gate_fwd", "edge_gate_tc_fwd"):
                 meta = ("gate", int(a[6]), a[3] is not None)         # n_edges, has edge features

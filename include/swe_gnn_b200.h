@@ -150,6 +150,19 @@ int swe_edge_gate_tc_fwd(const float* xs, const float* xd_src, const float* xd_d
                          int32_t k1, const int32_t* act3, const float* const* slope3, int32_t normalize,
                          float* s_out, float* dbg, void* stream);
 
+/* ---------------------------------------------------------------------------------------------
+ * Hop with the F×F filter on tcgen05 tensor cores (F = 64; 3xTF32, fp32 accumulation in TMEM).
+ * Same contract and reference span as swe_propagate_hop_fwd with wt != NULL (models/gnn.py:428-443);
+ * the aggregation is bit-identical to it, the filter product differs by ~1e-7 relative.
+ * ------------------------------------------------------------------------------------------- */
+size_t swe_hop_tc_image_bytes(void);
+/* w: filter_matrix[k].weight, torch layout [64, 64] -> pre-swizzled hi|lo TF32 image */
+int swe_hop_tc_pack(const float* w, void* image, void* stream);
+int swe_propagate_hop_tc_fwd(const float* o_src, const float* o_dst, const float* s, const int32_t* rowptr,
+                             const int32_t* src, int32_t dst_lo, int32_t n_dst, const void* w_image,
+                             int32_t with_gradient, int32_t upwind, const float* addend, int32_t act,
+                             const float* slope, float* agg_out, float* out, void* stream);
+
 /* out[dst_lo + i] = x[dst_lo + i] · Wᵀ for i < n_rows.  Replaces models/gnn.py:401-402
  * (filter_matrix[0]).  wt is the packed (k-major) F×F weight. */
 int swe_node_linear_fwd(const float* x, int32_t row_lo, int32_t n_rows, const float* wt, float* out,

@@ -124,7 +124,9 @@ __device__ __forceinline__ float leaky_slope(int act, const float* slope_p) {
 template <bool GENERIC>
 __global__ void __launch_bounds__(N_THREADS, 1) edge_gate_tc_kernel(const __grid_constant__ GateTcParams p) {
     extern __shared__ unsigned char smem_raw[];
-    unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    // 1 KB alignment by OFFSETTING the shared array: integer arithmetic on the pointer value loses the address
+    // space and turns every later shared access into a generic LD/ST
+    unsigned char* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
     unsigned char* a_ring = smem;
     unsigned char* w_ring = smem + (size_t)A_STAGES * SLOT_BYTES;
     float* s_bias = reinterpret_cast<float*>(w_ring + (size_t)W_STAGES * SLOT_BYTES);

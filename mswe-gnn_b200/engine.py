@@ -141,6 +141,22 @@ class PackedFilters:
         self.F, self.FP = F, FP
         self._stamp = None
         self._buf = None
+        self._tc_stamp = None
+        self._tc_img = None
+
+    def tc_images(self) -> List[torch.Tensor]:
+        """Pre-swizzled hi|lo TF32 images of W_0..W_K for the tcgen05 hop kernel (F = 64 only)."""
+        stamp = tuple((l.weight.data_ptr(), l.weight._version) for l in self.linears)
+        if stamp != self._tc_stamp:
+            dev = self.linears[0].weight.device
+            nb = lib.hop_tc_image_bytes()
+            if self._tc_img is None or self._tc_img.device != dev:
+                self._tc_img = torch.empty(len(self.linears), nb, dtype=torch.uint8, device=dev)
+            with torch.no_grad():
+                for i, lin in enumerate(self.linears):
+                    lib.hop_tc_pack(lin.weight.detach().contiguous(), self._tc_img[i])
+            self._tc_stamp = stamp
+        return [self._tc_img[i] for i in range(len(self.linears))]
 
     def tensors(self) -> List[torch.Tensor]:
         stamp = tuple((l.weight.data_ptr(), l.weight._version) for l in self.linears)
@@ -198,6 +214,12 @@ class PackedGateTC:
         codes = [ACT_CODES[activation_name_of(a)] for a in self.acts]
         slopes = [a.weight if isinstance(a, nn.PReLU) else None for a in self.acts]
         return codes, slopes
+
+
+def hop_backend() -> str:
+    """'tc' (tcgen05 filter, default for F = 64) or 'ffma' (exact-fp32 CUDA cores)."""
+    import os
+    return os.environ.get("MSWE_HOP", "tc")
 
 
 def gate_backend() -> str:
@@ -264,10 +286,17 @@ class SweGnnLauncher:
         if K > 1 and es.src_lo != es.dst_lo:
             raise NotImplementedError("multi-hop propagation needs source and destination in the same node set")
         bufs = [tmp_b, tmp_a] if o_src is tmp_a else [tmp_a, tmp_b]
+        use_tc = m.with_filter_matrix and self.F == 64 and FP == 64 and hop_backend() == "tc"
+        Wtc = self.filters.tc_images() if use_tc else None
         for k in range(K):
             last = k == K - 1
             dst_buf = out if last else bufs[k % 2]
-            lib.propagate_hop_fwd(o_src, o_dst, s_buf, es.rowptr, es.src, es.dst_lo, es.n_dst, W[k + 1],
-                                  m.with_gradient, m.upwind_mode, addend if last else None,
-                                  act_code if last else 0, act_slope if last else None, dst_buf, FP)
+            if use_tc:
+                lib.propagate_hop_tc_fwd(o_src, o_dst, s_buf, es.rowptr, es.src, es.dst_lo, es.n_dst, Wtc[k + 1],
+                                         m.with_gradient, m.upwind_mode, addend if last else None,
+                                         act_code if last else 0, act_slope if last else None, None, dst_buf)
+            else:
+                lib.propagate_hop_fwd(o_src, o_dst, s_buf, es.rowptr, es.src, es.dst_lo, es.n_dst, W[k + 1],
+                                      m.with_gradient, m.upwind_mode, addend if last else None,
+                                      act_code if last else 0, act_slope if last else None, dst_buf, FP)
             o_src = o_dst = dst_buf

@@ -63,6 +63,9 @@ SIGNATURES = {
     "swe_gate_tc_pack": (C.c_int, [_p, _i32, _p, _p, _p, _p, _p, _p, _p]),
     "swe_edge_gate_tc_fwd": (C.c_int, [_p, _p, _p, _p, _p, _p, _i64, _p, _i32, C.POINTER(C.c_int32),
                                        C.POINTER(C.c_void_p), _i32, _p, _p, _p]),
+    "swe_hop_tc_image_bytes": (_sz, []),
+    "swe_hop_tc_pack": (C.c_int, [_p, _p, _p]),
+    "swe_propagate_hop_tc_fwd": (C.c_int, [_p, _p, _p, _p, _p, _i32, _i32, _p, _i32, _i32, _p, _i32, _p, _p, _p, _p]),
     "swe_node_linear_fwd": (C.c_int, [_p, _i32, _i32, _p, _p, _i32, _p]),
     "swe_propagate_hop_fwd": (C.c_int, [_p, _p, _p, _p, _p, _i32, _i32, _p, _i32, _i32, _p, _i32, _p, _p, _i32, _p]),
     "swe_pool_mean_fwd": (C.c_int, [_p, _p, _p, _i32, _i32, _p, _i32, _p]),
@@ -224,6 +227,22 @@ def propagate_hop_fwd(o_src, o_dst, s, rowptr, src, dst_lo, n_dst, wt, with_grad
                                         ptr(src, torch.int32), dst_lo, n_dst, ptr(wt), int(with_gradient),
                                         int(upwind), ptr(addend), act, ptr(slope), ptr(out), F, _stream()),
            "swe_propagate_hop_fwd")
+
+
+def hop_tc_image_bytes() -> int:
+    return int(load().swe_hop_tc_image_bytes())
+
+
+def hop_tc_pack(w, image):
+    _check(load().swe_hop_tc_pack(ptr(w), image.data_ptr(), _stream()), "swe_hop_tc_pack")
+
+
+def propagate_hop_tc_fwd(o_src, o_dst, s, rowptr, src, dst_lo, n_dst, w_image, with_gradient, upwind, addend, act,
+                         slope, agg_out, out):
+    _check(load().swe_propagate_hop_tc_fwd(ptr(o_src), ptr(o_dst), ptr(s), ptr(rowptr, torch.int32),
+                                           ptr(src, torch.int32), dst_lo, n_dst, w_image.data_ptr(), int(with_gradient),
+                                           int(upwind), ptr(addend), act, ptr(slope), ptr(agg_out), ptr(out),
+                                           _stream()), "swe_propagate_hop_tc_fwd")
 
 
 def pool_mean_fwd(x, rowptr, fine, coarse_lo, n_coarse, out, F):
