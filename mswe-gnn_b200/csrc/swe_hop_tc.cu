@@ -14,21 +14,33 @@
 //   3. agg is split error-free into TF32 hi/lo and stored as the A operand (UMMA K-major SWIZZLE_128B);
 //      one thread issues agg·Wᵀ as 3xTF32 (A_lo·W_hi + A_hi·W_lo + A_hi·W_hi), fp32 accumulation in TMEM;
 //   4. epilogue: thread = (TMEM lane = node, 32 columns): tcgen05.ld, + o[c] (+ addend), activation, store.
+#include <stdlib.h>
 #include "swe_tc.cuh"
 
 namespace swe {
 namespace tc {
 
 constexpr int HF = 64;                         // feature width
-constexpr int HOP_THREADS = 256;
 constexpr int HOP_TILE = 128;
 constexpr int HOP_KC = 32;                     // k elements per 128-byte swizzled row
 constexpr int HOP_A_TILE = HOP_TILE * 128;     // bytes of one [128 x 32] tf32 tile
+constexpr int HOP_A_SLOT = 4 * HOP_A_TILE;     // 2 chunks x (hi | lo) = 64 KB
 constexpr int HOP_W_TILE = HF * 128;           // bytes of one [64 x 32] tf32 tile
 constexpr int HOP_SRC_CAP = 1024;              // staged src ids per tile (more -> read from global)
+constexpr int HOP_GATHER_WARPS = 16;
+constexpr int HOP_GATHER_THREADS = HOP_GATHER_WARPS * 32;      // 512: 32 groups of 16 lanes, 4 nodes per group per tile
+constexpr int HOP_EPI_WARPS = 4;               // warps 16-19: one TMEM lane quarter each
+constexpr int HOP_THREADS = HOP_GATHER_THREADS + HOP_EPI_WARPS * 32;        // 640 (20 warps: 96 registers each)
 constexpr size_t HOP_W_IMAGE = 2 * 2 * (size_t)HOP_W_TILE;      // 2 chunks x (hi | lo) = 32 KB
-constexpr size_t HOP_TC_SMEM = 1024 + 2 * 2 * (size_t)HOP_A_TILE + HOP_W_IMAGE +
-                               sizeof(int32_t) * (HOP_TILE + 4 + HOP_SRC_CAP) + 64;
+constexpr int HOP_CSR_INTS = HOP_TILE + 4 + HOP_SRC_CAP;        // rowptr slice (129, padded) + src slice
+
+struct __align__(8) HopBarriers {
+    uint64_t a_full[2], a_empty[2];    // A-operand slot written (512 arrivals) / consumed by the MMA (commit)
+    uint64_t d_full[2], d_empty[2];    // accumulator slot complete (commit) / drained by the epilogue (128 arrivals)
+};
+
+constexpr size_t HOP_TC_SMEM = 1024 + 2 * (size_t)HOP_A_SLOT + HOP_W_IMAGE + sizeof(int32_t) * 2 * HOP_CSR_INTS +
+                               sizeof(HopBarriers) + 16;
 
 __global__ void hop_tc_pack_kernel(const float* __restrict__ w, unsigned char* __restrict__ img) {
     for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < HF * HF; idx += gridDim.x * blockDim.x) {
@@ -52,203 +64,250 @@ struct HopTcParams {
     int act; const float* slope;
     float* out;
     float* agg_out;
-    long long* trace;           // optional [32 tiles][12 events] clock64 stamps of CTA 0 / thread 0 (profiling aid)
+    long long* trace;           // optional [3 roles][16 tiles][8 events] clock64 stamps of CTA 0 (profiling aid)
 };
 
-struct NodeAcc { float4 acc; };
+__device__ __forceinline__ void cp_async4(void* smem_dst, const void* gmem_src) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;\n" ::"r"(smem_u32(smem_dst)), "l"(gmem_src));
+}
 
-// first (up to) 4 edges of two nodes in flight together, remaining edges (rare) sequentially
-__device__ __forceinline__ void aggregate2(const HopTcParams& p, const int32_t* __restrict__ s_src, bool staged, int p_base,
-                                           int pa0, int pa1, int pb0, int pb1, float4 oca, float4 ocb, int q,
-                                           float4& acca, float4& accb) {
-    auto src_of = [&](int pp) -> int { return staged ? s_src[pp - p_base] : __ldg(p.src + pp); };
-    auto term = [&](const float4 oc, const float4 orow, const float4 sv) -> float4 {
-        float4 t;
-        if (p.with_gradient) {
-            float4 d = make_float4(__fsub_rn(oc.x, orow.x), __fsub_rn(oc.y, orow.y), __fsub_rn(oc.z, orow.z), __fsub_rn(oc.w, orow.w));
-            if (p.upwind) { d.x = fmaxf(d.x, 0.f); d.y = fmaxf(d.y, 0.f); d.z = fmaxf(d.z, 0.f); d.w = fmaxf(d.w, 0.f); }
-            t = make_float4(__fmul_rn(d.x, sv.x), __fmul_rn(d.y, sv.y), __fmul_rn(d.z, sv.z), __fmul_rn(d.w, sv.w));
-        } else {
-            t = make_float4(__fmul_rn(sv.x, orow.x), __fmul_rn(sv.y, orow.y), __fmul_rn(sv.z, orow.z), __fmul_rn(sv.w, orow.w));
-        }
-        return t;
-    };
-    auto add = [](float4& a, const float4 t) {
-        a.x = __fadd_rn(a.x, t.x); a.y = __fadd_rn(a.y, t.y); a.z = __fadd_rn(a.z, t.z); a.w = __fadd_rn(a.w, t.w);
-    };
-    int ra[4], rb[4];
-#pragma unroll
-    for (int u = 0; u < 4; ++u) {
-        ra[u] = (pa0 + u < pa1) ? src_of(pa0 + u) : -1;
-        rb[u] = (pb0 + u < pb1) ? src_of(pb0 + u) : -1;
+constexpr int HOP_EB = 3;       // edges of a node fetched in one batch (dual triangular meshes: in-degree <= 3 (+1 ghost edge))
+
+template <bool WG, bool UP>
+__device__ __forceinline__ float4 hop_term(const float4 oc, const float4 orow, const float4 sv) {
+    if (WG) {                                          // (o[c] − o[r]) · s   (gnn.py:430-433)
+        float4 d = make_float4(__fsub_rn(oc.x, orow.x), __fsub_rn(oc.y, orow.y), __fsub_rn(oc.z, orow.z), __fsub_rn(oc.w, orow.w));
+        if (UP) { d.x = fmaxf(d.x, 0.f); d.y = fmaxf(d.y, 0.f); d.z = fmaxf(d.z, 0.f); d.w = fmaxf(d.w, 0.f); }
+        return make_float4(__fmul_rn(d.x, sv.x), __fmul_rn(d.y, sv.y), __fmul_rn(d.z, sv.z), __fmul_rn(d.w, sv.w));
     }
-    float4 oa[4], sa[4], ob[4], sb[4];
+    return make_float4(__fmul_rn(sv.x, orow.x), __fmul_rn(sv.y, orow.y), __fmul_rn(sv.z, orow.z), __fmul_rn(sv.w, orow.w));
+}
+__device__ __forceinline__ void hop_add(float4& a, const float4 t) {      // sequential, in edge order
+    a.x = __fadd_rn(a.x, t.x); a.y = __fadd_rn(a.y, t.y); a.z = __fadd_rn(a.z, t.z); a.w = __fadd_rn(a.w, t.w);
+}
+
+// First HOP_EB edges of two nodes in flight together (up to 12 independent 16-byte loads + the two o[c]);
+// further edges (rare) sequentially.  src ids come from `ids` (shared memory when staged, global otherwise),
+// indexed by p - id_base.
+template <bool WG, bool UP>
+__device__ __forceinline__ void aggregate2(const float* __restrict__ o_src, const float* __restrict__ s,
+                                           const int32_t* __restrict__ ids, int id_base,
+                                           int pa0, int pa1, int pb0, int pb1, const float4 oca, const float4 ocb, int q4,
+                                           float4& acca, float4& accb) {
+    float4 oa[HOP_EB], sa[HOP_EB], ob[HOP_EB], sb[HOP_EB];
 #pragma unroll
-    for (int u = 0; u < 4; ++u) {
-        if (ra[u] >= 0) {
-            oa[u] = ldg4(p.o_src + (long long)ra[u] * HF + 4 * q);
-            sa[u] = ldg4_stream(p.s + (long long)(pa0 + u) * HF + 4 * q);
+    for (int u = 0; u < HOP_EB; ++u) {
+        if (pa0 + u < pa1) {
+            oa[u] = ldg4(o_src + (long long)ids[pa0 + u - id_base] * HF + q4);
+            sa[u] = ldg4_stream(s + (long long)(pa0 + u) * HF + q4);
         }
-        if (rb[u] >= 0) {
-            ob[u] = ldg4(p.o_src + (long long)rb[u] * HF + 4 * q);
-            sb[u] = ldg4_stream(p.s + (long long)(pb0 + u) * HF + 4 * q);
+        if (pb0 + u < pb1) {
+            ob[u] = ldg4(o_src + (long long)ids[pb0 + u - id_base] * HF + q4);
+            sb[u] = ldg4_stream(s + (long long)(pb0 + u) * HF + q4);
         }
     }
     acca = make_float4(0.f, 0.f, 0.f, 0.f);
     accb = acca;
 #pragma unroll
-    for (int u = 0; u < 4; ++u) {
-        if (ra[u] >= 0) add(acca, term(oca, oa[u], sa[u]));
-        if (rb[u] >= 0) add(accb, term(ocb, ob[u], sb[u]));
+    for (int u = 0; u < HOP_EB; ++u) {
+        if (pa0 + u < pa1) hop_add(acca, hop_term<WG, UP>(oca, oa[u], sa[u]));
+        if (pb0 + u < pb1) hop_add(accb, hop_term<WG, UP>(ocb, ob[u], sb[u]));
     }
-    for (int pp = pa0 + 4; pp < pa1; ++pp) {
-        const int r = src_of(pp);
-        add(acca, term(oca, ldg4(p.o_src + (long long)r * HF + 4 * q), ldg4_stream(p.s + (long long)pp * HF + 4 * q)));
-    }
-    for (int pp = pb0 + 4; pp < pb1; ++pp) {
-        const int r = src_of(pp);
-        add(accb, term(ocb, ldg4(p.o_src + (long long)r * HF + 4 * q), ldg4_stream(p.s + (long long)pp * HF + 4 * q)));
-    }
+    for (int pp = pa0 + HOP_EB; pp < pa1; ++pp)
+        hop_add(acca, hop_term<WG, UP>(oca, ldg4(o_src + (long long)ids[pp - id_base] * HF + q4), ldg4_stream(s + (long long)pp * HF + q4)));
+    for (int pp = pb0 + HOP_EB; pp < pb1; ++pp)
+        hop_add(accb, hop_term<WG, UP>(ocb, ldg4(o_src + (long long)ids[pp - id_base] * HF + q4), ldg4_stream(s + (long long)pp * HF + q4)));
 }
 
-__global__ void __launch_bounds__(HOP_THREADS, 2) hop_tc_kernel(const __grid_constant__ HopTcParams p) {
+// Persistent, one CTA per SM, warp-specialised:
+//   warps 0-15  gather    : stage the tile's CSR slice (cp.async, one tile ahead), aggregate, write the A operand
+//   warps 16-19 epilogue  : D (TMEM) -> + o[c] (+ addend) -> activation -> out; lane 0 of warp 16 also issues
+//                           the 24 tcgen05.mma of each tile (3xTF32); its commits release the A slot / publish D
+// A-operand slots and TMEM accumulators are double-buffered, so the gather warps never wait for the tensor
+// pipe or the epilogue in steady state — they are the only part that is bound by memory.
+template <bool WG, bool UP, bool TRACE>
+__global__ void __launch_bounds__(HOP_THREADS, 1) hop_tc_kernel(const __grid_constant__ HopTcParams p) {
     extern __shared__ unsigned char smem_raw[];
     // 1 KB alignment by OFFSETTING the shared array (integer arithmetic on the pointer value would turn every
     // later access into a generic LD/ST instead of LDS/STS)
     unsigned char* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
-    unsigned char* a_tile = smem;                                  // chunk c: [hi 16 KB | lo 16 KB]
-    unsigned char* w_tile = smem + 4 * (size_t)HOP_A_TILE;         // chunk c: [hi 8 KB | lo 8 KB]
-    int32_t* s_rp = reinterpret_cast<int32_t*>(w_tile + HOP_W_IMAGE);          // [129 (+3 pad)]
-    int32_t* s_src = s_rp + HOP_TILE + 4;                          // [HOP_SRC_CAP]
-    uint64_t* d_full = reinterpret_cast<uint64_t*>(s_src + HOP_SRC_CAP);
-    uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(d_full + 1);
+    unsigned char* a_slots = smem;                                  // slot s: chunk c: [hi 16 KB | lo 16 KB]
+    unsigned char* w_tile = smem + 2 * (size_t)HOP_A_SLOT;          // chunk c: [hi 8 KB | lo 8 KB]
+    int32_t* s_csr = reinterpret_cast<int32_t*>(w_tile + HOP_W_IMAGE);         // 2 x [rowptr 132 | src 1024]
+    HopBarriers* bar = reinterpret_cast<HopBarriers*>(s_csr + 2 * HOP_CSR_INTS);
+    uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(bar + 1);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    if (threadIdx.x == 0) { mbar_init(d_full, 1); fence_barrier_init(); }
+    if (threadIdx.x == 0) {
+        for (int i = 0; i < 2; ++i) {
+            mbar_init(&bar->a_full[i], HOP_GATHER_THREADS); mbar_init(&bar->a_empty[i], 1);
+            mbar_init(&bar->d_full[i], 1); mbar_init(&bar->d_empty[i], HOP_EPI_WARPS * 32);
+        }
+        fence_barrier_init();
+    }
     for (int i = threadIdx.x * 16; i < (int)HOP_W_IMAGE; i += HOP_THREADS * 16)
         *reinterpret_cast<float4*>(w_tile + i) = *reinterpret_cast<const float4*>(p.w_img + i);
     fence_proxy_async_smem();
-    if (warp == 0) tmem_alloc(tmem_holder, 64);
+    if (warp == HOP_GATHER_WARPS) tmem_alloc(tmem_holder, 128);
     tc_fence_before_sync();
     __syncthreads();
     tc_fence_after_sync();
-    const uint32_t tmem_d = *tmem_holder;
-
-    const float slope = (p.act == SWE_ACT_PRELU && p.slope) ? __ldg(p.slope) : 0.f;
-    const int g = threadIdx.x >> 4, q = threadIdx.x & 15;          // aggregation: 16 groups x 16 lanes
-    const int chunk = q >> 3, piece = q & 7;
-    const int lq = warp & 3, hf = warp >> 2;                       // epilogue: TMEM lane quarter, column half
-    const uint32_t idesc = make_idesc_tf32(HOP_TILE, HF);
-    const uint32_t a_u32 = smem_u32(a_tile), w_u32 = smem_u32(w_tile);
+    const uint32_t tmem_base = *tmem_holder;
     const int n_tiles = (p.n_dst + HOP_TILE - 1) / HOP_TILE;
-    uint32_t phase = 0;
+    // each CTA owns a CONTIGUOUS run of tiles: it stays inside the same 2 MB pages of o / s / out for many tiles
+    // (a grid-strided assignment touches new pages every tile and pays a TLB miss per array per tile)
+    const int tpc = (n_tiles + (int)gridDim.x - 1) / (int)gridDim.x;
+    const int tile0 = (int)blockIdx.x * tpc;
+    const int n_my = max(0, min(tpc, n_tiles - tile0));
+    const bool tr0 = TRACE && p.trace != nullptr && blockIdx.x == 0 && lane == 0;
+#define SWE_STAMP(role_, i_, ev_) do { if (TRACE && tr0 && (i_) < 16) p.trace[(role_) * 128 + (i_) * 8 + (ev_)] = clock64(); } while (0)
 
-    const bool tr = p.trace != nullptr && blockIdx.x == 0 && threadIdx.x == 0;
-    int t_i = 0;
-#define SWE_STAMP(ev_) do { if (tr && t_i < 32) p.trace[t_i * 12 + (ev_)] = clock64(); } while (0)
-    for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++t_i) {
-        const int row0 = tile * HOP_TILE;
-        SWE_STAMP(0);
-        const int rows = min(HOP_TILE, p.n_dst - row0);
-        // ---- 1. stage the CSR slice of this tile
-        if (threadIdx.x <= HOP_TILE) s_rp[threadIdx.x] = __ldg(p.rowptr + row0 + min((int)threadIdx.x, rows));
-        __syncthreads();
-        const int p_base = s_rp[0], p_cnt = s_rp[HOP_TILE] - p_base;
-        const bool staged = p_cnt <= HOP_SRC_CAP;
-        if (staged)
-            for (int j = threadIdx.x; j < p_cnt; j += HOP_THREADS) s_src[j] = __ldg(p.src + p_base + j);
-        __syncthreads();
-        SWE_STAMP(1);
-        // ---- 2./3. aggregate (two nodes per thread at a time) and write the A operand
+    if (warp < HOP_GATHER_WARPS) {
+        // =====================================================================================
+        // gather warps
+        // =====================================================================================
+        const int g = threadIdx.x >> 4, q = threadIdx.x & 15;      // 32 groups x 16 lanes
+        const int chunk = q >> 3, piece = q & 7, q4 = 4 * q;
+        const bool trw = tr0 && warp == 0;
+        // swizzled byte offsets of this thread's 16-byte piece in rows g, g+32, g+64, g+96
+        const uint32_t a_off0 = sw128_offset(g, piece * 4), a_off1 = sw128_offset(g + 32, piece * 4);
+        const uint32_t a_off2 = sw128_offset(g + 64, piece * 4), a_off3 = sw128_offset(g + 96, piece * 4);
 #pragma unroll 1
-        for (int jj = 0; jj < HOP_TILE / 16; jj += 2) {
-            SWE_STAMP(2 + jj / 2);
-            const int ia = g + 16 * jj, ib = ia + 16;
-            float4 oca = make_float4(0.f, 0.f, 0.f, 0.f), ocb = oca;
-            const int pa0 = s_rp[ia], pa1 = s_rp[ia + 1], pb0 = s_rp[ib], pb1 = s_rp[ib + 1];
-            if (p.o_dst) {
-                if (ia < rows) oca = ldg4(p.o_dst + ((long long)p.dst_lo + row0 + ia) * HF + 4 * q);
-                if (ib < rows) ocb = ldg4(p.o_dst + ((long long)p.dst_lo + row0 + ib) * HF + 4 * q);
-            }
-            float4 acca, accb;
-            aggregate2(p, s_src, staged, p_base, pa0, pa1, pb0, pb1, oca, ocb, q, acca, accb);
-            if (p.agg_out) {
-                if (ia < rows) stg4(p.agg_out + ((long long)p.dst_lo + row0 + ia) * HF + 4 * q, acca);
-                if (ib < rows) stg4(p.agg_out + ((long long)p.dst_lo + row0 + ib) * HF + 4 * q, accb);
-            }
-            unsigned char* base = a_tile + (size_t)chunk * 2 * HOP_A_TILE;
-            float4 hh, ll;
-            split_tf32(acca.x, hh.x, ll.x); split_tf32(acca.y, hh.y, ll.y); split_tf32(acca.z, hh.z, ll.z); split_tf32(acca.w, hh.w, ll.w);
-            uint32_t off = sw128_offset(ia, piece * 4);
-            *reinterpret_cast<float4*>(base + off) = hh;
-            *reinterpret_cast<float4*>(base + HOP_A_TILE + off) = ll;
-            split_tf32(accb.x, hh.x, ll.x); split_tf32(accb.y, hh.y, ll.y); split_tf32(accb.z, hh.z, ll.z); split_tf32(accb.w, hh.w, ll.w);
-            off = sw128_offset(ib, piece * 4);
-            *reinterpret_cast<float4*>(base + off) = hh;
-            *reinterpret_cast<float4*>(base + HOP_A_TILE + off) = ll;
-        }
-        SWE_STAMP(6);
-        fence_proxy_async_smem();
-        tc_fence_before_sync();
-        __syncthreads();
-        SWE_STAMP(7);
-        // ---- filter on the tensor core: D[128 x 64] = agg · Wᵀ (3xTF32)
-        if (threadIdx.x == 0) {
-            tc_fence_after_sync();
-#pragma unroll
-            for (int c = 0; c < 2; ++c) {
-                const uint32_t a_hi = a_u32 + c * 2 * HOP_A_TILE, a_lo = a_hi + HOP_A_TILE;
-                const uint32_t w_hi = w_u32 + c * 2 * HOP_W_TILE, w_lo = w_hi + HOP_W_TILE;
-#pragma unroll
-                for (int ks = 0; ks < HOP_KC / 8; ++ks) {
-                    const uint64_t dah = make_desc_sw128(a_hi + ks * 32), dal = make_desc_sw128(a_lo + ks * 32);
-                    const uint64_t dwh = make_desc_sw128(w_hi + ks * 32), dwl = make_desc_sw128(w_lo + ks * 32);
-                    mma_tf32_ss(tmem_d, dal, dwh, idesc, (c | ks) ? 1u : 0u);
-                    mma_tf32_ss(tmem_d, dah, dwl, idesc, 1u);
-                    mma_tf32_ss(tmem_d, dah, dwh, idesc, 1u);
+        for (int i = 0; i < n_my; ++i) {
+            const int slot = i & 1;
+            const uint32_t u = (uint32_t)(i >> 1);
+            const int row0 = (tile0 + i) * HOP_TILE;
+            const int rows = min(HOP_TILE, p.n_dst - row0);
+            // no CTA-wide staging / barrier here: every warp walks its own nodes (rowptr -> src -> rows) and drifts
+            // freely against the others, which keeps the memory pipe uniformly busy instead of bursty
+            const int32_t* rp = p.rowptr + row0;
+            if (trw) SWE_STAMP(0, i, 0);
+            if (trw) SWE_STAMP(0, i, 1);
+            mbar_wait(&bar->a_empty[slot], (u & 1) ^ 1);               // MMA of tile i-2 has consumed this slot
+            if (trw) SWE_STAMP(0, i, 2);
+            unsigned char* base = a_slots + (size_t)slot * HOP_A_SLOT + (size_t)chunk * 2 * HOP_A_TILE;
+            const int32_t* ids = p.src;
+            const int id_base = 0;
+            const float* orow_base = p.o_dst ? p.o_dst + ((long long)p.dst_lo + row0) * HF + q4 : nullptr;
+#pragma unroll 1
+            for (int jj = 0; jj < 2; ++jj) {
+                const int ia = g + 64 * jj, ib = ia + 32;
+                float4 oca = make_float4(0.f, 0.f, 0.f, 0.f), ocb = oca;
+                const int pa0 = __ldg(rp + min(ia, rows)), pa1 = __ldg(rp + min(ia + 1, rows));
+                const int pb0 = __ldg(rp + min(ib, rows)), pb1 = __ldg(rp + min(ib + 1, rows));
+                if (orow_base) {
+                    if (ia < rows) oca = ldg4(orow_base + ia * HF);
+                    if (ib < rows) ocb = ldg4(orow_base + ib * HF);
                 }
+                float4 acca, accb;
+                aggregate2<WG, UP>(p.o_src, p.s, ids, id_base, pa0, pa1, pb0, pb1, oca, ocb, q4, acca, accb);
+                if (p.agg_out) {
+                    if (ia < rows) stg4(p.agg_out + ((long long)p.dst_lo + row0 + ia) * HF + q4, acca);
+                    if (ib < rows) stg4(p.agg_out + ((long long)p.dst_lo + row0 + ib) * HF + q4, accb);
+                }
+                float4 hh, ll;
+                split_tf32(acca.x, hh.x, ll.x); split_tf32(acca.y, hh.y, ll.y); split_tf32(acca.z, hh.z, ll.z); split_tf32(acca.w, hh.w, ll.w);
+                const uint32_t offa = jj ? a_off2 : a_off0, offb = jj ? a_off3 : a_off1;
+                *reinterpret_cast<float4*>(base + offa) = hh;
+                *reinterpret_cast<float4*>(base + HOP_A_TILE + offa) = ll;
+                split_tf32(accb.x, hh.x, ll.x); split_tf32(accb.y, hh.y, ll.y); split_tf32(accb.z, hh.z, ll.z); split_tf32(accb.w, hh.w, ll.w);
+                *reinterpret_cast<float4*>(base + offb) = hh;
+                *reinterpret_cast<float4*>(base + HOP_A_TILE + offb) = ll;
+                if (trw) SWE_STAMP(0, i, 3 + jj);
             }
-            mma_commit(d_full);
+            fence_proxy_async_smem();
+            mbar_arrive(&bar->a_full[slot]);
         }
-        // ---- 4. epilogue
-        SWE_STAMP(8);
-        mbar_wait(d_full, phase);
-        phase ^= 1;
-        tc_fence_after_sync();
-        SWE_STAMP(9);
-        {
-            uint32_t v[32];
-            tmem_ld32(tmem_d + ((uint32_t)(lq * 32) << 16) + hf * 32, v);
-            tmem_wait_ld();
-            const int i = lq * 32 + lane;
-            if (i < rows) {
-                const long long c = (long long)p.dst_lo + row0 + i;
-                const float* od = p.o_dst ? p.o_dst + c * HF + hf * 32 : nullptr;
-                const float* ad = p.addend ? p.addend + c * HF + hf * 32 : nullptr;
-                float* o = p.out + c * HF + hf * 32;
-                float4 tod[8];                           // all loads first: the stores below may alias for the compiler
+    } else {
+        // =====================================================================================
+        // epilogue warps: thread = one TMEM lane = one node, 64 columns in two halves
+        // =====================================================================================
+        const int lq = warp & 3;
+        const float slope = (p.act == SWE_ACT_PRELU && p.slope) ? __ldg(p.slope) : 0.f;
+        const bool trw = tr0 && lq == 0;
+        const uint32_t idesc = make_idesc_tf32(HOP_TILE, HF);
+        const uint32_t a_u32 = smem_u32(a_slots), w_u32 = smem_u32(w_tile);
+#pragma unroll 1
+        for (int i = 0; i < n_my; ++i) {
+            const int slot = i & 1;
+            const uint32_t u = (uint32_t)(i >> 1);
+            if (warp == HOP_GATHER_WARPS) {
+                if (lane == 0) {
+                    SWE_STAMP(2, i, 0);
+                    mbar_wait(&bar->d_empty[slot], (u & 1) ^ 1);       // epilogue of tile i-2 has drained this accumulator
+                    mbar_wait(&bar->a_full[slot], u & 1);
+                    tc_fence_after_sync();
+                    SWE_STAMP(2, i, 1);
+                    const uint32_t d = tmem_base + slot * 64;
 #pragma unroll
-                for (int j = 0; j < 8; ++j) tod[j] = od ? ldg4(od + 4 * j) : make_float4(0.f, 0.f, 0.f, 0.f);
+                    for (int c = 0; c < 2; ++c) {
+                        const uint32_t a_hi = a_u32 + slot * HOP_A_SLOT + c * 2 * HOP_A_TILE, a_lo = a_hi + HOP_A_TILE;
+                        const uint32_t w_hi = w_u32 + c * 2 * HOP_W_TILE, w_lo = w_hi + HOP_W_TILE;
 #pragma unroll
-                for (int j = 0; j < 32; j += 4) {
-                    float4 r = make_float4(__uint_as_float(v[j]), __uint_as_float(v[j + 1]), __uint_as_float(v[j + 2]),
-                                           __uint_as_float(v[j + 3]));
-                    if (od) { const float4 t = tod[j >> 2]; r.x = t.x + r.x; r.y = t.y + r.y; r.z = t.z + r.z; r.w = t.w + r.w; }
-                    if (ad) { const float4 t = ldg4(ad + j); r.x += t.x; r.y += t.y; r.z += t.z; r.w += t.w; }
-                    if (p.act != SWE_ACT_NONE) {
-                        r.x = act_apply(p.act, r.x, slope); r.y = act_apply(p.act, r.y, slope);
-                        r.z = act_apply(p.act, r.z, slope); r.w = act_apply(p.act, r.w, slope);
+                        for (int ks = 0; ks < HOP_KC / 8; ++ks) {
+                            const uint64_t dah = make_desc_sw128(a_hi + ks * 32), dal = make_desc_sw128(a_lo + ks * 32);
+                            const uint64_t dwh = make_desc_sw128(w_hi + ks * 32), dwl = make_desc_sw128(w_lo + ks * 32);
+                            mma_tf32_ss(d, dal, dwh, idesc, (c | ks) ? 1u : 0u);
+                            mma_tf32_ss(d, dah, dwl, idesc, 1u);
+                            mma_tf32_ss(d, dah, dwh, idesc, 1u);
+                        }
                     }
-                    stg4(o + j, r);
+                    mma_commit(&bar->a_empty[slot]);
+                    mma_commit(&bar->d_full[slot]);
+                    SWE_STAMP(2, i, 2);
+                }
+                __syncwarp();
+            }
+            const int row0 = (tile0 + i) * HOP_TILE;
+            const int rows = min(HOP_TILE, p.n_dst - row0);
+            const int r = lq * 32 + lane;
+            const long long c = (long long)p.dst_lo + row0 + r;
+            const bool valid = r < rows;
+            // o[c] does not depend on the accumulator: fetch it while the MMA is still running
+            float4 tod[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) tod[j] = (valid && p.o_dst) ? ldg4(p.o_dst + c * HF + 4 * j) : make_float4(0.f, 0.f, 0.f, 0.f);
+            if (trw) SWE_STAMP(1, i, 0);
+            mbar_wait(&bar->d_full[slot], u & 1);
+            tc_fence_after_sync();
+            if (trw) SWE_STAMP(1, i, 1);
+#pragma unroll 1
+            for (int hf = 0; hf < 2; ++hf) {
+                uint32_t v[32];
+                tmem_ld32(tmem_base + ((uint32_t)(lq * 32) << 16) + slot * 64 + hf * 32, v);
+                tmem_wait_ld();
+                if (hf == 1) {                                       // accumulator slot fully read: hand it back early
+                    tc_fence_before_sync();
+                    mbar_arrive(&bar->d_empty[slot]);
+                }
+                if (valid) {
+                    const float* ad = p.addend ? p.addend + c * HF + hf * 32 : nullptr;
+                    float* o = p.out + c * HF + hf * 32;
+                    if (hf == 1 && p.o_dst) {
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) tod[j] = ldg4(p.o_dst + c * HF + 32 + 4 * j);
+                    }
+#pragma unroll
+                    for (int j = 0; j < 32; j += 4) {
+                        float4 t = tod[j >> 2];
+                        float4 rr = make_float4(t.x + __uint_as_float(v[j]), t.y + __uint_as_float(v[j + 1]),
+                                                t.z + __uint_as_float(v[j + 2]), t.w + __uint_as_float(v[j + 3]));
+                        if (ad) { const float4 a4 = ldg4(ad + j); rr.x += a4.x; rr.y += a4.y; rr.z += a4.z; rr.w += a4.w; }
+                        if (p.act != SWE_ACT_NONE) {
+                            rr.x = act_apply(p.act, rr.x, slope); rr.y = act_apply(p.act, rr.y, slope);
+                            rr.z = act_apply(p.act, rr.z, slope); rr.w = act_apply(p.act, rr.w, slope);
+                        }
+                        stg4(o + j, rr);
+                    }
                 }
             }
+            if (trw) SWE_STAMP(1, i, 2);
         }
-        tc_fence_before_sync();          // the next tile's MMA must not overwrite D before these loads retired
-        SWE_STAMP(10);
     }
 #undef SWE_STAMP
+    tc_fence_before_sync();
     __syncthreads();
-    if (warp == 0) tmem_dealloc(tmem_d, 64);
+    if (warp == HOP_GATHER_WARPS) tmem_dealloc(tmem_base, 128);
 }
 
 }  // namespace tc
@@ -292,9 +351,14 @@ extern "C" int swe_propagate_hop_tc_fwd_traced(const float* o_src, const float* 
     p.o_src = o_src; p.o_dst = o_dst; p.s = s; p.rowptr = rowptr; p.src = src; p.dst_lo = dst_lo; p.n_dst = n_dst;
     p.w_img = (const unsigned char*)w_image; p.with_gradient = with_gradient; p.upwind = upwind; p.addend = addend;
     p.act = act; p.slope = slope; p.out = out; p.agg_out = agg_out; p.trace = trace;
-    cudaError_t e = cudaFuncSetAttribute(tc::hop_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc::HOP_TC_SMEM);
+    void (*kern)(const tc::HopTcParams) = nullptr;
+    if (trace) kern = with_gradient ? (upwind ? tc::hop_tc_kernel<true, true, true> : tc::hop_tc_kernel<true, false, true>)
+                                    : tc::hop_tc_kernel<false, false, true>;
+    else kern = with_gradient ? (upwind ? tc::hop_tc_kernel<true, true, false> : tc::hop_tc_kernel<true, false, false>)
+                              : tc::hop_tc_kernel<false, false, false>;
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc::HOP_TC_SMEM);
     if (e != cudaSuccess) { set_error("hop_tc smem opt-in (%zu B): %s", tc::HOP_TC_SMEM, cudaGetErrorString(e)); return (int)e; }
     const int n_tiles = (n_dst + tc::HOP_TILE - 1) / tc::HOP_TILE;
-    tc::hop_tc_kernel<<<grid_for(n_tiles, 2), tc::HOP_THREADS, tc::HOP_TC_SMEM, (cudaStream_t)stream>>>(p);
+    kern<<<grid_for(n_tiles, 1), tc::HOP_THREADS, tc::HOP_TC_SMEM, (cudaStream_t)stream>>>(p);
     return check_launch("propagate_hop_tc_fwd");
 }

@@ -17,7 +17,9 @@ img = torch.empty(lib.hop_tc_image_bytes(), dtype=torch.uint8, device=DEV); lib.
 out = torch.empty_like(o)
 bytes_alg = 4 * 64 * (e + 2 * n) + 4 * (e + n + 1)
 def run(which):
-    if which == "ffma":
+    if which == "nofilter":
+        lib.propagate_hop_fwd(o, o, s, rowptr, src, 0, n, None, 1, 0, None, 0, None, out, 64)
+    elif which == "ffma":
         lib.propagate_hop_fwd(o, o, s, rowptr, src, 0, n, wt, 1, 0, None, 0, None, out, 64)
     else:
         lib.propagate_hop_tc_fwd(o, o, s, rowptr, src, 0, n, img, 1, 0, None, 0, None, None, out)
@@ -38,12 +40,13 @@ if os.environ.get("TRACE"):
     fn = l.swe_propagate_hop_tc_fwd_traced
     fn.restype = C.c_int
     fn.argtypes = [C.c_void_p] * 5 + [C.c_int32, C.c_int32, C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_int32] + [C.c_void_p] * 5
-    trace = torch.zeros(32 * 12, dtype=torch.int64, device=DEV)
+    trace = torch.zeros(3 * 128, dtype=torch.int64, device=DEV)
     rc = fn(o.data_ptr(), o.data_ptr(), s.data_ptr(), rowptr.data_ptr(), src.data_ptr(), 0, n, img.data_ptr(), 1, 0, None, 0, None,
             None, out.data_ptr(), trace.data_ptr(), torch.cuda.current_stream().cuda_stream)
     torch.cuda.synchronize()
-    t = trace.cpu().view(32, 12)
-    names = ["start", "staged", "r0", "r1", "r2", "r3", "agg_done", "synced", "mma_issued", "d_full", "epi_done"]
-    for tile in range(2, 10):
-        base = int(t[tile, 0])
-        print(tile, " ".join(f"{names[e]}={int(t[tile, e]) - base}" for e in range(11)), "next_start", int(t[tile + 1, 0]) - base)
+    t = trace.cpu().view(3, 16, 8)
+    t0 = int(t[0, 2, 0])
+    ev = [["start", "csr_ready", "slot_free", "round0", "round1"], ["oc_loaded", "d_full", "stored"], ["wait", "a_full", "issued"]]
+    for tile in range(2, 9):
+        for r, name in enumerate(["gather", "epilogue", "mma"]):
+            print(tile, name, " ".join(f"{ev[r][e]}={int(t[r, tile, e]) - t0}" for e in range(len(ev[r]))))
