@@ -26,21 +26,13 @@ constexpr int HOP_KC = 32;                     // k elements per 128-byte swizzl
 constexpr int HOP_A_TILE = HOP_TILE * 128;     // bytes of one [128 x 32] tf32 tile
 constexpr int HOP_A_SLOT = 4 * HOP_A_TILE;     // 2 chunks x (hi | lo) = 64 KB
 constexpr int HOP_W_TILE = HF * 128;           // bytes of one [64 x 32] tf32 tile
-constexpr int HOP_SRC_CAP = 1024;              // staged src ids per tile (more -> read from global)
 constexpr int HOP_GATHER_WARPS = 16;
 constexpr int HOP_GATHER_THREADS = HOP_GATHER_WARPS * 32;      // 512: 32 groups of 16 lanes, 4 nodes per group per tile
 constexpr int HOP_EPI_WARPS = 4;               // warps 16-19: one TMEM lane quarter each
 constexpr int HOP_THREADS = HOP_GATHER_THREADS + HOP_EPI_WARPS * 32;        // 640 (20 warps: 96 registers each)
 constexpr size_t HOP_W_IMAGE = 2 * 2 * (size_t)HOP_W_TILE;      // 2 chunks x (hi | lo) = 32 KB
-constexpr int HOP_CSR_INTS = HOP_TILE + 4 + HOP_SRC_CAP;        // rowptr slice (129, padded) + src slice
 
-struct __align__(8) HopBarriers {
-    uint64_t a_full[2], a_empty[2];    // A-operand slot written (512 arrivals) / consumed by the MMA (commit)
-    uint64_t d_full[2], d_empty[2];    // accumulator slot complete (commit) / drained by the epilogue (128 arrivals)
-};
-
-constexpr size_t HOP_TC_SMEM = 1024 + 2 * (size_t)HOP_A_SLOT + HOP_W_IMAGE + sizeof(int32_t) * 2 * HOP_CSR_INTS +
-                               sizeof(HopBarriers) + 16;
+constexpr int HOP_A_SLOTS = 1;                 // A-operand slots (64 KB each)
 
 __global__ void hop_tc_pack_kernel(const float* __restrict__ w, unsigned char* __restrict__ img) {
     for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < HF * HF; idx += gridDim.x * blockDim.x) {
@@ -120,21 +112,34 @@ __device__ __forceinline__ void aggregate2(const float* __restrict__ o_src, cons
 }
 
 // Persistent, one CTA per SM, warp-specialised:
-//   warps 0-15  gather    : stage the tile's CSR slice (cp.async, one tile ahead), aggregate, write the A operand
-//   warps 16-19 epilogue  : D (TMEM) -> + o[c] (+ addend) -> activation -> out; lane 0 of warp 16 also issues
-//                           the 24 tcgen05.mma of each tile (3xTF32); its commits release the A slot / publish D
-// A-operand slots and TMEM accumulators are double-buffered, so the gather warps never wait for the tensor
-// pipe or the epilogue in steady state — they are the only part that is bound by memory.
+//   warps 0-15  gather  : aggregate (every warp walks its own nodes, no CTA-wide barrier: the warps drift freely,
+//                         which keeps the memory pipe uniformly busy), write the A operand; one tile later they
+//                         also finish the output rows: D (from the shared-memory stage) + o[c] (+ addend) ->
+//                         activation -> out, 16 lanes x 16 B per row, i.e. fully coalesced loads and stores
+//   warps 16-19 epilogue: D (TMEM) -> shared-memory stage (thread = TMEM lane = node); lane 0 of warp 16 also
+//                         issues the 24 tcgen05.mma of each tile (3xTF32); its commits release the A slot / publish D
+// In steady state nothing but the gather warps' global loads is on the critical path.
+constexpr int HOP_STAGE_LD = HF + 4;                                     // floats per staged row (272 B: conflict-free)
+constexpr size_t HOP_STAGE_BYTES = (size_t)HOP_TILE * HOP_STAGE_LD * 4;   // 34,816 B
+
+struct __align__(8) HopBarriers {
+    uint64_t a_full[2], a_empty[2];    // A-operand slot written (512 arrivals) / consumed by the MMA (commit)
+    uint64_t d_full[2], d_empty[2];    // accumulator slot complete (commit) / copied to the stage (128 arrivals)
+    uint64_t st_full, st_empty;        // stage holds D of a tile (128 arrivals) / has been consumed (512 arrivals)
+};
+
+constexpr size_t HOP_TC_SMEM = 1024 + (size_t)HOP_A_SLOTS * HOP_A_SLOT + HOP_W_IMAGE + HOP_STAGE_BYTES + sizeof(HopBarriers) + 16;
+
 template <bool WG, bool UP, bool TRACE>
 __global__ void __launch_bounds__(HOP_THREADS, 1) hop_tc_kernel(const __grid_constant__ HopTcParams p) {
     extern __shared__ unsigned char smem_raw[];
     // 1 KB alignment by OFFSETTING the shared array (integer arithmetic on the pointer value would turn every
     // later access into a generic LD/ST instead of LDS/STS)
     unsigned char* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
-    unsigned char* a_slots = smem;                                  // slot s: chunk c: [hi 16 KB | lo 16 KB]
-    unsigned char* w_tile = smem + 2 * (size_t)HOP_A_SLOT;          // chunk c: [hi 8 KB | lo 8 KB]
-    int32_t* s_csr = reinterpret_cast<int32_t*>(w_tile + HOP_W_IMAGE);         // 2 x [rowptr 132 | src 1024]
-    HopBarriers* bar = reinterpret_cast<HopBarriers*>(s_csr + 2 * HOP_CSR_INTS);
+    unsigned char* a_slots = smem;                                          // slot s: chunk c: [hi 16 KB | lo 16 KB]
+    unsigned char* w_tile = smem + (size_t)HOP_A_SLOTS * HOP_A_SLOT;        // chunk c: [hi 8 KB | lo 8 KB]
+    float* stage = reinterpret_cast<float*>(w_tile + HOP_W_IMAGE);          // [128][68] fp32
+    HopBarriers* bar = reinterpret_cast<HopBarriers*>(reinterpret_cast<unsigned char*>(stage) + HOP_STAGE_BYTES);
     uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(bar + 1);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -143,6 +148,7 @@ __global__ void __launch_bounds__(HOP_THREADS, 1) hop_tc_kernel(const __grid_con
             mbar_init(&bar->a_full[i], HOP_GATHER_THREADS); mbar_init(&bar->a_empty[i], 1);
             mbar_init(&bar->d_full[i], 1); mbar_init(&bar->d_empty[i], HOP_EPI_WARPS * 32);
         }
+        mbar_init(&bar->st_full, HOP_EPI_WARPS * 32); mbar_init(&bar->st_empty, HOP_GATHER_THREADS);
         fence_barrier_init();
     }
     for (int i = threadIdx.x * 16; i < (int)HOP_W_IMAGE; i += HOP_THREADS * 16)
@@ -154,8 +160,7 @@ __global__ void __launch_bounds__(HOP_THREADS, 1) hop_tc_kernel(const __grid_con
     tc_fence_after_sync();
     const uint32_t tmem_base = *tmem_holder;
     const int n_tiles = (p.n_dst + HOP_TILE - 1) / HOP_TILE;
-    // each CTA owns a CONTIGUOUS run of tiles: it stays inside the same 2 MB pages of o / s / out for many tiles
-    // (a grid-strided assignment touches new pages every tile and pays a TLB miss per array per tile)
+    // each CTA owns a contiguous run of tiles (it stays inside the same pages / L2 neighbourhood for many tiles)
     const int tpc = (n_tiles + (int)gridDim.x - 1) / (int)gridDim.x;
     const int tile0 = (int)blockIdx.x * tpc;
     const int n_my = max(0, min(tpc, n_tiles - tile0));
@@ -166,28 +171,50 @@ __global__ void __launch_bounds__(HOP_THREADS, 1) hop_tc_kernel(const __grid_con
         // =====================================================================================
         // gather warps
         // =====================================================================================
-        const int g = threadIdx.x >> 4, q = threadIdx.x & 15;      // 32 groups x 16 lanes
+        const int g = threadIdx.x >> 4, q = threadIdx.x & 15;      // 32 groups x 16 lanes; nodes g, g+32, g+64, g+96
         const int chunk = q >> 3, piece = q & 7, q4 = 4 * q;
         const bool trw = tr0 && warp == 0;
-        // swizzled byte offsets of this thread's 16-byte piece in rows g, g+32, g+64, g+96
+        const float slope = (p.act == SWE_ACT_PRELU && p.slope) ? __ldg(p.slope) : 0.f;
         const uint32_t a_off0 = sw128_offset(g, piece * 4), a_off1 = sw128_offset(g + 32, piece * 4);
         const uint32_t a_off2 = sw128_offset(g + 64, piece * 4), a_off3 = sw128_offset(g + 96, piece * 4);
+        // out rows of tile j: D (stage) + o[c] (+ addend) -> act -> store; all accesses are whole 256-byte rows
+        auto finish_tile = [&](int j) {
+            const int row0 = (tile0 + j) * HOP_TILE;
+            const int rows = min(HOP_TILE, p.n_dst - row0);
+            const long long base_row = (long long)p.dst_lo + row0;
+            float4 oc[4];
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                const int r = g + 32 * k;
+                oc[k] = (p.o_dst && r < rows) ? ldg4(p.o_dst + (base_row + r) * HF + q4) : make_float4(0.f, 0.f, 0.f, 0.f);
+                if (p.addend && r < rows) {
+                    const float4 a4 = ldg4(p.addend + (base_row + r) * HF + q4);
+                    oc[k].x += a4.x; oc[k].y += a4.y; oc[k].z += a4.z; oc[k].w += a4.w;
+                }
+            }
+            mbar_wait(&bar->st_full, (uint32_t)j & 1);
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                const int r = g + 32 * k;
+                const float4 d = *reinterpret_cast<const float4*>(stage + r * HOP_STAGE_LD + q4);
+                float4 rr = make_float4(oc[k].x + d.x, oc[k].y + d.y, oc[k].z + d.z, oc[k].w + d.w);
+                if (p.act != SWE_ACT_NONE) {
+                    rr.x = act_apply(p.act, rr.x, slope); rr.y = act_apply(p.act, rr.y, slope);
+                    rr.z = act_apply(p.act, rr.z, slope); rr.w = act_apply(p.act, rr.w, slope);
+                }
+                if (r < rows) stg4(p.out + (base_row + r) * HF + q4, rr);
+            }
+            mbar_arrive(&bar->st_empty);
+        };
 #pragma unroll 1
         for (int i = 0; i < n_my; ++i) {
-            const int slot = i & 1;
-            const uint32_t u = (uint32_t)(i >> 1);
+            const int slot = i % HOP_A_SLOTS;
+            const uint32_t u = (uint32_t)(i / HOP_A_SLOTS);
             const int row0 = (tile0 + i) * HOP_TILE;
             const int rows = min(HOP_TILE, p.n_dst - row0);
-            // no CTA-wide staging / barrier here: every warp walks its own nodes (rowptr -> src -> rows) and drifts
-            // freely against the others, which keeps the memory pipe uniformly busy instead of bursty
             const int32_t* rp = p.rowptr + row0;
             if (trw) SWE_STAMP(0, i, 0);
-            if (trw) SWE_STAMP(0, i, 1);
-            mbar_wait(&bar->a_empty[slot], (u & 1) ^ 1);               // MMA of tile i-2 has consumed this slot
-            if (trw) SWE_STAMP(0, i, 2);
             unsigned char* base = a_slots + (size_t)slot * HOP_A_SLOT + (size_t)chunk * 2 * HOP_A_TILE;
-            const int32_t* ids = p.src;
-            const int id_base = 0;
             const float* orow_base = p.o_dst ? p.o_dst + ((long long)p.dst_lo + row0) * HF + q4 : nullptr;
 #pragma unroll 1
             for (int jj = 0; jj < 2; ++jj) {
@@ -200,10 +227,14 @@ __global__ void __launch_bounds__(HOP_THREADS, 1) hop_tc_kernel(const __grid_con
                     if (ib < rows) ocb = ldg4(orow_base + ib * HF);
                 }
                 float4 acca, accb;
-                aggregate2<WG, UP>(p.o_src, p.s, ids, id_base, pa0, pa1, pb0, pb1, oca, ocb, q4, acca, accb);
+                aggregate2<WG, UP>(p.o_src, p.s, p.src, 0, pa0, pa1, pb0, pb1, oca, ocb, q4, acca, accb);
                 if (p.agg_out) {
                     if (ia < rows) stg4(p.agg_out + ((long long)p.dst_lo + row0 + ia) * HF + q4, acca);
                     if (ib < rows) stg4(p.agg_out + ((long long)p.dst_lo + row0 + ib) * HF + q4, accb);
+                }
+                if (jj == 0) {
+                    mbar_wait(&bar->a_empty[slot], (u & 1) ^ 1);       // the MMA that last read this slot has completed
+                    if (trw) SWE_STAMP(0, i, 1);
                 }
                 float4 hh, ll;
                 split_tf32(acca.x, hh.x, ll.x); split_tf32(acca.y, hh.y, ll.y); split_tf32(acca.z, hh.z, ll.z); split_tf32(acca.w, hh.w, ll.w);
@@ -213,32 +244,37 @@ __global__ void __launch_bounds__(HOP_THREADS, 1) hop_tc_kernel(const __grid_con
                 split_tf32(accb.x, hh.x, ll.x); split_tf32(accb.y, hh.y, ll.y); split_tf32(accb.z, hh.z, ll.z); split_tf32(accb.w, hh.w, ll.w);
                 *reinterpret_cast<float4*>(base + offb) = hh;
                 *reinterpret_cast<float4*>(base + HOP_A_TILE + offb) = ll;
-                if (trw) SWE_STAMP(0, i, 3 + jj);
+                if (trw) SWE_STAMP(0, i, 2 + jj);
+                if (jj == 0 && i > 0) {                                  // the previous tile's D is in the stage by now
+                    finish_tile(i - 1);
+                    if (trw) SWE_STAMP(0, i, 4);
+                }
             }
             fence_proxy_async_smem();
             mbar_arrive(&bar->a_full[slot]);
         }
+        if (n_my > 0) finish_tile(n_my - 1);
     } else {
         // =====================================================================================
-        // epilogue warps: thread = one TMEM lane = one node, 64 columns in two halves
+        // epilogue warps: thread = one TMEM lane = one node; D -> stage
         // =====================================================================================
         const int lq = warp & 3;
-        const float slope = (p.act == SWE_ACT_PRELU && p.slope) ? __ldg(p.slope) : 0.f;
         const bool trw = tr0 && lq == 0;
         const uint32_t idesc = make_idesc_tf32(HOP_TILE, HF);
         const uint32_t a_u32 = smem_u32(a_slots), w_u32 = smem_u32(w_tile);
+        float* my_row = stage + (lq * 32 + lane) * HOP_STAGE_LD;
 #pragma unroll 1
         for (int i = 0; i < n_my; ++i) {
-            const int slot = i & 1;
-            const uint32_t u = (uint32_t)(i >> 1);
+            const int slot = i % HOP_A_SLOTS, dslot = i & 1;
+            const uint32_t u = (uint32_t)(i / HOP_A_SLOTS), ud = (uint32_t)(i >> 1);
             if (warp == HOP_GATHER_WARPS) {
                 if (lane == 0) {
                     SWE_STAMP(2, i, 0);
-                    mbar_wait(&bar->d_empty[slot], (u & 1) ^ 1);       // epilogue of tile i-2 has drained this accumulator
+                    mbar_wait(&bar->d_empty[dslot], (ud & 1) ^ 1);     // accumulator of tile i-2 has been copied out
                     mbar_wait(&bar->a_full[slot], u & 1);
                     tc_fence_after_sync();
                     SWE_STAMP(2, i, 1);
-                    const uint32_t d = tmem_base + slot * 64;
+                    const uint32_t d = tmem_base + dslot * 64;
 #pragma unroll
                     for (int c = 0; c < 2; ++c) {
                         const uint32_t a_hi = a_u32 + slot * HOP_A_SLOT + c * 2 * HOP_A_TILE, a_lo = a_hi + HOP_A_TILE;
@@ -253,54 +289,29 @@ __global__ void __launch_bounds__(HOP_THREADS, 1) hop_tc_kernel(const __grid_con
                         }
                     }
                     mma_commit(&bar->a_empty[slot]);
-                    mma_commit(&bar->d_full[slot]);
+                    mma_commit(&bar->d_full[dslot]);
                     SWE_STAMP(2, i, 2);
                 }
                 __syncwarp();
             }
-            const int row0 = (tile0 + i) * HOP_TILE;
-            const int rows = min(HOP_TILE, p.n_dst - row0);
-            const int r = lq * 32 + lane;
-            const long long c = (long long)p.dst_lo + row0 + r;
-            const bool valid = r < rows;
-            // o[c] does not depend on the accumulator: fetch it while the MMA is still running
-            float4 tod[8];
-#pragma unroll
-            for (int j = 0; j < 8; ++j) tod[j] = (valid && p.o_dst) ? ldg4(p.o_dst + c * HF + 4 * j) : make_float4(0.f, 0.f, 0.f, 0.f);
             if (trw) SWE_STAMP(1, i, 0);
-            mbar_wait(&bar->d_full[slot], u & 1);
+            mbar_wait(&bar->d_full[dslot], ud & 1);
             tc_fence_after_sync();
+            mbar_wait(&bar->st_empty, ((uint32_t)i & 1) ^ 1);          // stage consumed by the gather warps (tile i-1)
             if (trw) SWE_STAMP(1, i, 1);
 #pragma unroll 1
             for (int hf = 0; hf < 2; ++hf) {
                 uint32_t v[32];
-                tmem_ld32(tmem_base + ((uint32_t)(lq * 32) << 16) + slot * 64 + hf * 32, v);
+                tmem_ld32(tmem_base + ((uint32_t)(lq * 32) << 16) + dslot * 64 + hf * 32, v);
                 tmem_wait_ld();
-                if (hf == 1) {                                       // accumulator slot fully read: hand it back early
-                    tc_fence_before_sync();
-                    mbar_arrive(&bar->d_empty[slot]);
-                }
-                if (valid) {
-                    const float* ad = p.addend ? p.addend + c * HF + hf * 32 : nullptr;
-                    float* o = p.out + c * HF + hf * 32;
-                    if (hf == 1 && p.o_dst) {
 #pragma unroll
-                        for (int j = 0; j < 8; ++j) tod[j] = ldg4(p.o_dst + c * HF + 32 + 4 * j);
-                    }
-#pragma unroll
-                    for (int j = 0; j < 32; j += 4) {
-                        float4 t = tod[j >> 2];
-                        float4 rr = make_float4(t.x + __uint_as_float(v[j]), t.y + __uint_as_float(v[j + 1]),
-                                                t.z + __uint_as_float(v[j + 2]), t.w + __uint_as_float(v[j + 3]));
-                        if (ad) { const float4 a4 = ldg4(ad + j); rr.x += a4.x; rr.y += a4.y; rr.z += a4.z; rr.w += a4.w; }
-                        if (p.act != SWE_ACT_NONE) {
-                            rr.x = act_apply(p.act, rr.x, slope); rr.y = act_apply(p.act, rr.y, slope);
-                            rr.z = act_apply(p.act, rr.z, slope); rr.w = act_apply(p.act, rr.w, slope);
-                        }
-                        stg4(o + j, rr);
-                    }
-                }
+                for (int j = 0; j < 32; j += 4)
+                    *reinterpret_cast<float4*>(my_row + hf * 32 + j) =
+                        make_float4(__uint_as_float(v[j]), __uint_as_float(v[j + 1]), __uint_as_float(v[j + 2]), __uint_as_float(v[j + 3]));
             }
+            tc_fence_before_sync();
+            mbar_arrive(&bar->d_empty[dslot]);
+            mbar_arrive(&bar->st_full);
             if (trw) SWE_STAMP(1, i, 2);
         }
     }

@@ -46,7 +46,7 @@ if os.environ.get("TRACE"):
     torch.cuda.synchronize()
     t = trace.cpu().view(3, 16, 8)
     t0 = int(t[0, 2, 0])
-    ev = [["start", "csr_ready", "slot_free", "round0", "round1"], ["oc_loaded", "d_full", "stored"], ["wait", "a_full", "issued"]]
+    ev = [["start", "slot_free", "round0", "round1", "prev_out"], ["begin", "d_full", "staged"], ["wait", "a_full", "issued"]]
     for tile in range(2, 9):
         for r, name in enumerate(["gather", "epilogue", "mma"]):
             print(tile, name, " ".join(f"{ev[r][e]}={int(t[r, tile, e]) - t0}" for e in range(len(ev[r]))))
