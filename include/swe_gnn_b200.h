@@ -212,6 +212,10 @@ int swe_apply_bc(float* x, int32_t n_cols, int32_t n_static_raw, int32_t previou
                  const int64_t* node_bc, int32_t n_bc, const float* bc, int32_t n_steps_total,
                  const int32_t* step_ptr, void* stream);
 
+/* dst[i, :] = src[idx[i], :] for rows of `width` floats: packs the boundary rows a rank sends to a peer in the
+ * partitioned large-mesh rollout (no reference counterpart: the reference has no graph partitioning). */
+int swe_pack_rows(const float* src, const int32_t* idx, int64_t n_rows, int32_t width, float* dst, void* stream);
+
 /* *step_ptr += 1 (end of one rollout step, training/train.py:87). */
 int swe_step_advance(int32_t* step_ptr, void* stream);
 

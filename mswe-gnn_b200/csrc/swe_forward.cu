@@ -583,6 +583,24 @@ __global__ void apply_bc_kernel(float* __restrict__ x, int n_cols, int n_static_
     }
 }
 
+// dst[i, :] = src[idx[i], :]  (rows of `width` floats; halo send-buffer packing)
+__global__ void pack_rows_kernel(const float* __restrict__ src, const int32_t* __restrict__ idx, long long n, int width,
+                                 float* __restrict__ dst) {
+    if ((width & 3) == 0) {
+        const int qpr = width >> 2;
+        for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < n * qpr; t += (long long)gridDim.x * blockDim.x) {
+            const long long i = t / qpr;
+            const int q = (int)(t % qpr);
+            stg4(dst + i * width + 4 * q, ldg4(src + (long long)__ldg(idx + i) * width + 4 * q));
+        }
+    } else {
+        for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < n * width; t += (long long)gridDim.x * blockDim.x) {
+            const long long i = t / width;
+            dst[t] = __ldg(src + (long long)__ldg(idx + i) * width + (t % width));
+        }
+    }
+}
+
 __global__ void step_advance_kernel(int32_t* step_ptr) { if (threadIdx.x == 0 && blockIdx.x == 0) *step_ptr += 1; }
 
 // =============================================================================================
@@ -789,6 +807,15 @@ extern "C" int swe_apply_bc(float* x, int32_t n_cols, int32_t n_static_raw, int3
     apply_bc_kernel<<<1, 128, 0, (cudaStream_t)stream>>>(x, n_cols, n_static_raw, previous_t, type_bc, node_bc, n_bc,
                                                         bc, n_steps_total, step_ptr);
     return check_launch("apply_bc");
+}
+
+extern "C" int swe_pack_rows(const float* src, const int32_t* idx, int64_t n_rows, int32_t width, float* dst, void* stream) {
+    SWE_REQUIRE(src && idx && dst && n_rows >= 0 && width >= 1, SWE_E_INVAL, "pack_rows: bad arguments");
+    SWE_REQUIRE((width & 3) != 0 || (aligned16(src) && aligned16(dst)), SWE_E_ALIGN, "pack_rows: unaligned buffer");
+    if (n_rows == 0) return 0;
+    const long long work = n_rows * ((width & 3) == 0 ? width / 4 : width);
+    pack_rows_kernel<<<grid_for((work + 255) / 256, 8), 256, 0, (cudaStream_t)stream>>>(src, idx, n_rows, width, dst);
+    return check_launch("pack_rows");
 }
 
 extern "C" int swe_step_advance(int32_t* step_ptr, void* stream) {

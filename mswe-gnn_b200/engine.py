@@ -257,11 +257,13 @@ class SweGnnLauncher:
                               s_buf, self.FP)
 
     def run(self, es: EdgeSet, xs, xd_src, xd_dst, a, s_buf, o_dst_rows_zero: bool, tmp_a, tmp_b, out,
-            addend=None, act_code: int = 0, act_slope=None):
+            addend=None, act_code: int = 0, act_slope=None, halo=None, scale: int = 0):
         """Writes rows [es.dst_lo, es.dst_lo+es.n_dst) of `out`.
 
         xd_src: array holding x_d[row]; xd_dst: array holding x_d[col] or None when those rows are
         zero (then the hop also treats o[col] as zero).  tmp_a / tmp_b: scratch [N, FP] arrays.
+        halo: optional ``parallel.HaloExchanger`` (partitioned meshes): the halo rows of scale `scale`
+        are refreshed from their owners after every hop but the last.
         """
         m, FP = self.m, self.FP
         E = es.n_edges
@@ -299,4 +301,6 @@ class SweGnnLauncher:
                 lib.propagate_hop_fwd(o_src, o_dst, s_buf, es.rowptr, es.src, es.dst_lo, es.n_dst, W[k + 1],
                                       m.with_gradient, m.upwind_mode, addend if last else None,
                                       act_code if last else 0, act_slope if last else None, dst_buf, FP)
+            if halo is not None and not last:
+                halo.exchange(dst_buf, scale)
             o_src = o_dst = dst_buf

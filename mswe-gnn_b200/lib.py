@@ -73,6 +73,7 @@ SIGNATURES = {
                                       _p, _i32, _p]),
     "swe_apply_bc": (C.c_int, [_p, _i32, _i32, _i32, _i32, _p, _i32, _p, _i32, _p, _p]),
     "swe_step_advance": (C.c_int, [_p, _p]),
+    "swe_pack_rows": (C.c_int, [_p, _p, _i64, _i32, _p, _p]),
     # training path
     "swe_mlp_layer_fwd": (C.c_int, [_rows, _i64, _p, _p, _i32, _p, _p]),
     "swe_mlp_layer_bwd_dx": (C.c_int, [_p, _p, _i32, _p, _i64, _i32, _p, _i32, _i32, _i32, _i32, _p, _i32, _i32, _p,
@@ -267,6 +268,11 @@ def apply_bc(x, n_static_raw, previous_t, type_bc, node_bc, bc, step_ptr):
     _check(load().swe_apply_bc(ptr(x), x.shape[1], n_static_raw, previous_t, type_bc, ptr(node_bc, torch.int64),
                                node_bc.numel(), ptr(bc), bc.shape[-1], ptr(step_ptr, torch.int32), _stream()),
            "swe_apply_bc")
+
+
+def pack_rows(src, idx, n_rows, dst):
+    _check(load().swe_pack_rows(ptr(src), ptr(idx, torch.int32), n_rows, src.shape[1], ptr(dst), _stream()),
+           "swe_pack_rows")
 
 
 def step_advance(step_ptr):

@@ -258,7 +258,7 @@ class GNN(BaseFloodModel, _EncodeDecodeMixin):
         self._launch(plan, graph, graph.x.contiguous(), pred)
         return pred
 
-    def _launch(self, plan, graph, x, pred, step_ptr=None, pred_stride=0, x_next=None):
+    def _launch(self, plan, graph, x, pred, step_ptr=None, pred_stride=0, x_next=None, halo=None):
         FP = self._FP
         n_layers = len(self.gnn_processor)
         ws = self._workspace(plan, ["xs", "h0", "h1", "ta", "tb"])
@@ -270,9 +270,11 @@ class GNN(BaseFloodModel, _EncodeDecodeMixin):
         act_mod = self.gnn_activation
         slope = act_mod.weight if isinstance(act_mod, nn.PReLU) else None
         es = plan.edges[0]
-        for conv in self.gnn_processor:
+        for li, conv in enumerate(self.gnn_processor):
+            if halo is not None and li > 0:
+                halo.exchange(cur, 0)
             conv.launcher().run(es, ws["xs"], cur, cur, a, ws["s"], False, ws["ta"], ws["tb"], nxt,
-                                act_code=ACT_CODES[self._gnn_activation_name], act_slope=slope)
+                                act_code=ACT_CODES[self._gnn_activation_name], act_slope=slope, halo=halo, scale=0)
             cur, nxt = nxt, cur
         self._decode(cur, None, None, x, plan, pred, step_ptr, pred_stride, x_next)
 
@@ -360,7 +362,8 @@ class MSGNN(BaseFloodModel, _EncodeDecodeMixin):
         self._launch(plan, graph, graph.x.contiguous(), pred)
         return pred
 
-    def _launch(self, plan, graph, x, pred, step_ptr=None, pred_stride=0, x_next=None):
+    def _launch(self, plan, graph, x, pred, step_ptr=None, pred_stride=0, x_next=None, halo=None):
+        """halo: ``parallel.HaloExchanger`` when `graph` is one rank's part of a partitioned mesh."""
         FP, S = self._FP, self.num_scales
         ws = self._workspace(plan, ["xs", "cur", "down", "up", "ta", "tb"])
         a = self._encoded_edges(plan, graph, ws)
@@ -373,17 +376,26 @@ class MSGNN(BaseFloodModel, _EncodeDecodeMixin):
             return a[lo:hi] if hi > lo else None
 
         # fine -> coarse
+        cross = halo.part.inter_cross if halo is not None else None
         for i in range(S - 1):
             es = plan.edges[i]
-            self.gnn_processor[i].launcher().run(es, xs, cur, cur, a_of(i), s_buf, False, ta, tb, down)
+            if halo is not None and i > 0:
+                halo.exchange(cur, i)                     # pooled rows of the halo nodes come from their owners
+            self.gnn_processor[i].launcher().run(es, xs, cur, cur, a_of(i), s_buf, False, ta, tb, down, halo=halo, scale=i)
+            if halo is not None and cross[i]:
+                halo.exchange(down, i)                    # a child owned by another rank (real meshes, App. D-5)
             pe = plan.pool[i]
             lib.pool_mean_fwd(down, pe.rowptr, pe.src, pe.dst_lo, pe.n_dst, cur, FP)
         # coarse -> fine
         for i in range(S):
             s = S - 1 - i
             es = plan.edges[s]
-            self.gnn_processor[S - 1 + i].launcher().run(es, xs, cur, cur, a_of(s), s_buf, False, ta, tb, up)
+            if halo is not None and S > 1:
+                halo.exchange(cur, s)
+            self.gnn_processor[S - 1 + i].launcher().run(es, xs, cur, cur, a_of(s), s_buf, False, ta, tb, up, halo=halo, scale=s)
             if i < S - 1:
+                if halo is not None and cross[s - 1]:
+                    halo.exchange(up, s)
                 ue = plan.unpool[s - 1]
                 # x_d[fine] is identically zero here (nothing wrote the finer rows since the last
                 # pooling zeroed them), so the gate skips that block and the hop starts from 0

@@ -1,0 +1,351 @@
+"""Multi-GPU modes of the hot path (one process per GPU, ``torch.distributed``).
+
+The reference has no explicit distributed code (only Lightning-implicit DDP), so
+this module is new functionality with two modes (``BASELINE.json`` north_star):
+
+* **Partitioned large-mesh rollout** — the graph is cut by blocks of coarsest-level cells; every
+  finer node inherits the owner of its (first) parent, so pooling / un-pooling are local; every
+  level is sharded (no replicated level, hence no all-gather).  A rank's local graph holds, per
+  scale, its owned nodes followed by the halo nodes (sources of edges that end in an owned node),
+  grouped by owner, and exactly the edges that end in an owned node IN GLOBAL EDGE ORDER — so each
+  in-segment sum runs over the same edges in the same order as on one GPU and owned rows are
+  bit-identical to the single-GPU result.  Halo rows are refreshed by neighbour exchange: once
+  before each SWEGNN call (its input x_d) and after every hop but the last; the node inputs ``x``
+  (8 floats) once per rollout step.  Receives land directly in the halo row range (contiguous
+  per peer); sends are packed by ``swe_pack_rows``.
+* **Data-parallel training** — independent simulations per rank, one all-reduce of the flat fp32
+  gradient per optimizer step (what Lightning DDP does for the reference, ``main.py:107``).
+
+Integer artefacts (owner map, local numbering, send / receive lists) are checked bit-exactly against
+the loop restatement in ``oracle/partition_oracle.py``.
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass, field
+from typing import Dict, List, Optional, Sequence, Tuple
+
+import numpy as np
+import torch
+
+from .utils.data import Data
+
+
+# ------------------------------------------------------------------------------------------------
+# partitioning (host, NumPy, int64)
+# ------------------------------------------------------------------------------------------------
+def owner_map(node_ptr: np.ndarray, edge_index: np.ndarray, edge_ptr: np.ndarray, intra: np.ndarray,
+              intra_ptr: np.ndarray, world: int) -> np.ndarray:
+    """Owner rank of every node.  Coarsest scale: contiguous index blocks; finer scales: owner of
+    the FIRST parent in ``intra_mesh_edge_index`` order; nodes without a parent (ghost cells,
+    orphans): owner of the first edge neighbour that has one, else rank 0."""
+    S = len(node_ptr) - 1
+    N = int(node_ptr[-1])
+    owner = np.full(N, -1, dtype=np.int64)
+    lo, hi = int(node_ptr[S - 1]), int(node_ptr[S])
+    nc = hi - lo
+    owner[lo:hi] = np.minimum((np.arange(nc, dtype=np.int64) * world) // max(nc, 1), world - 1)
+    for j in range(S - 2, -1, -1):
+        a, b = int(intra_ptr[j]), int(intra_ptr[j + 1])
+        coarse, fine = intra[0, a:b], intra[1, a:b]
+        uf, first = np.unique(fine, return_index=True)
+        owner[uf] = owner[coarse[first]]
+    for _ in range(4):                      # parent-less nodes: take the owner of an edge neighbour
+        todo = owner < 0
+        if not todo.any():
+            break
+        row, col = edge_index[0], edge_index[1]
+        m = todo[row] & (owner[col] >= 0)
+        if m.any():
+            ur, first = np.unique(row[m], return_index=True)
+            owner[ur] = owner[col[m][first]]
+        todo = owner < 0
+        m = todo[col] & (owner[row] >= 0)
+        if m.any():
+            uc, first = np.unique(col[m], return_index=True)
+            owner[uc] = owner[row[m][first]]
+    owner[owner < 0] = 0
+    return owner
+
+
+@dataclass
+class LocalPartition:
+    """Everything one rank needs: its local graph and the exchange lists, per scale."""
+    rank: int
+    world: int
+    num_scales: int
+    graph: Data                                  # local multiscale graph (CPU tensors)
+    local_to_global: np.ndarray                  # [N_local]
+    n_owned: List[int]                           # per scale
+    n_halo: List[int]
+    scale_lo: List[int]                          # first local row of each scale
+    # per scale: {peer: int64 local rows to send (sorted by global id)}, {peer: (first local row, count)}
+    send: List[Dict[int, np.ndarray]] = field(default_factory=list)
+    recv: List[Dict[int, Tuple[int, int]]] = field(default_factory=list)
+    inter_cross: List[bool] = field(default_factory=list)   # inter-scale level j has edges crossing ranks
+    owned_rows: Optional[np.ndarray] = None      # local rows that are owned (all scales)
+    owned_global: Optional[np.ndarray] = None    # their global ids
+
+
+def partition_graph(graph, world: int, rank: int, owner: Optional[np.ndarray] = None) -> LocalPartition:
+    """Cut a multiscale graph (fields of SURVEY.md Appendix C, CPU tensors) for ``rank`` of ``world``.
+    A single-scale graph (no ``node_ptr``) is treated as one scale."""
+    x = graph.x
+    N = int(x.shape[0])
+    ei = graph.edge_index.numpy()
+    multiscale = hasattr(graph, "node_ptr") and getattr(graph, "node_ptr") is not None
+    if multiscale:
+        node_ptr = graph.node_ptr.numpy().astype(np.int64).reshape(-1)
+        edge_ptr = graph.edge_ptr.numpy().astype(np.int64)
+        intra = graph.intra_mesh_edge_index.numpy()
+        intra_ptr = graph.intra_edge_ptr.numpy().astype(np.int64)
+    else:
+        node_ptr = np.array([0, N], dtype=np.int64)
+        edge_ptr = np.array([0, ei.shape[1]], dtype=np.int64)
+        intra = np.zeros((2, 0), dtype=np.int64)
+        intra_ptr = np.array([0], dtype=np.int64)
+    S = len(node_ptr) - 1
+    if owner is None:
+        owner = owner_map(node_ptr, ei, edge_ptr, intra, intra_ptr, world)
+    r = rank
+
+    halo_sets: List[List[np.ndarray]] = [[] for _ in range(S)]          # global ids wanted as halo, per scale
+    send_sets: List[Dict[int, List[np.ndarray]]] = [dict() for _ in range(S)]
+
+    def want(scale: int, src: np.ndarray, dst: np.ndarray):
+        """edges src -> dst whose value at src is consumed at dst: halo / send bookkeeping."""
+        os_, od = owner[src], owner[dst]
+        cross = os_ != od
+        mine = cross & (od == r)
+        if mine.any():
+            halo_sets[scale].append(src[mine])
+        out = cross & (os_ == r)
+        if out.any():
+            peers = od[out]
+            nodes = src[out]
+            for q in np.unique(peers):
+                send_sets[scale].setdefault(int(q), []).append(nodes[peers == q])
+        return bool(cross.any())
+
+    for s in range(S):
+        a, b = int(edge_ptr[s]), int(edge_ptr[s + 1])
+        want(s, ei[0, a:b], ei[1, a:b])
+    inter_cross = []
+    for j in range(S - 1):
+        a, b = int(intra_ptr[j]), int(intra_ptr[j + 1])
+        coarse, fine = intra[0, a:b], intra[1, a:b]
+        c1 = want(j, fine, coarse)          # pooling reads fine rows at the coarse owner
+        c2 = want(j + 1, coarse, fine)      # un-pooling reads coarse rows at the fine owner
+        inter_cross.append(c1 or c2)
+
+    g2l = np.full(N, -1, dtype=np.int64)
+    l2g_parts, n_owned, n_halo, scale_lo = [], [], [], []
+    recv: List[Dict[int, Tuple[int, int]]] = []
+    cursor = 0
+    for s in range(S):
+        lo, hi = int(node_ptr[s]), int(node_ptr[s + 1])
+        ids = np.arange(lo, hi, dtype=np.int64)
+        owned = ids[owner[lo:hi] == r]
+        halo = np.unique(np.concatenate(halo_sets[s])) if halo_sets[s] else np.zeros(0, dtype=np.int64)
+        halo = halo[np.lexsort((halo, owner[halo]))]                     # by owner, then global id
+        scale_lo.append(cursor)
+        g2l[owned] = cursor + np.arange(owned.size)
+        g2l[halo] = cursor + owned.size + np.arange(halo.size)
+        rmap: Dict[int, Tuple[int, int]] = {}
+        if halo.size:
+            ho = owner[halo]
+            for q in np.unique(ho):
+                idx = np.nonzero(ho == q)[0]
+                rmap[int(q)] = (cursor + owned.size + int(idx[0]), int(idx.size))
+        recv.append(rmap)
+        l2g_parts += [owned, halo]
+        n_owned.append(int(owned.size)); n_halo.append(int(halo.size))
+        cursor += owned.size + halo.size
+    l2g = np.concatenate(l2g_parts) if l2g_parts else np.zeros(0, dtype=np.int64)
+    send: List[Dict[int, np.ndarray]] = []
+    for s in range(S):
+        send.append({q: g2l[np.unique(np.concatenate(v))] for q, v in sorted(send_sets[s].items())})
+
+    # ---- local graph: edges that end in an owned node, in global order; inter-scale edges with an owned end
+    e_parts, ea_parts, e_counts = [], [], []
+    for s in range(S):
+        a, b = int(edge_ptr[s]), int(edge_ptr[s + 1])
+        keep = np.nonzero(owner[ei[1, a:b]] == r)[0] + a
+        e_parts.append(g2l[ei[:, keep]])
+        ea_parts.append(keep)
+        e_counts.append(keep.size)
+    i_parts, i_counts = [], []
+    for j in range(S - 1):
+        a, b = int(intra_ptr[j]), int(intra_ptr[j + 1])
+        keep = np.nonzero((owner[intra[0, a:b]] == r) | (owner[intra[1, a:b]] == r))[0] + a
+        i_parts.append(g2l[intra[:, keep]])
+        i_counts.append(keep.size)
+    e_keep = np.concatenate(ea_parts) if ea_parts else np.zeros(0, dtype=np.int64)
+    local = Data(
+        x=x[torch.from_numpy(l2g)].contiguous(),
+        edge_index=torch.from_numpy(np.concatenate(e_parts, 1) if e_parts else np.zeros((2, 0), dtype=np.int64)).contiguous(),
+        edge_attr=graph.edge_attr[torch.from_numpy(e_keep)].contiguous(),
+    )
+    if multiscale:
+        local.node_ptr = torch.tensor(scale_lo + [cursor], dtype=torch.long)
+        local.edge_ptr = torch.from_numpy(np.concatenate([[0], np.cumsum(e_counts)]).astype(np.int64))
+        local.intra_mesh_edge_index = torch.from_numpy(np.concatenate(i_parts, 1) if i_parts
+                                                       else np.zeros((2, 0), dtype=np.int64)).contiguous()
+        local.intra_edge_ptr = torch.from_numpy(np.concatenate([[0], np.cumsum(i_counts)]).astype(np.int64))
+    if hasattr(graph, "node_BC"):
+        nbc = graph.node_BC.numpy().astype(np.int64)
+        present = np.nonzero(g2l[nbc] >= 0)[0]
+        local.node_BC = torch.from_numpy(g2l[nbc[present]])
+        local.BC = graph.BC[torch.from_numpy(present)].contiguous()
+        local.type_BC = graph.type_BC
+    if hasattr(graph, "y") and graph.y is not None and graph.y.shape[0] == N:
+        local.y = graph.y[torch.from_numpy(l2g)].contiguous()
+    for k in ("previous_t", "temporal_res"):
+        if hasattr(graph, k):
+            setattr(local, k, getattr(graph, k))
+    owned_rows = np.concatenate([scale_lo[s] + np.arange(n_owned[s]) for s in range(S)]) if S else np.zeros(0, np.int64)
+    return LocalPartition(rank, world, S, local, l2g, n_owned, n_halo, scale_lo, send, recv, inter_cross,
+                          owned_rows.astype(np.int64), l2g[owned_rows.astype(np.int64)])
+
+
+# ------------------------------------------------------------------------------------------------
+# halo exchange
+# ------------------------------------------------------------------------------------------------
+class HaloExchanger:
+    """Neighbour exchange of halo rows for one rank.
+
+    transport='nccl'   : ``dist.batch_isend_irecv`` on device tensors (NVLink / NVSwitch);
+    transport='staged' : the same messages through pinned host buffers (gloo) — used by the tests
+                         that run two ranks on one GPU or on CPU tensors."""
+
+    def __init__(self, part: LocalPartition, device, transport: str = "nccl", group=None):
+        import torch.distributed as dist
+        self.dist = dist
+        self.part, self.device, self.transport, self.group = part, torch.device(device), transport, group
+        self.send_idx = [{q: torch.from_numpy(v.astype(np.int32)).to(self.device) for q, v in d.items()} for d in part.send]
+        self.recv = part.recv
+        self._bufs: Dict[Tuple[int, int, int], torch.Tensor] = {}
+        self.n_exchanges = 0
+        self.bytes_sent = 0
+
+    def _send_buf(self, scale: int, q: int, n: int, width: int) -> torch.Tensor:
+        key = (scale, q, width)
+        b = self._bufs.get(key)
+        if b is None:
+            b = torch.empty(max(n, 1), width, dtype=torch.float32, device=self.device)
+            self._bufs[key] = b
+        return b
+
+    def exchange(self, arr: torch.Tensor, scale: int):
+        """Refresh the halo rows of scale ``scale`` in ``arr`` ([N_local, width] fp32, local row order)."""
+        sends, recvs = self.send_idx[scale], self.recv[scale]
+        if not sends and not recvs:
+            return
+        dist = self.dist
+        width = arr.shape[1]
+        ops, staged = [], []
+        for q, idx in sends.items():
+            n = int(idx.numel())
+            buf = self._send_buf(scale, q, n, width)
+            if arr.is_cuda:
+                from . import lib
+                lib.pack_rows(arr, idx, n, buf)
+            else:
+                torch.index_select(arr, 0, idx.long(), out=buf[:n])
+            self.bytes_sent += n * width * 4
+            if self.transport == "nccl":
+                ops.append(dist.P2POp(dist.isend, buf[:n], q, group=self.group))
+            else:
+                ops.append(dist.P2POp(dist.isend, buf[:n].cpu(), q, group=self.group))
+        for q, (row, n) in recvs.items():
+            if self.transport == "nccl":
+                ops.append(dist.P2POp(dist.irecv, arr[row:row + n], q, group=self.group))
+            else:
+                tmp = torch.empty(n, width, dtype=torch.float32)
+                staged.append((row, n, tmp))
+                ops.append(dist.P2POp(dist.irecv, tmp, q, group=self.group))
+        for w in dist.batch_isend_irecv(ops):
+            w.wait()
+        for row, n, tmp in staged:
+            arr[row:row + n].copy_(tmp)
+        self.n_exchanges += 1
+
+
+class PartitionedRollout:
+    """Autoregressive rollout of one large mesh cut over the ranks of ``group``.
+
+    Same loop as ``RolloutRunner`` (``training/train.py:67-95``) run eagerly on the local graph,
+    with the halo refreshes inserted by the model's launch sequence.  ``preds`` holds the local rows
+    (owned + halo); ``owned_predictions()`` returns the owned rows with their global ids."""
+
+    def __init__(self, model, graph_cpu, n_steps: int, device, transport: str = "nccl", group=None,
+                 part: Optional[LocalPartition] = None):
+        import torch.distributed as dist
+        from . import lib
+        from .utils.dataset import NUM_WATER_VARS, check_type_BC
+        self.lib = lib
+        rank, world = dist.get_rank(group), dist.get_world_size(group)
+        self.part = part if part is not None else partition_graph(graph_cpu, world, rank)
+        self.model, self.T = model, int(n_steps)
+        self.graph = self.part.graph.to(device)
+        self.halo = HaloExchanger(self.part, device, transport, group)
+        model._check_input(self.graph)
+        multiscale = model.type_model == "MSGNN"
+        self.plan = model._plans.get(self.graph, getattr(model, "num_scales", 1), multiscale)
+        N = self.plan.n_nodes
+        self.x = self.graph.x.detach().clone().contiguous()
+        self.preds = torch.empty(self.T, N, NUM_WATER_VARS, dtype=torch.float32, device=device)
+        self.step = torch.zeros(1, dtype=torch.int32, device=device)
+        self.type_BC = int(self.graph.type_BC)
+        check_type_BC(self.type_BC)
+        self.node_BC = self.graph.node_BC.to(device, torch.int64).contiguous()
+        self.bc = self.graph.BC.to(device, torch.float32).contiguous()
+        self.n_static_raw = self.x.shape[1] - model.previous_t * NUM_WATER_VARS
+        self.launches_per_step = 0
+
+    def _one_step(self):
+        lib, m = self.lib, self.model
+        c0 = lib.launch_count
+        if self.node_BC.numel():
+            lib.apply_bc(self.x, self.n_static_raw, m.previous_t, self.type_BC, self.node_BC, self.bc, self.step)
+        m._launch(self.plan, self.graph, self.x, self.preds, step_ptr=self.step,
+                  pred_stride=self.preds.shape[1] * 2, x_next=self.x, halo=self.halo)
+        lib.step_advance(self.step)
+        # the window shift wrote garbage into the halo rows of x: refresh them from their owners
+        for s in range(self.part.num_scales):
+            self.halo.exchange(self.x, s)
+        self.launches_per_step = lib.launch_count - c0
+
+    def run(self, n_steps: Optional[int] = None):
+        for _ in range(self.T if n_steps is None else n_steps):
+            self._one_step()
+        return self.preds
+
+    def owned_predictions(self):
+        rows = torch.from_numpy(self.part.owned_rows).to(self.preds.device)
+        return self.preds[:, rows], self.part.owned_global
+
+
+# ------------------------------------------------------------------------------------------------
+# data-parallel training
+# ------------------------------------------------------------------------------------------------
+def allreduce_gradients(params: Sequence[torch.Tensor], group=None, average: bool = True):
+    """One all-reduce of the flat fp32 gradient (811,309 floats = 3.25 MB for the default model)."""
+    import torch.distributed as dist
+    ps = [p for p in params if p.grad is not None]
+    if not ps:
+        return 0
+    flat = torch.cat([p.grad.reshape(-1) for p in ps])
+    dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=group)
+    if average:
+        flat /= dist.get_world_size(group)
+    off = 0
+    for p in ps:
+        n = p.grad.numel()
+        p.grad.copy_(flat[off:off + n].view_as(p.grad))
+        off += n
+    return flat.numel() * 4
+
+
+def shard_simulations(n_sims: int, world: int, rank: int) -> List[int]:
+    """Indices of the simulations rank ``rank`` trains on (round-robin, every index exactly once)."""
+    return list(range(rank, n_sims, world))

@@ -12,5 +12,5 @@ $CMD > $OUT/plain_$TAG.log 2>&1 && \
 ncu --metrics gpu__time_duration.sum --clock-control none -c 700 --csv --log-file $OUT/launches_$TAG.csv $CMD > $OUT/ncu_launch_$TAG.log 2>&1
 echo "launch list rc=$?"
 $CMD > $OUT/plain2_$TAG.log 2>&1 && \
-ncu --set full --clock-control none --import-source on -k "regex:hop_kernel|edge_gate_tc_kernel" -c 3 -f -o $OUT/prof_$TAG $CMD > $OUT/ncu_full_$TAG.log 2>&1
+ncu --set full --clock-control none --import-source on -k "regex:hop_tc_kernel|edge_gate_tc_kernel" -c 3 -f -o $OUT/prof_$TAG $CMD > $OUT/ncu_full_$TAG.log 2>&1
 echo "full rc=$?"
