@@ -151,11 +151,25 @@ def run_reference(args):
 # --------------------------------------------------------------------------------------------------
 # our arm
 # --------------------------------------------------------------------------------------------------
+def mesh_for(world, wl):
+    """Workload mesh.  N=1: the named config.  N>1 (default workload): the cfg3 mesh grown so that every GPU keeps
+    cfg3's node count (weak scaling of ONE partitioned mesh): tri(712a, 712b) with a*b = N."""
+    nx, ny = WORKLOADS[wl]
+    if world > 1 and wl == "cfg3":
+        a = 1
+        while a * a < world:
+            a *= 2
+        b = world // a
+        nx, ny = nx * a, ny * b
+    return nx, ny
+
+
 def run_ours(args):
     import torch.distributed as dist
     import mswe_gnn_b200  # noqa: F401
     from mswe_gnn_b200 import lib
     from mswe_gnn_b200.models.gnn import MSGNN
+    from mswe_gnn_b200.parallel import PartitionedRollout, partition_graph
     from mswe_gnn_b200.training.train import RolloutRunner, rollout_test
     from mswe_gnn_b200.utils.synthetic import make_tri_mesh
 
@@ -168,25 +182,35 @@ def run_ours(args):
         dist.init_process_group("nccl", device_id=dev)
     lib.load()
     wl = args.workload or "cfg3"
-    nx, ny = WORKLOADS[wl]
+    nx, ny = mesh_for(world, wl)
     K, W = args.steps, max(args.warmup, 3)
     model = MSGNN(**CTOR).to(dev)
-    host = make_tri_mesh(nx, ny, S, rollout_steps=K + W, seed=rank)      # one simulation per rank (replicas)
-    N_nodes = host.x.shape[0]
-    data = host.to(dev)
-    runner = RolloutRunner(model, data, K + W, use_cuda_graph=True)
+    partitioned = world > 1 and args.multi != "replicas"
+    host = make_tri_mesh(nx, ny, S, rollout_steps=K + W, seed=0 if partitioned else rank)
+    N_global = host.x.shape[0]
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
+    if partitioned:
+        # ONE mesh cut over the ranks (blocks of coarsest cells, halo exchange per hop over NCCL)
+        part = partition_graph(host, world, rank)
+        runner = PartitionedRollout(model, host, K + W, dev, transport="nccl", part=part)
+        N_nodes = sum(part.n_owned)
+        N_total = N_global
+    else:
+        data = host.to(dev)
+        runner = RolloutRunner(model, data, K + W, use_cuda_graph=True)
+        N_nodes = N_global
+        N_total = N_global * world
+
     runner.run(W)                                                          # warm-up (includes graph capture)
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
     barrier()
-    l0 = lib.launch_count
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     ev0.record()
     runner.run(K)
@@ -199,10 +223,11 @@ def run_ours(args):
         t = torch.tensor([ms], device=dev)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         ms = float(t.item())
-    value = N_nodes * world * K / (ms * 1e-3)
+    value = N_total * K / (ms * 1e-3)
 
-    # ---- end-to-end through the public API with HOST (pinned) inputs: rollout_test(model, host_graph)
-    host_p = host.clone()
+    # ---- end-to-end through the public API with HOST (pinned) inputs
+    src_graph = part.graph if partitioned else host
+    host_p = src_graph.clone()
     for k in host_p.keys():
         v = getattr(host_p, k)
         if torch.is_tensor(v):
@@ -210,13 +235,27 @@ def run_ours(args):
     host_p.y = torch.empty(0, 2, K)                     # only its last dimension (number of steps) is read
     h2d = sum(getattr(host_p, k).numel() * getattr(host_p, k).element_size() for k in host_p.keys()
               if torch.is_tensor(getattr(host_p, k)) and k != "y")
-    out_host = torch.empty(N_nodes, 2, K, dtype=torch.float32).pin_memory()
+    n_out = N_nodes
+    out_host = torch.empty(K, n_out, 2, dtype=torch.float32).pin_memory()
 
-    def e2e_call():
-        g = host_p.to(dev, non_blocking=True)
-        pred = rollout_test(model, g)
-        out_host.copy_(pred, non_blocking=True)
-        torch.cuda.synchronize()
+    if partitioned:
+        part_p = part
+        owned_rows = torch.from_numpy(part.owned_rows).to(dev)
+
+        def e2e_call():
+            import copy
+            pp = copy.copy(part_p)
+            pp.graph = host_p                           # pinned local graph: PartitionedRollout uploads it
+            r = PartitionedRollout(model, None, K, dev, transport="nccl", part=pp)
+            preds = r.run()
+            out_host.copy_(preds[:, owned_rows], non_blocking=True)
+            torch.cuda.synchronize()
+    else:
+        def e2e_call():
+            g = host_p.to(dev, non_blocking=True)
+            pred = rollout_test(model, g)
+            out_host.copy_(pred.permute(2, 0, 1), non_blocking=True)
+            torch.cuda.synchronize()
 
     e2e_call()                                          # warm (plan build for the new tensors)
     barrier()
@@ -228,16 +267,24 @@ def run_ours(args):
         t = torch.tensor([e2e_s], device=dev)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         e2e_s = float(t.item())
-    e2e_value = N_nodes * world * K / e2e_s
+    e2e_value = N_total * K / e2e_s
+    halo_info = None
+    if partitioned:
+        hb = torch.tensor([float(runner.halo.bytes_sent) / max(runner.halo.n_exchanges, 1), float(sum(part.n_halo))], device=dev)
+        dist.all_reduce(hb, op=dist.ReduceOp.MAX)
+        halo_info = {"exchanges_per_step": runner.halo.n_exchanges // (K + W), "max_bytes_per_exchange": int(hb[0].item()),
+                     "max_halo_nodes_per_rank": int(hb[1].item())}
 
+    # ---- per-kernel timing of one eager (non-graph) step with CUDA events (roofline of the dominant kernel);
+    # a partitioned step exchanges halos, so every rank has to take part
+    alg = algorithmic_bytes(nx, ny)
+    if partitioned:                                      # per-rank share of the algorithmic bytes
+        alg = {k: (v / world if not isinstance(v, list) else [x / world for x in v]) for k, v in alg.items()}
+    kern = profile_kernels(runner, alg) if (partitioned or rank == 0) else None
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
         return
-
-    # ---- per-kernel timing of one eager step with CUDA events (roofline of the dominant kernel)
-    alg = algorithmic_bytes(nx, ny)
-    kern = profile_kernels(runner, alg)
     pk = peaks()
     dom = max(kern.values(), key=lambda r: r["ms_per_step"])
     if dom["bound"] == "hbm":
@@ -253,22 +300,32 @@ def run_ours(args):
         r = cpu_reference_rate(2, 1)
         cpu = {"value": r["value"], "unit": "node-steps/s", "cores": r["cores"], "kind": "port", "sample": r["sample"]}
 
+    if partitioned:
+        multi = (f"ONE mesh tri({nx},{ny}) = {N_global} nodes cut over {world} GPUs by blocks of coarsest cells "
+                 f"(every level sharded, {halo_info['exchanges_per_step']} NCCL halo exchanges per step, "
+                 f"<= {halo_info['max_bytes_per_exchange']} B each); per-GPU work fixed at cfg3's size")
+    elif world > 1:
+        multi = "independent simulations per rank (replicas, no collective)"
+    else:
+        multi = "single GPU"
     line = {"metric": "mSWE-GNN rollout node-steps/sec", "value": value, "unit": "node-steps/s", "n_gpus": world,
             "steps": K, "warmup": W, "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": f"{wl}: default config.yaml mSWE-GNN (K=4,F=64,mlp_layers=3,S=4) autoregressive rollout on "
-                                   f"tri({nx},{ny}) = {N_nodes} nodes per GPU; random-init weights seed 666; 30% wet nodes",
-                       "l2": f"working set {alg['total'] / 1e9:.1f} GB per step >> 126 MB L2 (inputs larger than L2, no flush needed)",
-                       "multi_gpu": "independent simulations per rank (replicas, no collective)" if world > 1 else "single GPU",
-                       "cuda_graph": True},
+                                   f"tri({nx},{ny}) = {N_global} nodes ({N_nodes} owned per GPU); random-init weights seed 666; 30% wet nodes",
+                       "l2": f"working set {alg['total'] / 1e9:.1f} GB per step per GPU >> 126 MB L2 (inputs larger than L2, no flush needed)",
+                       "multi_gpu": multi, "cuda_graph": not partitioned},
             "clocks": clocks,
-            "e2e": {"value": e2e_value, "unit": "node-steps/s", "h2d_bytes_per_step": h2d // K, "d2h_bytes_per_step": N_nodes * 8,
-                    "what": "rollout_test(model, host_graph): pinned host graph -> device, plan build, K steps, predictions -> pinned host"},
+            "e2e": {"value": e2e_value, "unit": "node-steps/s", "h2d_bytes_per_step": h2d // K, "d2h_bytes_per_step": n_out * 8,
+                    "what": ("PartitionedRollout(model, pinned local graph): upload, plan build, K steps with halo exchange, owned "
+                             "predictions -> pinned host (host-side partitioning excluded)") if partitioned else
+                            "rollout_test(model, host_graph): pinned host graph -> device, plan build, K steps, predictions -> pinned host"},
             "gpu_launches": per_step_launches * K,
             "roofline": roof,
             "hbm_fraction_whole_step": {"algorithmic_GB_per_step": alg["total"] / 1e9, "achieved_GBps": step_gbs,
                                         "frac_of_peak": step_gbs / pk["hbm"], "peak_source": pk["hbm_src"]},
             "kernels": sorted(kern.values(), key=lambda r: -r["ms_per_step"]),
+            "halo": halo_info,
             "cpu_baseline": cpu}
     print(json.dumps(line), flush=True)
     if world > 1:
@@ -306,6 +363,7 @@ def profile_kernels(runner, alg):
         wrap(n)
     try:
         reps = 3
+        runner.reset()                                   # step counter back to 0: stay inside the BC / prediction buffers
         for _ in range(reps):
             runner._one_step()
         torch.cuda.synchronize()
@@ -344,6 +402,8 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default=None, choices=[None, *WORKLOADS])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--multi", default="partitioned", choices=["partitioned", "replicas"],
+                    help="N>1: one mesh partitioned over the GPUs with halo exchange (default) or independent replicas")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

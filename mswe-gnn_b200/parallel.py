@@ -286,7 +286,7 @@ class PartitionedRollout:
         rank, world = dist.get_rank(group), dist.get_world_size(group)
         self.part = part if part is not None else partition_graph(graph_cpu, world, rank)
         self.model, self.T = model, int(n_steps)
-        self.graph = self.part.graph.to(device)
+        self.graph = self.part.graph.to(device, non_blocking=True)
         self.halo = HaloExchanger(self.part, device, transport, group)
         model._check_input(self.graph)
         multiscale = model.type_model == "MSGNN"
@@ -314,6 +314,10 @@ class PartitionedRollout:
         for s in range(self.part.num_scales):
             self.halo.exchange(self.x, s)
         self.launches_per_step = lib.launch_count - c0
+
+    def reset(self):
+        self.x.copy_(self.graph.x)
+        self.step.zero_()
 
     def run(self, n_steps: Optional[int] = None):
         for _ in range(self.T if n_steps is None else n_steps):
