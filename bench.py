@@ -20,6 +20,8 @@ import time
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
+if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
+    os.environ["NCCL_DEBUG"] = "WARN"                  # keep NCCL's version banner off stdout: rank 0 prints ONE JSON line
 
 import torch  # noqa: E402
 
@@ -133,6 +135,16 @@ def cpu_reference_rate(steps, warmup, threads=None):
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
+        return
+    if args.workload in TRAIN_WORKLOADS:
+        r = cpu_training_rate(args.workload)
+        line = {"impl": "reference", "metric": "mSWE-GNN training node-steps/sec (forward+backward+AdamW)", "value": r["value"],
+                "unit": "node-steps/s", "n_gpus": args.gpus, "steps": 1, "warmup": 1, "ms_per_step": None, "higher_is_better": True,
+                "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+                "config": {"workload": f"{args.workload}: CPU arm timed on a bounded sample: {r['sample']}"},
+                "cpu_baseline": {"value": r["value"], "unit": "node-steps/s", "cores": r["cores"], "kind": "port", "sample": r["sample"]},
+                "e2e": {"value": r["value"], "unit": "node-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}
+        print(json.dumps(line), flush=True)
         return
     steps, warmup = min(args.steps, 3), min(args.warmup, 1)
     r = cpu_reference_rate(steps, warmup)
@@ -332,6 +344,202 @@ def run_ours(args):
         dist.destroy_process_group()
 
 
+
+# --------------------------------------------------------------------------------------------------
+# training workloads (secondary metric: BASELINE.json configs[1] and configs[4])
+# --------------------------------------------------------------------------------------------------
+TRAIN_WORKLOADS = {
+    # name: (model, (nx, ny), graphs per rank, rollout steps)
+    "cfg2-train": ("GNN", (160, 160), 8, 1),      # single-scale SWE-GNN, 8 x 51,201-node meshes, 1 GPU
+    "cfg5-train": ("MSGNN", (224, 224), 4, 1),    # data parallel: 4 x 133,284-node simulations per GPU, gradient all-reduce
+}
+
+
+def _train_setup(wl, rank, dev, small=False):
+    from mswe_gnn_b200.models.gnn import GNN, MSGNN
+    from mswe_gnn_b200.utils.data import Batch
+    from mswe_gnn_b200.utils.synthetic import make_single_scale_mesh, make_tri_mesh
+    kind, (nx, ny), G, R = TRAIN_WORKLOADS[wl]
+    if small:
+        nx, ny, G = 64, 64, 1
+    if kind == "GNN":
+        cfg = {k: v for k, v in MODEL_CFG.items() if k not in ("learned_pooling", "skip_connections")}
+        ctor = dict(num_node_features=8, num_edge_features=1, previous_t=3, n_GNN_layers=2, **cfg)
+        graphs = [make_single_scale_mesh(nx, ny, rollout_steps=R, seed=1000 * rank + i) for i in range(G)]
+        model = GNN(**ctor)
+    else:
+        ctor = CTOR
+        graphs = [make_tri_mesh(nx, ny, S, rollout_steps=R, seed=1000 * rank + i) for i in range(G)]
+        model = MSGNN(**ctor)
+    batch = Batch.from_data_list(graphs)
+    return kind, ctor, model.to(dev) if dev is not None else model, batch, R, (nx, ny, G)
+
+
+def cpu_training_rate(wl, threads=None):
+    """Reference training step (oracle port of training/train.py:125-145 + torch.autograd) on the host cores."""
+    from oracle import swe_oracle as O
+    threads = threads or os.cpu_count()
+    torch.set_num_threads(threads)
+    kind, ctor, model, batch, R, (nx, ny, G) = _train_setup(wl, 0, None, small=True)
+    g = batch._graphs[0]
+    spec = O.ModelSpec(kind, **ctor)
+    sd = {k: v.detach().clone().requires_grad_(True) for k, v in model.state_dict().items()}
+    times = []
+    for _ in range(2):
+        t0 = time.perf_counter()
+        loss = O.training_step(sd, spec, g, R)
+        loss.backward()
+        times.append(time.perf_counter() - t0)
+    n = g.x.shape[0] * R
+    return dict(value=n / times[-1], cores=threads,
+                sample=f"1 training step (fwd+bwd, {R} rollout step) of the same {kind} on one tri({nx},{ny}) graph ({g.x.shape[0]} nodes), "
+                       f"torch {torch.__version__} CPU autograd, {threads} threads")
+
+
+def run_train(args):
+    import torch.distributed as dist
+    import mswe_gnn_b200  # noqa: F401
+    from mswe_gnn_b200 import lib
+    from mswe_gnn_b200.training.train import training_step
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    lib.load()
+    wl = args.workload
+    kind, ctor, model, batch_host, R, (nx, ny, G) = _train_setup(wl, rank, dev)
+    for k in batch_host.keys():
+        v = getattr(batch_host, k)
+        if torch.is_tensor(v):
+            setattr(batch_host, k, v.pin_memory())
+    batch = batch_host.to(dev)
+    opt = torch.optim.AdamW(model.parameters(), lr=3e-3, weight_decay=0.0)       # config.yaml lr_info
+    n_nodes = batch.x.shape[0]
+    K, W = args.steps, max(args.warmup, 3)
+
+    def step(b):
+        opt.zero_grad(set_to_none=True)
+        loss = training_step(model, b, R, only_where_water=True, velocity_scaler=7.0)
+        torch.nn.utils.clip_grad_norm_(model.parameters(), 1.0)                   # main.py:109 gradient_clip_val=1
+        opt.step()
+        return loss
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(W):
+        step(batch)
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    barrier()
+    l0 = lib.launch_count
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev0.record()
+    for _ in range(K):
+        step(batch)
+    ev1.record()
+    barrier()
+    launches = lib.launch_count - l0
+    ms = ev0.elapsed_time(ev1)
+    clocks = sampler.stop() if rank == 0 else None
+    # e2e: the batch comes from pinned host memory every step, the loss goes back to the host
+    h2d = sum(getattr(batch_host, k).numel() * getattr(batch_host, k).element_size() for k in batch_host.keys()
+              if torch.is_tensor(getattr(batch_host, k)))
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(K):
+        loss_host = float(step(batch_host.to(dev, non_blocking=True)))
+    barrier()
+    e2e_s = time.perf_counter() - t0
+    if world > 1:
+        t = torch.tensor([ms, e2e_s], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms, e2e_s = float(t[0]), float(t[1])
+    value = n_nodes * R * world * K / (ms * 1e-3)
+    kern = profile_train_kernels(lambda: step(batch))
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+    pk = peaks()
+    dom = max(kern.values(), key=lambda r: r["ms_per_step"])
+    cpu = None
+    if world == 1 and not args.no_cpu_baseline:
+        r = cpu_training_rate(wl)
+        cpu = {"value": r["value"], "unit": "node-steps/s", "cores": r["cores"], "kind": "port", "sample": r["sample"]}
+    line = {"metric": "mSWE-GNN training node-steps/sec (forward+backward+AdamW)", "value": value, "unit": "node-steps/s",
+            "n_gpus": world, "steps": K, "warmup": W, "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": f"{wl}: {kind} (config.yaml hyper-parameters: F=64, K=4, mlp_layers=3) training step, {G} x tri({nx},{ny}) "
+                                   f"graphs per GPU = {n_nodes} nodes, {R} rollout step(s), loss RMSE on wet cells, grad-clip 1, AdamW",
+                       "l2": "saved activations >> 126 MB L2 (inputs larger than L2, no flush needed)",
+                       "multi_gpu": "data parallel over simulations, one all-reduce of the flat fp32 gradient per step" if world > 1 else "single GPU"},
+            "clocks": clocks,
+            "e2e": {"value": n_nodes * R * world * K / e2e_s, "unit": "node-steps/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4,
+                    "what": "training_step(model, batch.to(device)) from pinned host memory every step, loss.item() back"},
+            "gpu_launches": launches,
+            "roofline": {"bound": "tensor", "kernel": dom["name"], "achieved": dom["tflops"], "peak": pk["bf16"], "unit": "TFLOP/s",
+                         "frac": dom["tflops"] / pk["bf16"], "traffic": None,
+                         "peak_source": pk["hbm_src"] + " (sustained bf16; the backward GEMMs run in exact fp32 on CUDA cores this round)"},
+            "kernels": sorted(kern.values(), key=lambda r: -r["ms_per_step"])[:12],
+            "cpu_baseline": cpu}
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def profile_train_kernels(step_fn):
+    """CUDA-event pair around every C-ABI launch of one training step, grouped by entry point."""
+    from mswe_gnn_b200 import lib
+    records, orig = [], {}
+    names = [n[4:] for n in lib.SIGNATURES if n.startswith("swe_") and hasattr(lib, n[4:]) and callable(getattr(lib, n[4:]))
+             and n[4:] not in ("mlp_layer_bwd_dx_grid", "mlp_layer_bwd_dw_grid", "gate_tc_image_bytes", "hop_tc_image_bytes", "csr_build")]
+
+    def wrap(name):
+        fn = getattr(lib, name)
+        orig[name] = fn
+
+        def inner(*a, **k):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            r = fn(*a, **k)
+            e1.record()
+            fl = 0.0
+            if name == "mlp_layer_bwd_dx" and a[11] is not None:
+                fl = 2.0 * a[4] * a[5] * a[10]
+            elif name == "mlp_layer_bwd_dw":
+                fl = 2.0 * a[1] * a[2] * a[4]
+            records.append((name, e0, e1, fl))
+            return r
+        setattr(lib, name, inner)
+
+    for n in names:
+        wrap(n)
+    try:
+        step_fn()
+        torch.cuda.synchronize()
+    finally:
+        for n, fn in orig.items():
+            setattr(lib, n, fn)
+    out = {}
+    for name, e0, e1, fl in records:
+        r = out.setdefault(name, dict(name="swe_" + name, ms_per_step=0.0, launches_per_step=0, flops_per_step=0.0))
+        r["ms_per_step"] += e0.elapsed_time(e1)
+        r["launches_per_step"] += 1
+        r["flops_per_step"] += fl
+    tot = sum(r["ms_per_step"] for r in out.values())
+    for r in out.values():
+        r["tflops"] = r["flops_per_step"] / (r["ms_per_step"] * 1e-3) / 1e12 if r["ms_per_step"] > 0 else 0.0
+        r["share"] = r["ms_per_step"] / tot if tot else 0.0
+    return out
+
+
 def profile_kernels(runner, alg):
     """One eager (non-graph) step with a CUDA-event pair around every C-ABI launch, grouped by
     kernel.  Events are recorded on torch's current stream, the stream the kernels launch on."""
@@ -400,13 +608,15 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default=None, choices=[None, *WORKLOADS])
+    ap.add_argument("--workload", default=None, choices=[None, *WORKLOADS, *TRAIN_WORKLOADS])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--multi", default="partitioned", choices=["partitioned", "replicas"],
                     help="N>1: one mesh partitioned over the GPUs with halo exchange (default) or independent replicas")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)
+    elif args.workload in TRAIN_WORKLOADS:
+        run_train(args)
     else:
         run_ours(args)
 

@@ -152,3 +152,31 @@ def rollout_test(model, batch, use_cuda_graph: Optional[bool] = None):
     runner = RolloutRunner(model, temp, final_step, use_cuda_graph)
     preds = runner.run()
     return preds.permute(1, 2, 0)
+
+
+def training_step(model, batch, rollout_steps: int = 1, type_loss: str = "RMSE", only_where_water: bool = True,
+                  velocity_scaler: float = 7.0, group=None):
+    """One training step of the reference's ``LightningTrainer.training_step`` (``training/train.py:125-145``):
+    BPTT through ``rollout_steps`` model calls (no detach), mean of the per-step losses, ``backward()``; with a
+    process group the flat gradient is all-reduced (data parallel over simulations).  Returns the detached loss.
+    The optimizer step stays with the caller (``torch.optim.AdamW`` in the reference, ``train.py:147-155``)."""
+    from .loss import loss_function
+    temp = adapt_batch_training(batch) if _is_batch(batch) else batch.clone()
+    dyn = model.previous_t * NUM_WATER_VARS
+    roll = []
+    x = temp.x
+    for i in range(rollout_steps):
+        xd = x[:, -dyn:].clone()
+        xd = apply_boundary_condition(xd, temp.BC[:, :, i], temp.node_BC, type_BC=int(temp.type_BC))
+        temp.x = torch.cat((x[:, :-dyn], xd), 1)
+        preds = model(temp)
+        x = use_prediction(temp.x, preds, model.previous_t)
+        roll.append(loss_function(preds, temp.y[:, :, i], temp, None, type_loss=type_loss,
+                                  only_where_water=only_where_water, velocity_scaler=velocity_scaler))
+    loss = torch.stack(roll).mean()
+    loss.backward()
+    if group is not None or (torch.distributed.is_available() and torch.distributed.is_initialized()
+                             and torch.distributed.get_world_size() > 1):
+        from ..parallel import allreduce_gradients
+        allreduce_gradients(list(model.parameters()), group)
+    return loss.detach()
