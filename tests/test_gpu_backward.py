@@ -175,3 +175,33 @@ def test_backward_is_deterministic():
         runs.append([q.grad.clone() for q in model.parameters()])
     for a, b in zip(*runs):
         assert torch.equal(a, b)
+
+
+def test_training_step_on_a_batch_vs_oracle():
+    """The public `training_step` (Batch -> adapt_batch_training -> BPTT -> loss -> backward) against the oracle's
+    restatement of training/train.py:125-145 on the same adapted batch (3 multiscale graphs, 2 rollout steps)."""
+    from mswe_gnn_b200.models.gnn import MSGNN
+    from mswe_gnn_b200.training.train import training_step
+    from mswe_gnn_b200.utils.data import Batch
+    ctor = dict(num_node_features=8, num_edge_features=1, num_scales=3, previous_t=3, hid_features=16, mlp_layers=2,
+                seed=3, learned_residuals=True, mlp_activation="prelu", gnn_activation="tanh", with_WL=True, K=2)
+    graphs = [make_tri_mesh(16, 8, 3, seed=s, rollout_steps=2) for s in (1, 2, 3)]
+    batch = Batch.from_data_list(graphs)
+    model = MSGNN(**ctor).to(DEV)
+    loss = training_step(model, batch.to(DEV), rollout_steps=2, only_where_water=True, velocity_scaler=7.0)
+    ours = {k: p.grad for k, p in model.named_parameters()}
+    spec = O.ModelSpec("MSGNN", **ctor)
+    refs = []
+    for dt in (torch.float64, torch.float32):
+        sd = _sd_grad(model, dt)
+        ab = O.adapt_batch(batch, graphs)
+        for k in ab.keys():
+            v = getattr(ab, k)
+            if torch.is_tensor(v) and v.is_floating_point():
+                setattr(ab, k, v.to(dt))
+        l = O.training_step(sd, spec, ab, 2)
+        l.backward()
+        refs.append({k: v.grad for k, v in sd.items()})
+        if dt == torch.float64:
+            assert abs(float(loss) - float(l.detach())) <= 2e-5 * max(1.0, abs(float(l.detach())))
+    _check_grads(ours, refs[0], refs[1])
