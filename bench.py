@@ -547,7 +547,7 @@ def profile_kernels(runner, alg):
     from mswe_gnn_b200 import lib
     records = []
     orig = {}
-    names = ["node_encode_fwd", "edge_gate_fwd", "edge_gate_tc_fwd", "node_linear_fwd", "propagate_hop_fwd", "propagate_hop_tc_fwd", "pool_mean_fwd",
+    names = ["node_encode_fwd", "edge_gate_fwd", "edge_gate_tc_fwd", "edge_gate_tc_dec_fwd", "gate_partials_tc", "node_linear_fwd", "propagate_hop_fwd", "propagate_hop_tc_fwd", "pool_mean_fwd",
              "decode_head_fwd", "edge_encode_fwd", "apply_bc", "step_advance"]
 
     def wrap(name):
@@ -564,6 +564,8 @@ def profile_kernels(runner, alg):
                 meta = ("hop", int(a[6]), a[7] is not None)          # n_dst, has filter
             elif name in ("edge_gate_fwd", "edge_gate_tc_fwd"):
                 meta = ("gate", int(a[6]), a[3] is not None)         # n_edges, has edge features
+            elif name == "edge_gate_tc_dec_fwd":
+                meta = ("gate", int(a[5]), a[2] is not None)
             records.append((name, e0, e1, meta))
             return r
         setattr(lib, name, inner)

@@ -150,6 +150,18 @@ int swe_edge_gate_tc_fwd(const float* xs, const float* xd_src, const float* xd_d
                          int32_t k1, const int32_t* act3, const float* const* slope3, int32_t normalize,
                          float* s_out, float* dbg, void* stream);
 
+/* Decomposed first layer of the edge MLP: W1·[x_s[r]|x_s[c]|x_d[r]|x_d[c]|a] = P_src[r] + P_dst[c] + E·a with
+ *   P_src[n] = A·x_s[n] + C·x_d[n]   (role 0),   P_dst[n] = B·x_s[n] + D·x_d[n]   (role 1; xd NULL drops D·x_d),
+ * evaluated once per NODE (2·128² MAC) instead of once per edge.  swe_gate_partials_tc writes one table
+ * p_out[row_lo + i, 0:128) for i < n_rows; swe_edge_gate_tc_dec_fwd is swe_edge_gate_tc_fwd reading the tables
+ * (same reference span models/gnn.py:414-426; the sum is re-associated, ~1e-7 relative). */
+int swe_gate_partials_tc(const float* xs, const float* xd, int32_t row_lo, int32_t n_rows, const void* image,
+                         int32_t k1, int32_t role, float* p_out, void* stream);
+int swe_edge_gate_tc_dec_fwd(const float* p_src, const float* p_dst, const float* a, const int32_t* src,
+                             const int32_t* dst, int64_t n_edges, const void* image, int32_t k1,
+                             const int32_t* act3, const float* const* slope3, int32_t normalize, float* s_out,
+                             void* stream);
+
 /* ---------------------------------------------------------------------------------------------
  * Hop with the F×F filter on tcgen05 tensor cores (F = 64; 3xTF32, fp32 accumulation in TMEM).
  * Same contract and reference span as swe_propagate_hop_fwd with wt != NULL (models/gnn.py:428-443);

@@ -92,12 +92,17 @@ struct GateTcParams {
     float* s_out;
     float* dbg;                 // optional [128*128 + 128*128 + 128*64] raw accumulators of tile 0
     long long* trace;           // optional [3 roles][16 tiles][8 events] clock64 stamps of CTA 0 (profiling aid)
+    // layer-0 input segments gathered and multiplied on the tensor core, in order (0 x_s[r], 1 x_s[c], 2 x_d[r],
+    // 3 x_d[c], 4 a_e); MODE 0: all present ones; MODE 1 (decomposed): only a_e, the node part comes from the
+    // per-node partial tables; MODE 2 (partials): the kernel IS the producer of such a table for a node range
+    int n_seg; int segs[5];
+    const float* p_src; const float* p_dst;      // MODE 1: [*, 128] partial tables indexed by plan id
+    float* p_out; int row_lo;                    // MODE 2: output table rows [row_lo, row_lo + n_edges)
 };
 
-__device__ __forceinline__ int l1_chunk_segment(int i, bool has_xd_dst) {
-    // i-th ACTIVE chunk of layer 0 -> input segment (0 x_s[r], 1 x_s[c], 2 x_d[r], 3 x_d[c], 4 a_e)
-    const int sg = i >> 1;
-    return sg < 3 ? sg : ((sg == 3 && has_xd_dst) ? 3 : 4);
+__device__ __forceinline__ int l1_chunk_segment(const GateTcParams& p, int i) {
+    // i-th ACTIVE chunk of layer 0 -> input segment (two 32-column chunks per 64-wide segment)
+    return p.segs[i >> 1];
 }
 
 // "leaky family" activations (none / relu / leakyrelu / prelu) are v > 0 ? v : slope * v
@@ -121,7 +126,12 @@ __device__ __forceinline__ float leaky_slope(int act, const float* slope_p) {
 // row workers:  G(t_0) ;  for i: { E1(t_i) ; G(t_{i+1})[0,h) ; E2(t_i) ; G(t_{i+1})[h,n_l1) ; E3(t_i) }
 // so the tensor pipe works on the next tile's layer 0 while the row workers run this tile's
 // epilogues, and on this tile's layers 1-2 while they gather the next tile's inputs.
-template <bool GENERIC>
+//
+// MODE 1 (decomposed layer 0): W1·z = (A·x_s[r] + C·x_d[r]) + (B·x_s[c] + D·x_d[c]) + E·a_e.  The two brackets only
+// depend on ONE node, so they are evaluated once per node (MODE 2 launches of this kernel, 2·128² MAC per node)
+// instead of once per edge (4·64·128 MAC per edge, ~3 edges per node); the per-edge layer-0 work shrinks from 10
+// K-chunks to the 2 of a_e (none for un-pool calls), and epilogue 1 adds P_src[r] + P_dst[c] in fp32.
+template <bool GENERIC, int MODE>
 __global__ void __launch_bounds__(N_THREADS, 1) edge_gate_tc_kernel(const __grid_constant__ GateTcParams p) {
     extern __shared__ unsigned char smem_raw[];
     // 1 KB alignment by OFFSETTING the shared array: integer arithmetic on the pointer value loses the address
@@ -135,8 +145,7 @@ __global__ void __launch_bounds__(N_THREADS, 1) edge_gate_tc_kernel(const __grid
     uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(bar + 1);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const bool has_xd_dst = p.xd_dst != nullptr, has_a = p.a != nullptr;
-    const int n_l1 = 2 * (3 + (has_xd_dst ? 1 : 0) + (has_a ? 1 : 0));      // active layer-0 chunks
+    const int n_l1 = 2 * p.n_seg;                                            // active layer-0 chunks
     const int h_l1 = n_l1 / 2;
     const long long n_tiles_all = (p.n_edges + TILE_ROWS - 1) / TILE_ROWS;
     const int n_my = (int)((n_tiles_all - blockIdx.x + gridDim.x - 1) / gridDim.x);   // tiles of this CTA
@@ -179,11 +188,11 @@ __global__ void __launch_bounds__(N_THREADS, 1) edge_gate_tc_kernel(const __grid
             if (threadIdx.x < TILE_ROWS) {
                 long long e = e0 + threadIdx.x;
                 if (e >= p.n_edges) e = p.n_edges - 1;
-                ids[threadIdx.x] = __ldg(p.src + e);
+                ids[threadIdx.x] = MODE == 2 ? (int32_t)(p.row_lo + e) : __ldg(p.src + e);
             } else {
                 long long e = e0 + threadIdx.x - TILE_ROWS;
                 if (e >= p.n_edges) e = p.n_edges - 1;
-                ids[threadIdx.x] = __ldg(p.dst + e);                  // ids[128 + r]
+                ids[threadIdx.x] = MODE == 2 ? (int32_t)(p.row_lo + e) : __ldg(p.dst + e);     // ids[128 + r]
             }
             asm volatile("bar.sync 1, 256;" ::: "memory");
         };
@@ -191,7 +200,7 @@ __global__ void __launch_bounds__(N_THREADS, 1) edge_gate_tc_kernel(const __grid
             const long long e0 = ((long long)blockIdx.x + (long long)i * gridDim.x) * TILE_ROWS;
             const int32_t* ids = s_ids + (i & 1) * 2 * TILE_ROWS;
             auto issue = [&](int c, float4 (&v)[4]) {                 // 4 independent 16-B loads per thread
-                const int sg = l1_chunk_segment(c, has_xd_dst);
+                const int sg = l1_chunk_segment(p, c);
                 const int koff = (c & 1) * KC + piece * 4;
                 if (sg == 4) {
 #pragma unroll
@@ -207,6 +216,7 @@ __global__ void __launch_bounds__(N_THREADS, 1) edge_gate_tc_kernel(const __grid
                     for (int j = 0; j < 4; ++j) v[j] = ldg4(base + (long long)idp[32 * j] * GF + koff);
                 }
             };
+            if (c_lo >= c_hi) return;                                  // decomposed layer 0 of an un-pool call: nothing to gather
             float4 cur[4], nxt[4];
             issue(c_lo, cur);
 #pragma unroll 1
@@ -230,9 +240,30 @@ __global__ void __launch_bounds__(N_THREADS, 1) edge_gate_tc_kernel(const __grid
             }
         };
         // D -> bias, activation -> hi/lo -> TMEM A operand; this thread owns 64 columns of its lane
-        auto epilogue_mid = [&](int layer, uint32_t ph, bool dump) {
-            mbar_wait(&bar->d_full[layer], ph);
-            tc_fence_after_sync();
+        auto epilogue_mid = [&](int layer, uint32_t ph, bool dump, int i) {
+            // MODE 1, layer 0: the node part of W1·z comes from the per-node tables; fetch it before waiting for D
+            float4 padd[16];
+            const bool with_p = MODE == 1 && layer == 0;
+            if (with_p) {
+                const int32_t* ids = s_ids + (i & 1) * 2 * TILE_ROWS;
+                const float* ps = p.p_src + (long long)ids[row] * GH + hf * 64;
+                const float* pd = p.p_dst + (long long)ids[TILE_ROWS + row] * GH + hf * 64;
+#pragma unroll
+                for (int j = 0; j < 16; ++j) {
+                    const float4 x = ldg4(ps + 4 * j), y = ldg4(pd + 4 * j);
+                    padd[j] = make_float4(x.x + y.x, x.y + y.y, x.z + y.z, x.w + y.w);
+                }
+            }
+            const bool have_d = !(with_p && n_l1 == 0);               // un-pool calls have no a_e: no layer-0 MMA at all
+            if (have_d) {
+                mbar_wait(&bar->d_full[layer], ph);
+                tc_fence_after_sync();
+            } else if (i > 0) {
+                // nothing of this tile to wait for, but the activations written below are still being read by the
+                // layer-2 MMA of the previous tile until that one completes
+                mbar_wait(&bar->d_full[2], (uint32_t)(i - 1) & 1);
+                tc_fence_after_sync();
+            }
             const uint32_t dcol = (layer == 0 ? COL_D_A : COL_D_B) + hf * 64;
             const float* bias = s_bias + layer * 128 + hf * 64;
             const int act = p.act[layer];
@@ -240,8 +271,23 @@ __global__ void __launch_bounds__(N_THREADS, 1) edge_gate_tc_kernel(const __grid
 #pragma unroll
             for (int cb = 0; cb < 2; ++cb) {
                 uint32_t v[32];
-                tmem_ld32(lane_addr + dcol + cb * 32, v);
-                tmem_wait_ld();
+                if (have_d) {
+                    tmem_ld32(lane_addr + dcol + cb * 32, v);
+                    tmem_wait_ld();
+                } else {
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) v[j] = 0u;
+                }
+                if (with_p) {
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) {
+                        const float4 t = padd[cb * 8 + j];
+                        v[4 * j] = __float_as_uint(__uint_as_float(v[4 * j]) + t.x);
+                        v[4 * j + 1] = __float_as_uint(__uint_as_float(v[4 * j + 1]) + t.y);
+                        v[4 * j + 2] = __float_as_uint(__uint_as_float(v[4 * j + 2]) + t.z);
+                        v[4 * j + 3] = __float_as_uint(__uint_as_float(v[4 * j + 3]) + t.w);
+                    }
+                }
                 if (dump) {
                     float* d = p.dbg + (size_t)layer * 128 * 128 + (size_t)row * 128 + hf * 64 + cb * 32;
 #pragma unroll
@@ -324,6 +370,34 @@ __global__ void __launch_bounds__(N_THREADS, 1) edge_gate_tc_kernel(const __grid
         const bool tr = p.trace != nullptr && blockIdx.x == 0 && lane == 0 && (warp == 0 || warp == 4);
         long long* trp = p.trace + (warp == 0 ? 0 : 1) * 128;
 #define SWE_STAMP(i_, ev_) do { if (tr && (i_) < 16) trp[(i_) * 8 + (ev_)] = clock64(); } while (0)
+        if (MODE == 2) {
+            // partial-table producer: D alternates between the two accumulators, so the tensor pipe works on tile
+            // i+1 while tile i is written out.   G(t_0) ; for i: { G(t_{i+1}) ; OUT(t_i) }
+            if (n_my > 0) { load_ids(0); gather(0, 0, n_l1); }
+#pragma unroll 1
+            for (int i = 0; i < n_my; ++i) {
+                if (i + 1 < n_my) { load_ids(i + 1); gather(i + 1, 0, n_l1); }
+                const int buf = i & 1;
+                mbar_wait(&bar->d_full[buf], (uint32_t)(i >> 1) & 1);
+                tc_fence_after_sync();
+                const long long e = ((long long)blockIdx.x + (long long)i * gridDim.x) * TILE_ROWS + row;
+                float* o = p.p_out + ((long long)p.row_lo + e) * GH + hf * 64;
+#pragma unroll
+                for (int cb = 0; cb < 2; ++cb) {
+                    uint32_t v[32];
+                    tmem_ld32(lane_addr + (buf ? COL_D_B : COL_D_A) + hf * 64 + cb * 32, v);
+                    tmem_wait_ld();
+                    if (e < p.n_edges) {
+#pragma unroll
+                        for (int j = 0; j < 32; j += 4)
+                            stg4(o + cb * 32 + j, make_float4(__uint_as_float(v[j]), __uint_as_float(v[j + 1]),
+                                                              __uint_as_float(v[j + 2]), __uint_as_float(v[j + 3])));
+                    }
+                }
+                tc_fence_before_sync();
+                mbar_arrive(&bar->a_ready[buf]);                      // accumulator `buf` may be overwritten
+            }
+        } else {
         if (n_my > 0) { load_ids(0); gather(0, 0, n_l1); }
 #pragma unroll 1
         for (int i = 0; i < n_my; ++i) {
@@ -331,16 +405,17 @@ __global__ void __launch_bounds__(N_THREADS, 1) edge_gate_tc_kernel(const __grid
             const bool dump = p.dbg != nullptr && i == 0 && blockIdx.x == 0;
             const bool more = i + 1 < n_my;
             SWE_STAMP(i, 0);
-            epilogue_mid(0, ph, dump);
+            epilogue_mid(0, ph, dump, i);
             SWE_STAMP(i, 1);
             if (more) { load_ids(i + 1); gather(i + 1, 0, h_l1); }
             SWE_STAMP(i, 2);
-            epilogue_mid(1, ph, dump);
+            epilogue_mid(1, ph, dump, i);
             SWE_STAMP(i, 3);
             if (more) gather(i + 1, h_l1, n_l1);
             SWE_STAMP(i, 4);
             epilogue_final(i, ph, dump);
             SWE_STAMP(i, 5);
+        }
         }
 #undef SWE_STAMP
     } else if (warp == 8) {
@@ -349,6 +424,7 @@ __global__ void __launch_bounds__(N_THREADS, 1) edge_gate_tc_kernel(const __grid
         // =====================================================================================
         if (lane == 0) {
             uint32_t w_cnt = 0;
+            bool n_my_done = false;
             auto load = [&](const unsigned char* srcp, uint32_t bytes) {
                 const uint32_t slot = w_cnt % W_STAGES;
                 mbar_wait(&bar->w_empty[slot], ((w_cnt / W_STAGES) & 1) ^ 1);
@@ -358,10 +434,14 @@ __global__ void __launch_bounds__(N_THREADS, 1) edge_gate_tc_kernel(const __grid
             };
             auto load_l1 = [&](int c_lo, int c_hi) {
                 for (int c = c_lo; c < c_hi; ++c)
-                    load(p.img + img_l1_off(2 * l1_chunk_segment(c, has_xd_dst) + (c & 1)), SLOT_BYTES);
+                    load(p.img + img_l1_off(2 * l1_chunk_segment(p, c) + (c & 1)), SLOT_BYTES);
             };
             if (n_my > 0) load_l1(0, n_l1);
-            for (int i = 0; i < n_my; ++i) {
+            if (MODE == 2) {
+                for (int i = 1; i < n_my; ++i) load_l1(0, n_l1);
+                n_my_done = true;
+            }
+            for (int i = 0; i < n_my && !n_my_done; ++i) {
                 const bool more = i + 1 < n_my;
                 for (int c = 0; c < 4; ++c) load(p.img + img_l2_off(p.n_l1_img, c), SLOT_BYTES);
                 if (more) load_l1(0, h_l1);
@@ -378,6 +458,8 @@ __global__ void __launch_bounds__(N_THREADS, 1) edge_gate_tc_kernel(const __grid
             const uint32_t a_ring_u32 = smem_u32(a_ring), w_ring_u32 = smem_u32(w_ring);
             uint32_t a_cnt = 0, w_cnt = 0;
             // layer 0 (SS): D_a (+)= A_chunk · W_chunkᵀ for chunks [c_lo, c_hi)
+            uint32_t d_l1 = COL_D_A;                                   // accumulator of layer 0 (MODE 2 alternates)
+            int dfull_l1 = 0;
             auto mma_l1 = [&](int c_lo, int c_hi, bool last) {
                 for (int c = c_lo; c < c_hi; ++c, ++a_cnt, ++w_cnt) {
                     const uint32_t sa = a_cnt % A_STAGES, sw = w_cnt % W_STAGES;
@@ -390,14 +472,14 @@ __global__ void __launch_bounds__(N_THREADS, 1) edge_gate_tc_kernel(const __grid
                     for (int ks = 0; ks < KC / 8; ++ks) {
                         const uint64_t dah = make_desc_sw128(a_hi + ks * 32), dal = make_desc_sw128(a_lo + ks * 32);
                         const uint64_t dwh = make_desc_sw128(w_hi + ks * 32), dwl = make_desc_sw128(w_lo + ks * 32);
-                        mma_tf32_ss(tmem_base + COL_D_A, dal, dwh, idesc128, (c | ks) ? 1u : 0u);
-                        mma_tf32_ss(tmem_base + COL_D_A, dah, dwl, idesc128, 1u);
-                        mma_tf32_ss(tmem_base + COL_D_A, dah, dwh, idesc128, 1u);
+                        mma_tf32_ss(tmem_base + d_l1, dal, dwh, idesc128, (c | ks) ? 1u : 0u);
+                        mma_tf32_ss(tmem_base + d_l1, dah, dwl, idesc128, 1u);
+                        mma_tf32_ss(tmem_base + d_l1, dah, dwh, idesc128, 1u);
                     }
                     mma_commit(&bar->a_empty[sa]);
                     mma_commit(&bar->w_empty[sw]);
                 }
-                if (last) mma_commit(&bar->d_full[0]);
+                if (last && n_l1 > 0) mma_commit(&bar->d_full[dfull_l1]);
             };
             // layers 1 / 2 (TS): A from TMEM, D_b (layer 1: 128 columns, layer 2: 64 columns)
             auto mma_ts = [&](int layer, uint32_t ph) {
@@ -425,6 +507,16 @@ __global__ void __launch_bounds__(N_THREADS, 1) edge_gate_tc_kernel(const __grid
             const bool tr = p.trace != nullptr && blockIdx.x == 0;
             long long* trp = p.trace + 2 * 128;
 #define SWE_STAMP(i_, ev_) do { if (tr && (i_) < 16) trp[(i_) * 8 + (ev_)] = clock64(); } while (0)
+            if (MODE == 2) {
+                for (int i = 0; i < n_my; ++i) {
+                    const int buf = i & 1;
+                    mbar_wait(&bar->a_ready[buf], (((uint32_t)(i >> 1)) & 1) ^ 1);     // tile i-2 has been written out
+                    tc_fence_after_sync();
+                    d_l1 = buf ? COL_D_B : COL_D_A;
+                    dfull_l1 = buf;
+                    mma_l1(0, n_l1, true);
+                }
+            } else {
             if (n_my > 0) mma_l1(0, n_l1, true);
             for (int i = 0; i < n_my; ++i) {
                 const uint32_t ph = i & 1;
@@ -438,6 +530,7 @@ __global__ void __launch_bounds__(N_THREADS, 1) edge_gate_tc_kernel(const __grid
                 SWE_STAMP(i, 3);
                 if (more) mma_l1(h_l1, n_l1, true);
                 SWE_STAMP(i, 4);
+            }
             }
 #undef SWE_STAMP
         }
@@ -455,6 +548,22 @@ using namespace swe;
 extern "C" int swe_edge_gate_tc_fwd_traced(const float*, const float*, const float*, const float*, const int32_t*,
                                            const int32_t*, int64_t, const void*, int32_t, const int32_t*,
                                            const float* const*, int32_t, float*, float*, long long*, void*);
+
+static int gate_tc_launch(const tc::GateTcParams& p, int mode, void* stream) {
+    bool generic = false;
+    if (mode != 2)
+        for (int i = 0; i < 3; ++i)
+            generic |= !(p.act[i] == SWE_ACT_NONE || p.act[i] == SWE_ACT_PRELU || p.act[i] == SWE_ACT_RELU || p.act[i] == SWE_ACT_LEAKYRELU);
+    void (*kern)(const tc::GateTcParams) = nullptr;
+    if (mode == 0) kern = generic ? tc::edge_gate_tc_kernel<true, 0> : tc::edge_gate_tc_kernel<false, 0>;
+    else if (mode == 1) kern = generic ? tc::edge_gate_tc_kernel<true, 1> : tc::edge_gate_tc_kernel<false, 1>;
+    else kern = tc::edge_gate_tc_kernel<false, 2>;
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc::GATE_TC_SMEM);
+    if (e != cudaSuccess) { set_error("edge_gate_tc smem opt-in (%zu B): %s", tc::GATE_TC_SMEM, cudaGetErrorString(e)); return (int)e; }
+    const long long n_tiles = (p.n_edges + tc::TILE_ROWS - 1) / tc::TILE_ROWS;
+    kern<<<grid_for(n_tiles, 1), tc::N_THREADS, tc::GATE_TC_SMEM, (cudaStream_t)stream>>>(p);
+    return 0;
+}
 
 extern "C" size_t swe_gate_tc_image_bytes(int32_t k1) { return tc::img_bytes(k1 / tc::KC); }
 
@@ -488,17 +597,59 @@ extern "C" int swe_edge_gate_tc_fwd_traced(const float* xs, const float* xd_src,
     SWE_REQUIRE(k1 == (a ? 5 : 4) * tc::GF, SWE_E_UNSUPP, "edge_gate_tc: k1=%d does not match the inputs", k1);
     if (n_edges == 0) return 0;
     tc::GateTcParams p;
+    memset(&p, 0, sizeof(p));
     p.xs = xs; p.xd_src = xd_src; p.xd_dst = xd_dst; p.a = a; p.src = src; p.dst = dst; p.n_edges = n_edges;
     p.img = (const unsigned char*)image; p.n_l1_img = k1 / tc::KC;
     for (int i = 0; i < 3; ++i) { p.act[i] = act3[i]; p.slope[i] = slope3[i]; }
     p.normalize = normalize; p.s_out = s_out; p.dbg = dbg; p.trace = trace;
-    bool generic = false;
-    for (int i = 0; i < 3; ++i)
-        generic |= !(act3[i] == SWE_ACT_NONE || act3[i] == SWE_ACT_PRELU || act3[i] == SWE_ACT_RELU || act3[i] == SWE_ACT_LEAKYRELU);
-    auto kern = generic ? tc::edge_gate_tc_kernel<true> : tc::edge_gate_tc_kernel<false>;
-    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc::GATE_TC_SMEM);
-    if (e != cudaSuccess) { set_error("edge_gate_tc smem opt-in (%zu B): %s", tc::GATE_TC_SMEM, cudaGetErrorString(e)); return (int)e; }
-    const long long n_tiles = (n_edges + tc::TILE_ROWS - 1) / tc::TILE_ROWS;
-    kern<<<grid_for(n_tiles, 1), tc::N_THREADS, tc::GATE_TC_SMEM, (cudaStream_t)stream>>>(p);
+    p.n_seg = 0;
+    for (int sg = 0; sg < 5; ++sg)
+        if (sg < 3 || (sg == 3 && xd_dst) || (sg == 4 && a)) p.segs[p.n_seg++] = sg;
+    if (int r = gate_tc_launch(p, 0, stream)) return r;
     return check_launch("edge_gate_tc_fwd");
+}
+
+// ---------------------------------------------------------------------------------------------
+// decomposed layer 0 (see the kernel comment): per-node partial tables + gate reading them
+// ---------------------------------------------------------------------------------------------
+extern "C" int swe_gate_partials_tc(const float* xs, const float* xd, int32_t row_lo, int32_t n_rows, const void* image,
+                                    int32_t k1, int32_t role, float* p_out, void* stream) {
+    SWE_REQUIRE(xs && image && p_out && row_lo >= 0 && n_rows >= 0 && (role == 0 || role == 1), SWE_E_INVAL,
+                "gate_partials_tc: bad arguments");
+    SWE_REQUIRE(role == 1 || xd, SWE_E_INVAL, "gate_partials_tc: the source role needs x_d");
+    SWE_REQUIRE(aligned16(xs) && aligned16(image) && aligned16(p_out) && (!xd || aligned16(xd)), SWE_E_ALIGN,
+                "gate_partials_tc: unaligned buffer");
+    SWE_REQUIRE(k1 == 4 * tc::GF || k1 == 5 * tc::GF, SWE_E_UNSUPP, "gate_partials_tc: k1=%d", k1);
+    if (n_rows == 0) return 0;
+    tc::GateTcParams p;
+    memset(&p, 0, sizeof(p));
+    p.xs = xs; p.xd_src = xd; p.xd_dst = xd; p.n_edges = n_rows; p.row_lo = row_lo; p.p_out = p_out;
+    p.img = (const unsigned char*)image; p.n_l1_img = k1 / tc::KC;
+    p.n_seg = 0;
+    p.segs[p.n_seg++] = role;                         // x_s block of this role (0: x_s[r], 1: x_s[c])
+    if (xd) p.segs[p.n_seg++] = 2 + role;             // x_d block (2: x_d[r], 3: x_d[c])
+    if (int r = gate_tc_launch(p, 2, stream)) return r;
+    return check_launch("gate_partials_tc");
+}
+
+extern "C" int swe_edge_gate_tc_dec_fwd(const float* p_src, const float* p_dst, const float* a, const int32_t* src,
+                                        const int32_t* dst, int64_t n_edges, const void* image, int32_t k1,
+                                        const int32_t* act3, const float* const* slope3, int32_t normalize, float* s_out,
+                                        void* stream) {
+    SWE_REQUIRE(p_src && p_dst && src && dst && s_out && image && act3 && slope3 && n_edges >= 0, SWE_E_INVAL,
+                "edge_gate_tc_dec: bad arguments");
+    SWE_REQUIRE(aligned16(p_src) && aligned16(p_dst) && aligned16(s_out) && aligned16(image) && (!a || aligned16(a)),
+                SWE_E_ALIGN, "edge_gate_tc_dec: unaligned buffer");
+    SWE_REQUIRE(k1 == (a ? 5 : 4) * tc::GF, SWE_E_UNSUPP, "edge_gate_tc_dec: k1=%d does not match the inputs", k1);
+    if (n_edges == 0) return 0;
+    tc::GateTcParams p;
+    memset(&p, 0, sizeof(p));
+    p.a = a; p.src = src; p.dst = dst; p.n_edges = n_edges; p.p_src = p_src; p.p_dst = p_dst;
+    p.img = (const unsigned char*)image; p.n_l1_img = k1 / tc::KC;
+    for (int i = 0; i < 3; ++i) { p.act[i] = act3[i]; p.slope[i] = slope3[i]; }
+    p.normalize = normalize; p.s_out = s_out;
+    p.n_seg = 0;
+    if (a) p.segs[p.n_seg++] = 4;
+    if (int r = gate_tc_launch(p, 1, stream)) return r;
+    return check_launch("edge_gate_tc_dec_fwd");
 }

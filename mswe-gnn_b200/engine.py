@@ -222,6 +222,13 @@ def hop_backend() -> str:
     return os.environ.get("MSWE_HOP", "tc")
 
 
+def gate_layer0() -> str:
+    """'dec' (default): layer 0 of the tcgen05 edge MLP is decomposed into per-node partial tables
+    (swe_gate_partials_tc) + the edge part; 'full': every edge multiplies its whole 5F-wide input."""
+    import os
+    return os.environ.get("MSWE_GATE_L0", "dec")
+
+
 def gate_backend() -> str:
     """'tc' (tcgen05 3xTF32, default where eligible) or 'ffma' (exact-fp32 CUDA cores)."""
     import os
@@ -245,19 +252,27 @@ class SweGnnLauncher:
         self.filters = PackedFilters(list(module.filter_matrix), F, self.FP) if module.with_filter_matrix else None
         self.tc = PackedGateTC(module.edge_mlp) if PackedGateTC.eligible(module.edge_mlp, F) else None
 
-    def gate(self, es, xs, xd_src, xd_dst, a, s_buf, dbg=None):
+    def gate(self, es, xs, xd_src, xd_dst, a, s_buf, dbg=None, ptab=None):
         m = self.m
         if self.tc is not None and gate_backend() == "tc":
             codes, slopes = self.tc.acts_and_slopes()
             k1 = self.tc.linears[0].weight.shape[1]
-            lib.edge_gate_tc_fwd(xs, xd_src, xd_dst, a, es.src, es.dst, es.n_edges, self.tc.image(), k1, codes, slopes,
-                                 m.normalize, s_buf, dbg)
+            img = self.tc.image()
+            if ptab is not None and dbg is None and gate_layer0() == "dec":
+                p_src, p_dst = ptab
+                lib.gate_partials_tc(xs, xd_src, es.src_lo, es.src_hi - es.src_lo, img, k1, 0, p_src)
+                lib.gate_partials_tc(xs, xd_dst, es.dst_lo, es.n_dst, img, k1, 1, p_dst)
+                lib.edge_gate_tc_dec_fwd(p_src, p_dst, a, es.src, es.dst, es.n_edges, img, k1, codes, slopes,
+                                         m.normalize, s_buf)
+            else:
+                lib.edge_gate_tc_fwd(xs, xd_src, xd_dst, a, es.src, es.dst, es.n_edges, img, k1, codes, slopes,
+                                     m.normalize, s_buf, dbg)
         else:
             lib.edge_gate_fwd(xs, xd_src, xd_dst, a, es.src, es.dst, es.n_edges, self.mlp.struct(), m.normalize,
                               s_buf, self.FP)
 
     def run(self, es: EdgeSet, xs, xd_src, xd_dst, a, s_buf, o_dst_rows_zero: bool, tmp_a, tmp_b, out,
-            addend=None, act_code: int = 0, act_slope=None, halo=None, scale: int = 0):
+            addend=None, act_code: int = 0, act_slope=None, halo=None, scale: int = 0, ptab=None):
         """Writes rows [es.dst_lo, es.dst_lo+es.n_dst) of `out`.
 
         xd_src: array holding x_d[row]; xd_dst: array holding x_d[col] or None when those rows are
@@ -267,7 +282,7 @@ class SweGnnLauncher:
         """
         m, FP = self.m, self.FP
         E = es.n_edges
-        self.gate(es, xs, xd_src, xd_dst, a, s_buf)
+        self.gate(es, xs, xd_src, xd_dst, a, s_buf, ptab=ptab)
         K = m.K
         if m.with_filter_matrix:
             W = self.filters.tensors()

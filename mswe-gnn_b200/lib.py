@@ -63,6 +63,9 @@ SIGNATURES = {
     "swe_gate_tc_pack": (C.c_int, [_p, _i32, _p, _p, _p, _p, _p, _p, _p]),
     "swe_edge_gate_tc_fwd": (C.c_int, [_p, _p, _p, _p, _p, _p, _i64, _p, _i32, C.POINTER(C.c_int32),
                                        C.POINTER(C.c_void_p), _i32, _p, _p, _p]),
+    "swe_gate_partials_tc": (C.c_int, [_p, _p, _i32, _i32, _p, _i32, _i32, _p, _p]),
+    "swe_edge_gate_tc_dec_fwd": (C.c_int, [_p, _p, _p, _p, _p, _i64, _p, _i32, C.POINTER(C.c_int32), C.POINTER(C.c_void_p),
+                                           _i32, _p, _p]),
     "swe_hop_tc_image_bytes": (_sz, []),
     "swe_hop_tc_pack": (C.c_int, [_p, _p, _p]),
     "swe_propagate_hop_tc_fwd": (C.c_int, [_p, _p, _p, _p, _p, _i32, _i32, _p, _i32, _i32, _p, _i32, _p, _p, _p, _p]),
@@ -228,6 +231,19 @@ def propagate_hop_fwd(o_src, o_dst, s, rowptr, src, dst_lo, n_dst, wt, with_grad
                                         ptr(src, torch.int32), dst_lo, n_dst, ptr(wt), int(with_gradient),
                                         int(upwind), ptr(addend), act, ptr(slope), ptr(out), F, _stream()),
            "swe_propagate_hop_fwd")
+
+
+def gate_partials_tc(xs, xd, row_lo, n_rows, image, k1, role, p_out):
+    _check(load().swe_gate_partials_tc(ptr(xs), ptr(xd), row_lo, n_rows, image.data_ptr(), k1, role, ptr(p_out), _stream()),
+           "swe_gate_partials_tc")
+
+
+def edge_gate_tc_dec_fwd(p_src, p_dst, a, src, dst, n_edges, image, k1, acts, slopes, normalize, s_out):
+    act3 = (C.c_int32 * 3)(*acts)
+    slope3 = (C.c_void_p * 3)(*[None if s is None else ptr(s) for s in slopes])
+    _check(load().swe_edge_gate_tc_dec_fwd(ptr(p_src), ptr(p_dst), ptr(a), ptr(src, torch.int32), ptr(dst, torch.int32),
+                                           n_edges, image.data_ptr(), k1, act3, slope3, int(normalize), ptr(s_out),
+                                           _stream()), "swe_edge_gate_tc_dec_fwd")
 
 
 def hop_tc_image_bytes() -> int:

@@ -97,7 +97,8 @@ class SWEGNN(nn.Module):
             a = widen(edge_attr)[es.eid.long()].contiguous()
         s_buf = torch.empty(max(es.n_edges, 1), FP, device=xd.device)
         ta, tb, out = torch.empty_like(xd), torch.empty_like(xd), torch.empty_like(xd)
-        la.run(es, xs, xd, xd, a, s_buf, False, ta, tb, out)
+        ptab = (torch.empty(N, 2 * FP, device=xd.device), torch.empty(N, 2 * FP, device=xd.device)) if FP == 64 else None
+        la.run(es, xs, xd, xd, a, s_buf, False, ta, tb, out, ptab=ptab)
         return out if FP == F else out[:, :F].contiguous()
 
     def __repr__(self):
@@ -149,6 +150,9 @@ class _EncodeDecodeMixin:
             FP, N = self._FP, plan.n_nodes
             ws = {n: torch.empty(N, FP, dtype=torch.float32, device=dev) for n in names}
             ws["s"] = torch.empty(plan.max_edges, FP, dtype=torch.float32, device=dev)
+            # per-node partial tables of the decomposed edge-MLP layer 0 (tcgen05 gate, F = 64)
+            ws["ptab"] = (torch.empty(N, 2 * FP, dtype=torch.float32, device=dev),
+                          torch.empty(N, 2 * FP, dtype=torch.float32, device=dev)) if FP == 64 else None
             ws["a"] = None
             if len(self._ws) >= 2:
                 self._ws.pop(next(iter(self._ws)))
@@ -274,7 +278,8 @@ class GNN(BaseFloodModel, _EncodeDecodeMixin):
             if halo is not None and li > 0:
                 halo.exchange(cur, 0)
             conv.launcher().run(es, ws["xs"], cur, cur, a, ws["s"], False, ws["ta"], ws["tb"], nxt,
-                                act_code=ACT_CODES[self._gnn_activation_name], act_slope=slope, halo=halo, scale=0)
+                                act_code=ACT_CODES[self._gnn_activation_name], act_slope=slope, halo=halo, scale=0,
+                                ptab=ws["ptab"])
             cur, nxt = nxt, cur
         self._decode(cur, None, None, x, plan, pred, step_ptr, pred_stride, x_next)
 
@@ -381,7 +386,8 @@ class MSGNN(BaseFloodModel, _EncodeDecodeMixin):
             es = plan.edges[i]
             if halo is not None and i > 0:
                 halo.exchange(cur, i)                     # pooled rows of the halo nodes come from their owners
-            self.gnn_processor[i].launcher().run(es, xs, cur, cur, a_of(i), s_buf, False, ta, tb, down, halo=halo, scale=i)
+            self.gnn_processor[i].launcher().run(es, xs, cur, cur, a_of(i), s_buf, False, ta, tb, down, halo=halo, scale=i,
+                                                 ptab=ws["ptab"])
             if halo is not None and cross[i]:
                 halo.exchange(down, i)                    # a child owned by another rank (real meshes, App. D-5)
             pe = plan.pool[i]
@@ -392,7 +398,8 @@ class MSGNN(BaseFloodModel, _EncodeDecodeMixin):
             es = plan.edges[s]
             if halo is not None and S > 1:
                 halo.exchange(cur, s)
-            self.gnn_processor[S - 1 + i].launcher().run(es, xs, cur, cur, a_of(s), s_buf, False, ta, tb, up, halo=halo, scale=s)
+            self.gnn_processor[S - 1 + i].launcher().run(es, xs, cur, cur, a_of(s), s_buf, False, ta, tb, up, halo=halo, scale=s,
+                                                         ptab=ws["ptab"])
             if i < S - 1:
                 if halo is not None and cross[s - 1]:
                     halo.exchange(up, s)
@@ -400,5 +407,5 @@ class MSGNN(BaseFloodModel, _EncodeDecodeMixin):
                 # x_d[fine] is identically zero here (nothing wrote the finer rows since the last
                 # pooling zeroed them), so the gate skips that block and the hop starts from 0
                 self.intra_scale_gnn[i].launcher().run(ue, xs, up, None, None, s_buf, True, ta, tb, cur,
-                                                       addend=down if self.skip_connections else None)
+                                                       addend=down if self.skip_connections else None, ptab=ws["ptab"])
         self._decode(up, self._gnn_activation_name, self.gnn_activation, x, plan, pred, step_ptr, pred_stride, x_next)

@@ -101,3 +101,42 @@ def test_gate_tc_zero_rows_give_zero_gate_not_nan():
     s = torch.full((E, 64), float("nan"), device=DEV)
     lib.edge_gate_tc_fwd(xs, xd, xd, None, src, dst, E, tc.image(), k1, codes, slopes, True, s, None)
     assert float(s.abs().max()) == 0.0
+
+
+@pytest.mark.parametrize("n_edge_feat,drop_dst,nx,ny", [(64, False, 60, 40), (0, False, 33, 21), (0, True, 33, 21), (64, False, 5, 3),
+                                                      (0, True, 400, 300), (64, False, 400, 300)])   # the last two: ~19 tiles per CTA
+def test_gate_tc_decomposed_layer0_matches_exact_fp32_kernel(n_edge_feat, drop_dst, nx, ny):
+    """Per-node partial tables (swe_gate_partials_tc) + decomposed gate against the exact-fp32 CUDA-core gate and the
+    full tcgen05 gate: the first layer is only re-associated (P_src[r] + P_dst[c] + E·a)."""
+    n, E, src, dst, xs, xd, a, mlp, k1 = _setup(n_edge_feat, seed=7, nx=nx, ny=ny)
+    tc = PackedGateTC(mlp)
+    codes, slopes = tc.acts_and_slopes()
+    xd_dst = None if drop_dst else xd
+    nseg = 3 + (0 if drop_dst else 1) + (1 if n_edge_feat else 0)
+    # fp64 table check:  P_src = A xs + C xd,  P_dst = B xs + D xd
+    W1 = [m for m in mlp if isinstance(m, torch.nn.Linear)][0].weight.detach().double()
+    p_src = torch.full((n, 128), float("nan"), device=DEV)
+    p_dst = torch.full((n, 128), float("nan"), device=DEV)
+    lib.gate_partials_tc(xs, xd, 0, n, tc.image(), k1, 0, p_src)
+    lib.gate_partials_tc(xs, xd_dst, 0, n, tc.image(), k1, 1, p_dst)
+    ref_src = xs.double() @ W1[:, 0:64].T + xd.double() @ W1[:, 128:192].T
+    ref_dst = xs.double() @ W1[:, 64:128].T + (0 if drop_dst else xd.double() @ W1[:, 192:256].T)
+    scale = float(ref_src.abs().max())
+    assert float((p_src.double() - ref_src).abs().max()) < 2e-6 * scale
+    assert float((p_dst.double() - ref_dst).abs().max()) < 2e-6 * scale
+    s_dec = torch.empty(E, 64, device=DEV)
+    lib.edge_gate_tc_dec_fwd(p_src, p_dst, a, src, dst, E, tc.image(), k1, codes, slopes, True, s_dec)
+    s_ff = torch.empty(E, 64, device=DEV)
+    pk = PackedMLP(mlp, [(64, 64)] * (5 if n_edge_feat else 4), {})
+    lib.edge_gate_fwd(xs, xd, xd_dst, a, src, dst, E, pk.struct(), True, s_ff, 64)
+    s_full = torch.empty(E, 64, device=DEV)
+    lib.edge_gate_tc_fwd(xs, xd, xd_dst, a, src, dst, E, tc.image(), k1, codes, slopes, True, s_full, None)
+    torch.cuda.synchronize()
+    assert bool(torch.isfinite(s_dec).all())
+    assert float((s_dec - s_ff).abs().max()) < 1e-5, float((s_dec - s_ff).abs().max())
+    assert float((s_dec - s_full).abs().max()) < 1e-5
+    # a sub-range of table rows leaves the other rows untouched
+    p2 = torch.zeros(n, 128, device=DEV)
+    lo, cnt = n // 3, n // 2
+    lib.gate_partials_tc(xs, xd, lo, cnt, tc.image(), k1, 0, p2)
+    assert torch.equal(p2[lo:lo + cnt], p_src[lo:lo + cnt]) and float(p2[:lo].abs().max()) == 0 and float(p2[lo + cnt:].abs().max()) == 0

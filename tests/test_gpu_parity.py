@@ -255,7 +255,9 @@ def test_large_mesh_properties():
     with torch.no_grad():
         a = m(d)
         b = m(d)
-    assert a.shape == (1346574, 2) and torch.equal(a, b) and bool(torch.isfinite(a).all())
+    assert a.shape == (1346574, 2)
+    assert bool(torch.isfinite(a).all())
+    assert torch.equal(a, b), f"not deterministic: {int((a != b).sum())} entries differ"
     assert bool((a >= 0).all())
     h, q = a[:, 0], a[:, 1]
     assert bool(((h == 0) | (h.abs() > 1e-4)).all())                 # dry mask, models.py:79-91
