@@ -608,7 +608,8 @@ def profile_kernels(runner, alg):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--steps", type=int, default=48,
+                    help="timed rollout steps (default 48 = the reference's rollout length: 96 h at 120 min, train.py:84)")
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default=None, choices=[None, *WORKLOADS, *TRAIN_WORKLOADS])

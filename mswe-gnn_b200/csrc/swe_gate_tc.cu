@@ -549,7 +549,12 @@ extern "C" int swe_edge_gate_tc_fwd_traced(const float*, const float*, const flo
                                            const int32_t*, int64_t, const void*, int32_t, const int32_t*,
                                            const float* const*, int32_t, float*, float*, long long*, void*);
 
-static int gate_tc_launch(const tc::GateTcParams& p, int mode, void* stream) {
+static long long* g_next_trace = nullptr;      // profiling aid: consumed by the next launch (tools/bench_gate.py)
+extern "C" void swe_gate_tc_set_trace(long long* t) { g_next_trace = t; }
+
+static int gate_tc_launch(const tc::GateTcParams& p_in, int mode, void* stream) {
+    tc::GateTcParams p = p_in;
+    if (g_next_trace && !p.trace) { p.trace = g_next_trace; g_next_trace = nullptr; }
     bool generic = false;
     if (mode != 2)
         for (int i = 0; i < 3; ++i)
