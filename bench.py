@@ -199,7 +199,7 @@ def run_ours(args):
     K, W = args.steps, max(args.warmup, 3)
     model = MSGNN(**CTOR).to(dev)
     partitioned = world > 1 and args.multi != "replicas"
-    host = make_tri_mesh(nx, ny, S, rollout_steps=K + W, seed=0 if partitioned else rank)
+    host = make_tri_mesh(nx, ny, S, rollout_steps=K + W, seed=0 if partitioned else rank, with_y=False)
     N_global = host.x.shape[0]
 
     def barrier():
@@ -547,7 +547,7 @@ def profile_kernels(runner, alg):
     from mswe_gnn_b200 import lib
     records = []
     orig = {}
-    names = ["node_encode_fwd", "edge_gate_fwd", "edge_gate_tc_fwd", "edge_gate_tc_dec_fwd", "gate_partials_tc", "node_linear_fwd", "propagate_hop_fwd", "propagate_hop_tc_fwd", "pool_mean_fwd",
+    names = ["row_mlp_tc", "node_encode_fwd", "edge_gate_fwd", "edge_gate_tc_fwd", "edge_gate_tc_dec_fwd", "gate_partials_tc", "node_linear_fwd", "propagate_hop_fwd", "propagate_hop_tc_fwd", "pool_mean_fwd",
              "decode_head_fwd", "edge_encode_fwd", "apply_bc", "step_advance"]
 
     def wrap(name):

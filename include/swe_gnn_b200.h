@@ -175,6 +175,29 @@ int swe_propagate_hop_tc_fwd(const float* o_src, const float* o_dst, const float
                              int32_t with_gradient, int32_t upwind, const float* addend, int32_t act,
                              const float* slope, float* agg_out, float* out, void* stream);
 
+/* ---------------------------------------------------------------------------------------------
+ * Row MLPs on tcgen05 (F = 64): encoders (models/gnn.py:281-294), filter_matrix[0] (gnn.py:401-402) and the decoder
+ * head (gnn.py:339-348 + models/models.py:50-91 + utils/dataset.py:508-529) as ONE row-streaming kernel:
+ *   X0 = act_in(x_rows[row_lo + r])   |   act_first(w_first · raw(r) + b_first)   (first Linear of an encoder, <= 8 raw
+ *        inputs incl. the optional WL = raw[wl_col_a] + raw[wl_col_b], evaluated on CUDA cores)
+ *   X1 = act[0](W_0 X0 + bias[0]),  X2 = act[1](W_1 X1 + bias[1]) (n_tc = 2)      64 -> 64 layers, 3xTF32 on tcgen05
+ *   out_rows[row_lo + r] = X_last     |   head != 0: pred / x_next exactly like swe_decode_head_fwd
+ * img[l]: swe_hop_tc_pack image of the layer's [64, 64] weight.
+ * ------------------------------------------------------------------------------------------- */
+typedef struct swe_rowmlp {
+    const float* x_rows; int32_t act_in; int32_t _pad0; const float* slope_in;
+    const float* raw; int32_t raw_ld; int32_t raw_col0; int32_t raw_cols; int32_t with_wl; int32_t wl_col_a; int32_t wl_col_b;
+    const int32_t* perm;
+    const float* w_first; const float* b_first; int32_t act_first; int32_t _pad1; const float* slope_first;
+    int32_t row_lo; int32_t _pad2; int64_t n_rows;
+    int32_t n_tc; int32_t _pad3; const void* img[2]; const float* bias[2]; int32_t act[2]; const float* slope[2];
+    float* out_rows;
+    int32_t head; int32_t act_head; const float* w_head; const float* b_head; const float* slope_head;
+    const float* x0; int32_t n_cols; int32_t previous_t; const int32_t* head_perm; int32_t res_mode; float eps;
+    const float* res_w; float* pred; const int32_t* step_ptr; int64_t pred_step_stride; float* x_next;
+} swe_rowmlp_t;
+int swe_row_mlp_tc(const swe_rowmlp_t* desc, void* stream);
+
 /* out[dst_lo + i] = x[dst_lo + i] · Wᵀ for i < n_rows.  Replaces models/gnn.py:401-402
  * (filter_matrix[0]).  wt is the packed (k-major) F×F weight. */
 int swe_node_linear_fwd(const float* x, int32_t row_lo, int32_t n_rows, const float* wt, float* out,

@@ -1,0 +1,448 @@
+// Row MLPs on the 5th-generation tensor cores (F = 64): node / edge encoders, filter_matrix[0] and the
+// decoder head.  On CUDA cores these streams are FP32-FMA-bound (2·64² FLOP per layer per row against
+// ~0.5 KB of traffic per row); here the 64→64 layers are tcgen05.mma (3xTF32, fp32 accumulation in TMEM)
+// and the kernel is a row stream again.
+//
+//   X0   = act_in(x_rows[r])                                    (INPUT_ROWS)      [models/gnn.py:401-402, 339]
+//        | act_f(W_f · raw(r) + b_f),  raw = ≤ 8 raw input columns (+ WL)  (first Linear of an encoder on CUDA
+//                                                                cores: 64·k MACs)  [models/gnn.py:281-294]
+//   X1   = act_0(W_0 · X0 + b_0)                                 tcgen05, SS (A from shared memory)
+//   X2   = act_1(W_1 · X1 + b_1)                                 tcgen05, TS (A stays in TMEM)         (n_tc = 2)
+//   out  = X_last rows                                           (ROW output)
+//        | decoder head: relu(act_h(w_h · X_last) + residual(x0)), dry mask, prediction + window shift
+//                                                                [models/gnn.py:339-348, models/models.py:50-91,
+//                                                                 utils/dataset.py:508-529]
+//
+// Persistent, one CTA per SM, 21 warps:
+//   warps 0-15  row warps  : build X0 (16 lanes × 16 B per row, coalesced), split into TF32 hi/lo, write the A
+//                            operand; one tile later read the result from the shared-memory stage and store the
+//                            rows / run the head — fully coalesced global traffic on both sides
+//   warps 16-19 epilogue   : thread = TMEM lane = row: D → bias, activation → (TS operand for the next layer | stage)
+//   warp  20    MMA issuer
+#include "swe_tc.cuh"
+
+namespace swe {
+namespace tc {
+
+constexpr int RF = 64;
+constexpr int R_TILE = 128;
+constexpr int R_KC = 32;
+constexpr int R_A_TILE = R_TILE * 128;          // [128 x 32] tf32 tile, bytes
+constexpr int R_A_SLOT = 4 * R_A_TILE;          // 2 chunks x (hi | lo)
+constexpr int R_W_TILE = RF * 128;              // [64 x 32] tf32 tile
+constexpr size_t R_W_IMAGE = 4 * (size_t)R_W_TILE;       // 32 KB per layer (same layout as swe_hop_tc_pack)
+constexpr int R_ROW_WARPS = 16, R_ROW_THREADS = 512, R_EPI_WARPS = 4;
+constexpr int R_THREADS = R_ROW_THREADS + R_EPI_WARPS * 32 + 32;    // 672
+constexpr int R_STAGE_LD = RF + 4;
+constexpr size_t R_STAGE_BYTES = (size_t)R_TILE * R_STAGE_LD * 4;
+constexpr uint32_t RC_D0 = 0, RC_D1 = 64, RC_AHI = 128, RC_ALO = 192;      // TMEM columns (256 allocated)
+
+// Activations inside the per-element loops: the "leaky family" (none / relu / leakyrelu / prelu) is two FP32
+// instructions; everything else goes through ONE out-of-line function.  Inlining the 8-way act_apply switch at the
+// ~200 call sites of this kernel produced 24 k SASS instructions (392 KB) and the epilogue ran out of the
+// instruction cache (12 k cycles per tile instead of ~1 k).
+__device__ __noinline__ float act_generic(int act, float v, float slope) { return act_apply(act, v, slope); }
+struct ActSel { int act; float slope; bool leaky; };
+__device__ __forceinline__ ActSel act_select(int act, const float* slope_p) {
+    ActSel a;
+    a.act = act;
+    a.leaky = (act == SWE_ACT_NONE || act == SWE_ACT_PRELU || act == SWE_ACT_RELU || act == SWE_ACT_LEAKYRELU);
+    a.slope = act == SWE_ACT_NONE ? 1.f : act == SWE_ACT_RELU ? 0.f : act == SWE_ACT_LEAKYRELU ? 0.1f
+              : (act == SWE_ACT_PRELU && slope_p) ? __ldg(slope_p) : 0.f;
+    return a;
+}
+__device__ __forceinline__ float act_do(const ActSel& a, float v) {
+    return a.leaky ? fmaxf(v, 0.f) + a.slope * fminf(v, 0.f) : act_generic(a.act, v, a.slope);
+}
+
+struct __align__(8) RowBarriers {
+    uint64_t a_full, a_empty;          // A operand written (512) / consumed by layer-0 MMAs (commit)
+    uint64_t d0_full, d1_full;         // layer-0 / layer-1 accumulators complete (commit)
+    uint64_t x1_ready;                 // layer-1 operand written to TMEM (128)
+    uint64_t d0_free;                  // layer-0 accumulator read by the epilogue (128): the next tile's layer 0 may start
+    uint64_t st_full, st_empty;        // stage holds a tile (128) / consumed (512)
+};
+
+constexpr size_t ROWMLP_SMEM = 1024 + (size_t)R_A_SLOT + 2 * R_W_IMAGE + R_STAGE_BYTES + 64 * 8 * 4 + 64 * 4 +
+                               2 * 64 * 4 + 2 * 64 * 4 + sizeof(RowBarriers) + 16;
+
+struct RowMlpParams {
+    // ---- input
+    const float* x_rows; int act_in; const float* slope_in;          // INPUT_ROWS: [*, 64] rows row_lo + r
+    const float* raw; int raw_ld; int raw_col0; int raw_cols; int with_wl; int wl_col_a, wl_col_b;
+    const int32_t* perm;                                              // raw row of row r = perm[row_lo + r] (NULL: identity)
+    const float* w_first; const float* b_first; int act_first; const float* slope_first;   // [64][raw_k] torch layout
+    int raw_k;                                                        // raw_cols + with_wl  (<= 8)
+    int row_lo; long long n_rows;
+    // ---- tensor-core layers
+    int n_tc; const unsigned char* img[2]; const float* bias[2]; int act[2]; const float* slope[2];
+    // ---- output
+    float* out_rows;                                                  // [*, 64] or NULL
+    // decoder head
+    int head; const float* w_head; const float* b_head; int act_head; const float* slope_head;   // [2][64]
+    const float* x0; int n_cols; const int32_t* head_perm; int previous_t; int res_mode; const float* res_w; float eps;
+    float* pred; const int32_t* step_ptr; long long pred_step_stride; float* x_next;
+    long long* trace;          // profiling aid: [3 roles][16 tiles][8 events] clock64 stamps of CTA 0
+};
+
+__global__ void __launch_bounds__(R_THREADS, 1) row_mlp_tc_kernel(const __grid_constant__ RowMlpParams p) {
+    extern __shared__ unsigned char smem_raw[];
+    unsigned char* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+    unsigned char* a_slot = smem;
+    unsigned char* w_tile = smem + R_A_SLOT;                           // layer l at + l * 32 KB
+    float* stage = reinterpret_cast<float*>(w_tile + 2 * R_W_IMAGE);
+    float* s_wf = stage + R_TILE * R_STAGE_LD;                          // [64][8] first-layer weights (padded with 0)
+    float* s_bf = s_wf + 64 * 8;                                        // [64]
+    float* s_bias = s_bf + 64;                                          // [2][64]
+    float* s_wh = s_bias + 128;                                         // [2][64] head weights
+    RowBarriers* bar = reinterpret_cast<RowBarriers*>(s_wh + 128);
+    uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(bar + 1);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (threadIdx.x == 0) {
+        mbar_init(&bar->a_full, R_ROW_THREADS); mbar_init(&bar->a_empty, 1);
+        mbar_init(&bar->d0_full, 1); mbar_init(&bar->d1_full, 1);
+        mbar_init(&bar->x1_ready, R_EPI_WARPS * 32); mbar_init(&bar->d0_free, R_EPI_WARPS * 32);
+        mbar_init(&bar->st_full, R_EPI_WARPS * 32); mbar_init(&bar->st_empty, R_ROW_THREADS);
+        fence_barrier_init();
+    }
+    for (int l = 0; l < p.n_tc; ++l)
+        for (int i = threadIdx.x * 16; i < (int)R_W_IMAGE; i += R_THREADS * 16)
+            *reinterpret_cast<float4*>(w_tile + l * R_W_IMAGE + i) = *reinterpret_cast<const float4*>(p.img[l] + i);
+    for (int i = threadIdx.x; i < 64 * 8; i += R_THREADS) {
+        const int n = i >> 3, k = i & 7;
+        s_wf[i] = (p.w_first && k < p.raw_k) ? p.w_first[n * p.raw_k + k] : 0.f;
+    }
+    for (int i = threadIdx.x; i < 64; i += R_THREADS) {
+        s_bf[i] = p.b_first ? p.b_first[i] : 0.f;
+        s_bias[i] = p.bias[0] ? p.bias[0][i] : 0.f;
+        s_bias[64 + i] = (p.n_tc > 1 && p.bias[1]) ? p.bias[1][i] : 0.f;
+        s_wh[i] = p.head ? p.w_head[i] : 0.f;
+        s_wh[64 + i] = p.head ? p.w_head[64 + i] : 0.f;
+    }
+    fence_proxy_async_smem();
+    if (warp == R_ROW_WARPS + R_EPI_WARPS) tmem_alloc(tmem_holder, 256);
+    tc_fence_before_sync();
+    __syncthreads();
+    tc_fence_after_sync();
+    const uint32_t tmem_base = *tmem_holder;
+    const long long n_tiles = (p.n_rows + R_TILE - 1) / R_TILE;
+    const long long tpc = (n_tiles + gridDim.x - 1) / gridDim.x;
+    const long long tile0 = (long long)blockIdx.x * tpc;
+    const int n_my = (int)max(0ll, min(tpc, n_tiles - tile0));
+
+#define R_STAMP(role_, i_, ev_) do { if (p.trace && blockIdx.x == 0 && lane == 0 && (i_) < 16) p.trace[(role_) * 128 + (i_) * 8 + (ev_)] = clock64(); } while (0)
+    if (warp < R_ROW_WARPS) {
+        // =====================================================================================
+        // row warps
+        // =====================================================================================
+        const int g = threadIdx.x >> 4, q = threadIdx.x & 15, q4 = 4 * q;
+        const int chunk = q >> 3, piece = q & 7;
+        uint32_t a_off[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) a_off[k] = sw128_offset(g + 32 * k, piece * 4);
+        const ActSel a_in = act_select(p.act_in, p.slope_in), a_f = act_select(p.act_first, p.slope_first),
+                     a_h = act_select(p.act_head, p.slope_head);
+        // this lane's 4 output columns of the CUDA-core first layer
+        float wf[4][8], bf[4];
+        if (p.raw) {
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+                bf[c] = s_bf[q4 + c];
+#pragma unroll
+                for (int k = 0; k < 8; ++k) wf[c][k] = s_wf[(q4 + c) * 8 + k];
+            }
+        }
+        const int n_static_raw = p.n_cols - 2 * p.previous_t;
+        auto finish_tile = [&](int j) {
+            const long long r0 = (tile0 + j) * R_TILE;
+            // head: lane c (< n_cols <= 16) of a row's 16 lanes owns input column c of that row: one coalesced
+            // load of the node's inputs before the wait, one coalesced store of its shifted window after it
+            float xr[4];
+            long long orow[4];
+            if (p.head) {
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    const long long row = r0 + g + 32 * k;
+                    xr[k] = 0.f; orow[k] = 0;
+                    if (row < p.n_rows) {
+                        const long long node = (long long)p.row_lo + row;
+                        orow[k] = p.head_perm ? p.head_perm[node] : node;
+                        if (q < p.n_cols) xr[k] = p.x0[orow[k] * p.n_cols + q];
+                    }
+                }
+            }
+            mbar_wait(&bar->st_full, (uint32_t)j & 1);
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                const int r = g + 32 * k;
+                const long long row = r0 + r;
+                const float4 d = *reinterpret_cast<const float4*>(stage + r * R_STAGE_LD + q4);
+                if (!p.head) {
+                    if (row < p.n_rows) stg4(p.out_rows + ((long long)p.row_lo + row) * RF + q4, d);
+                } else {
+                    // last decoder layer 64 -> 2: every lane holds 4 of the 64 inputs
+                    float y0 = d.x * s_wh[q4] + d.y * s_wh[q4 + 1] + d.z * s_wh[q4 + 2] + d.w * s_wh[q4 + 3];
+                    float y1 = d.x * s_wh[64 + q4] + d.y * s_wh[64 + q4 + 1] + d.z * s_wh[64 + q4 + 2] + d.w * s_wh[64 + q4 + 3];
+                    // residual (models/models.py:50-77): this lane's column contributes to variable (c - n_static) & 1
+                    float c0 = 0.f, c1 = 0.f;
+                    const int rel = q - n_static_raw;
+                    if (rel >= 0 && q < p.n_cols && p.res_mode != 0) {
+                        const int t = rel >> 1, jv = rel & 1;
+                        const float w = p.res_mode == 1 ? __ldg(p.res_w + t) : p.res_mode == 2 ? __ldg(p.res_w + 2 * t + jv)
+                                        : (t == p.previous_t - 1 ? 1.f : 0.f);
+                        if (jv) c1 = xr[k] * w; else c0 = xr[k] * w;
+                    }
+#pragma unroll
+                    for (int off = 8; off >= 1; off >>= 1) {
+                        y0 += __shfl_xor_sync(0xffffffffu, y0, off);
+                        y1 += __shfl_xor_sync(0xffffffffu, y1, off);
+                        c0 += __shfl_xor_sync(0xffffffffu, c0, off);
+                        c1 += __shfl_xor_sync(0xffffffffu, c1, off);
+                    }
+                    const float shifted = __shfl_down_sync(0xffffffffu, xr[k], 2, 16);       // column c + 2 of the same row
+                    if (p.b_head) { y0 += __ldg(p.b_head); y1 += __ldg(p.b_head + 1); }
+                    y0 = fmaxf(act_do(a_h, y0) + c0, 0.f);
+                    y1 = fmaxf(act_do(a_h, y1) + c1, 0.f);
+                    const float oh = (fabsf(y0) > p.eps) ? y0 : 0.f;                        // h · [|h| > eps]
+                    const float oq = (y0 != 0.f) ? y1 : 0.f;                                 // q · [h != 0] (un-thresholded h)
+                    if (row < p.n_rows) {
+                        if (q < 2) {
+                            float* pr = p.pred + (p.step_ptr ? (long long)(*p.step_ptr) * p.pred_step_stride : 0) + orow[k] * 2;
+                            pr[q] = q ? oq : oh;
+                        }
+                        if (p.x_next && q < p.n_cols) {
+                            const float v = q < n_static_raw ? xr[k] : (q < p.n_cols - 2 ? shifted : (q == p.n_cols - 2 ? oh : oq));
+                            p.x_next[orow[k] * p.n_cols + q] = v;
+                        }
+                    }
+                }
+            }
+            mbar_arrive(&bar->st_empty);
+        };
+#pragma unroll 1
+        for (int i = 0; i < n_my; ++i) {
+            const long long r0 = (tile0 + i) * R_TILE;
+            if (warp == 0) R_STAMP(0, i, 0);
+            float4 x[4];
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                const long long row = r0 + g + 32 * k;
+                x[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (row < p.n_rows) {
+                    if (p.x_rows) {
+                        x[k] = ldg4(p.x_rows + ((long long)p.row_lo + row) * RF + q4);
+                        if (p.act_in != SWE_ACT_NONE) {
+                            x[k].x = act_do(a_in, x[k].x); x[k].y = act_do(a_in, x[k].y);
+                            x[k].z = act_do(a_in, x[k].z); x[k].w = act_do(a_in, x[k].w);
+                        }
+                    } else {
+                        const long long node = (long long)p.row_lo + row;
+                        const float* xr = p.raw + (long long)(p.perm ? p.perm[node] : node) * p.raw_ld;
+                        float in[8];
+#pragma unroll
+                        for (int c = 0; c < 8; ++c) in[c] = c < p.raw_cols ? __ldg(xr + p.raw_col0 + c) : 0.f;
+                        if (p.with_wl) {
+                            const float wl = __ldg(xr + p.wl_col_a) + __ldg(xr + p.wl_col_b);
+#pragma unroll
+                            for (int c = 0; c < 8; ++c) if (c == p.raw_cols) in[c] = wl;
+                        }
+                        float o[4];
+#pragma unroll
+                        for (int c = 0; c < 4; ++c) {
+                            float acc = 0.f;
+#pragma unroll
+                            for (int kk = 0; kk < 8; ++kk) acc = fmaf(in[kk], wf[c][kk], acc);
+                            o[c] = act_do(a_f, acc + bf[c]);
+                        }
+                        x[k] = make_float4(o[0], o[1], o[2], o[3]);
+                    }
+                }
+            }
+            if (warp == 0) R_STAMP(0, i, 1);
+            mbar_wait(&bar->a_empty, ((uint32_t)i & 1) ^ 1);               // layer-0 MMAs of the previous tile are done
+            if (warp == 0) R_STAMP(0, i, 2);
+            unsigned char* base = a_slot + (size_t)chunk * 2 * R_A_TILE;
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                float4 hh, ll;
+                split_tf32(x[k].x, hh.x, ll.x); split_tf32(x[k].y, hh.y, ll.y); split_tf32(x[k].z, hh.z, ll.z); split_tf32(x[k].w, hh.w, ll.w);
+                *reinterpret_cast<float4*>(base + a_off[k]) = hh;
+                *reinterpret_cast<float4*>(base + R_A_TILE + a_off[k]) = ll;
+            }
+            fence_proxy_async_smem();
+            mbar_arrive(&bar->a_full);
+            if (warp == 0) R_STAMP(0, i, 3);
+            if (i > 0) finish_tile(i - 1);
+            if (warp == 0) R_STAMP(0, i, 4);
+        }
+        if (n_my > 0) finish_tile(n_my - 1);
+    } else if (warp < R_ROW_WARPS + R_EPI_WARPS) {
+        // =====================================================================================
+        // epilogue warps
+        // =====================================================================================
+        const int lq = warp & 3;
+        const uint32_t lane_addr = tmem_base + ((uint32_t)(lq * 32) << 16);
+        // everything indexed by the layer is selected into registers HERE: a runtime index into the parameter
+        // struct (or a local array) becomes a local-memory load + a dependent branch per element in the loops below
+        const ActSel a0 = act_select(p.act[0], p.slope[0]), a1 = act_select(p.act[1], p.slope[1]);
+        const bool two = p.n_tc > 1;
+        const ActSel a_l = two ? a1 : a0;
+        const float* bias_l = s_bias + (two ? 64 : 0);
+        const uint32_t dcol_l = two ? RC_D1 : RC_D0;
+        float* my_row = stage + (lq * 32 + lane) * R_STAGE_LD;
+#pragma unroll 1
+        for (int i = 0; i < n_my; ++i) {
+            const uint32_t ph = (uint32_t)i & 1;
+            if (lq == 0) R_STAMP(1, i, 0);
+            mbar_wait(&bar->d0_full, ph);
+            tc_fence_after_sync();
+            if (lq == 0) R_STAMP(1, i, 1);
+            if (two) {
+                // X1 = act(D0 + b0) -> TF32 hi/lo -> TMEM operand of layer 1
+#pragma unroll 1
+                for (int hf = 0; hf < 2; ++hf) {
+                    uint32_t v[32], lo[32];
+                    tmem_ld32(lane_addr + RC_D0 + hf * 32, v);
+                    tmem_wait_ld();
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) {
+                        const float y = act_do(a0, __uint_as_float(v[j]) + s_bias[hf * 32 + j]);
+                        const float hh = round_tf32(y);
+                        v[j] = __float_as_uint(hh);
+                        lo[j] = __float_as_uint(y - hh);
+                    }
+                    tmem_st32(lane_addr + RC_AHI + hf * 32, v);
+                    tmem_st32(lane_addr + RC_ALO + hf * 32, lo);
+                }
+                tmem_wait_st();
+                tc_fence_before_sync();
+                mbar_arrive(&bar->d0_free);
+                mbar_arrive(&bar->x1_ready);
+                mbar_wait(&bar->d1_full, ph);
+                tc_fence_after_sync();
+            }
+            mbar_wait(&bar->st_empty, ph ^ 1);                            // stage consumed (tile i-1)
+            if (lq == 0) R_STAMP(1, i, 2);
+#pragma unroll 1
+            for (int hf = 0; hf < 2; ++hf) {
+                uint32_t v[32];
+                tmem_ld32(lane_addr + dcol_l + hf * 32, v);
+                tmem_wait_ld();
+#pragma unroll
+                for (int j = 0; j < 32; j += 4) {
+                    float4 r;
+                    r.x = act_do(a_l, __uint_as_float(v[j]) + bias_l[hf * 32 + j]);
+                    r.y = act_do(a_l, __uint_as_float(v[j + 1]) + bias_l[hf * 32 + j + 1]);
+                    r.z = act_do(a_l, __uint_as_float(v[j + 2]) + bias_l[hf * 32 + j + 2]);
+                    r.w = act_do(a_l, __uint_as_float(v[j + 3]) + bias_l[hf * 32 + j + 3]);
+                    *reinterpret_cast<float4*>(my_row + hf * 32 + j) = r;
+                }
+            }
+            tc_fence_before_sync();
+            if (!two) mbar_arrive(&bar->d0_free);
+            mbar_arrive(&bar->st_full);
+            if (lq == 0) R_STAMP(1, i, 3);
+        }
+    } else {
+        // =====================================================================================
+        // MMA issuer
+        // =====================================================================================
+        if (lane == 0) {
+            const uint32_t idesc = make_idesc_tf32(R_TILE, RF);
+            const uint32_t a_u32 = smem_u32(a_slot), w_u32 = smem_u32(w_tile);
+            for (int i = 0; i < n_my; ++i) {
+                const uint32_t ph = (uint32_t)i & 1;
+                R_STAMP(2, i, 0);
+                mbar_wait(&bar->d0_free, ph ^ 1);                         // D0 of tile i-1 has been read
+                R_STAMP(2, i, 1);
+                mbar_wait(&bar->a_full, ph);
+                tc_fence_after_sync();
+                R_STAMP(2, i, 2);
+#pragma unroll
+                for (int c = 0; c < 2; ++c) {
+                    const uint32_t a_hi = a_u32 + c * 2 * R_A_TILE, a_lo = a_hi + R_A_TILE;
+                    const uint32_t w_hi = w_u32 + c * 2 * R_W_TILE, w_lo = w_hi + R_W_TILE;
+#pragma unroll
+                    for (int ks = 0; ks < R_KC / 8; ++ks) {
+                        const uint64_t dah = make_desc_sw128(a_hi + ks * 32), dal = make_desc_sw128(a_lo + ks * 32);
+                        const uint64_t dwh = make_desc_sw128(w_hi + ks * 32), dwl = make_desc_sw128(w_lo + ks * 32);
+                        mma_tf32_ss(tmem_base + RC_D0, dal, dwh, idesc, (c | ks) ? 1u : 0u);
+                        mma_tf32_ss(tmem_base + RC_D0, dah, dwl, idesc, 1u);
+                        mma_tf32_ss(tmem_base + RC_D0, dah, dwh, idesc, 1u);
+                    }
+                }
+                mma_commit(&bar->a_empty);
+                mma_commit(&bar->d0_full);
+                R_STAMP(2, i, 3);
+                if (p.n_tc > 1) {
+                    mbar_wait(&bar->x1_ready, ph);
+                    tc_fence_after_sync();
+#pragma unroll
+                    for (int c = 0; c < 2; ++c) {
+                        const uint32_t w_hi = w_u32 + (uint32_t)R_W_IMAGE + c * 2 * R_W_TILE, w_lo = w_hi + R_W_TILE;
+#pragma unroll
+                        for (int ks = 0; ks < R_KC / 8; ++ks) {
+                            const uint32_t kcol = c * R_KC + ks * 8;
+                            const uint64_t dwh = make_desc_sw128(w_hi + ks * 32), dwl = make_desc_sw128(w_lo + ks * 32);
+                            mma_tf32_ts(tmem_base + RC_D1, tmem_base + RC_ALO + kcol, dwh, idesc, (c | ks) ? 1u : 0u);
+                            mma_tf32_ts(tmem_base + RC_D1, tmem_base + RC_AHI + kcol, dwl, idesc, 1u);
+                            mma_tf32_ts(tmem_base + RC_D1, tmem_base + RC_AHI + kcol, dwh, idesc, 1u);
+                        }
+                    }
+                    mma_commit(&bar->d1_full);
+                }
+            }
+        }
+    }
+    tc_fence_before_sync();
+    __syncthreads();
+    if (warp == R_ROW_WARPS + R_EPI_WARPS) tmem_dealloc(tmem_base, 256);
+}
+
+}  // namespace tc
+}  // namespace swe
+
+using namespace swe;
+
+static long long* g_rowmlp_trace = nullptr;
+extern "C" void swe_row_mlp_tc_set_trace(long long* t) { g_rowmlp_trace = t; }
+
+extern "C" int swe_row_mlp_tc(const swe_rowmlp_t* d, void* stream) {
+    SWE_REQUIRE(d, SWE_E_INVAL, "row_mlp_tc: null descriptor");
+    SWE_REQUIRE(d->n_rows >= 0 && d->row_lo >= 0 && (d->n_tc == 1 || d->n_tc == 2), SWE_E_INVAL, "row_mlp_tc: bad sizes");
+    SWE_REQUIRE((d->x_rows != nullptr) != (d->raw != nullptr), SWE_E_INVAL, "row_mlp_tc: exactly one of x_rows / raw");
+    SWE_REQUIRE(!d->raw || (d->w_first && d->raw_cols >= 1 && d->raw_cols + (d->with_wl ? 1 : 0) <= 8), SWE_E_UNSUPP,
+                "row_mlp_tc: the CUDA-core first layer takes at most 8 inputs");
+    SWE_REQUIRE((d->out_rows != nullptr) != (d->head != 0), SWE_E_INVAL, "row_mlp_tc: exactly one of out_rows / head");
+    SWE_REQUIRE(!d->head || d->n_cols <= 16, SWE_E_UNSUPP, "row_mlp_tc: the head handles at most 16 input columns");
+    SWE_REQUIRE(!d->head || (d->w_head && d->x0 && d->pred && d->previous_t >= 1 && d->n_cols > 2 * d->previous_t &&
+                             d->res_mode >= 0 && d->res_mode <= 3 && (d->res_mode == 0 || d->res_mode == 3 || d->res_w)),
+                SWE_E_INVAL, "row_mlp_tc: bad head arguments");
+    for (int l = 0; l < d->n_tc; ++l)
+        SWE_REQUIRE(d->img[l] && aligned16(d->img[l]), SWE_E_ALIGN, "row_mlp_tc: layer %d image null/unaligned", l);
+    SWE_REQUIRE((!d->x_rows || aligned16(d->x_rows)) && (!d->out_rows || aligned16(d->out_rows)), SWE_E_ALIGN,
+                "row_mlp_tc: unaligned rows");
+    if (d->n_rows == 0) return 0;
+    tc::RowMlpParams p;
+    memset(&p, 0, sizeof(p));
+    p.x_rows = d->x_rows; p.act_in = d->act_in; p.slope_in = d->slope_in;
+    p.raw = d->raw; p.raw_ld = d->raw_ld; p.raw_col0 = d->raw_col0; p.raw_cols = d->raw_cols; p.with_wl = d->with_wl;
+    p.wl_col_a = d->wl_col_a; p.wl_col_b = d->wl_col_b; p.perm = d->perm;
+    p.w_first = d->w_first; p.b_first = d->b_first; p.act_first = d->act_first; p.slope_first = d->slope_first;
+    p.raw_k = d->raw_cols + (d->with_wl ? 1 : 0);
+    p.row_lo = d->row_lo; p.n_rows = d->n_rows; p.n_tc = d->n_tc;
+    for (int l = 0; l < 2; ++l) {
+        p.img[l] = (const unsigned char*)d->img[l]; p.bias[l] = d->bias[l]; p.act[l] = d->act[l]; p.slope[l] = d->slope[l];
+    }
+    p.out_rows = d->out_rows; p.head = d->head; p.w_head = d->w_head; p.b_head = d->b_head; p.act_head = d->act_head;
+    p.slope_head = d->slope_head; p.x0 = d->x0; p.n_cols = d->n_cols; p.head_perm = d->head_perm; p.previous_t = d->previous_t;
+    p.res_mode = d->res_mode; p.res_w = d->res_w; p.eps = d->eps; p.pred = d->pred; p.step_ptr = d->step_ptr;
+    p.pred_step_stride = d->pred_step_stride; p.x_next = d->x_next;
+    p.trace = g_rowmlp_trace; g_rowmlp_trace = nullptr;
+    cudaError_t e = cudaFuncSetAttribute(tc::row_mlp_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc::ROWMLP_SMEM);
+    if (e != cudaSuccess) { set_error("row_mlp_tc smem opt-in (%zu B): %s", tc::ROWMLP_SMEM, cudaGetErrorString(e)); return (int)e; }
+    const long long n_tiles = (d->n_rows + tc::R_TILE - 1) / tc::R_TILE;
+    tc::row_mlp_tc_kernel<<<grid_for(n_tiles, 1), tc::R_THREADS, tc::ROWMLP_SMEM, (cudaStream_t)stream>>>(p);
+    return check_launch("row_mlp_tc");
+}

@@ -33,10 +33,14 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
 }
 // Bounded wait: a protocol bug must surface as a trapped kernel (reported cudaError), never as a
 // GPU that hangs until the box is reclaimed.
+//
+// Back-off: a failed try_wait is followed by a short nanosleep so that hundreds of idle threads do not re-issue
+// try_wait back to back on the shared-memory pipe that also feeds the tensor core its SS-mode operands.
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
     if (mbar_try_wait(bar, parity)) return;
     const long long t0 = clock64();
     while (!mbar_try_wait(bar, parity)) {
+        __nanosleep(64);
         if (clock64() - t0 > 4000000000ll) {       // ~2 s at 2 GHz
             printf("swe tc: mbarrier wait timed out (block %d thread %d bar %p parity %u)\n", blockIdx.x,
                    threadIdx.x, (void*)bar, parity);

@@ -216,6 +216,122 @@ class PackedGateTC:
         return codes, slopes
 
 
+def rowmlp_backend() -> str:
+    """'tc' (tcgen05 row MLPs for encoders / W0 / decoder head, default for F = 64) or 'ffma'."""
+    import os
+    return os.environ.get("MSWE_ROWMLP", "tc")
+
+
+class RowMlpTC:
+    """tcgen05 image of a ``make_mlp`` stack for ``swe_row_mlp_tc``.
+
+    kind='encoder': Linear(k<=8 -> 64) on CUDA cores + two 64->64 tensor-core layers;
+    kind='decoder': two 64->64 tensor-core layers + the 64->2 head;
+    kind='linear' : a single bias-free 64->64 layer (filter_matrix[0])."""
+
+    def __init__(self, linears, acts, kind: str):
+        self.linears, self.acts, self.kind = list(linears), list(acts), kind
+        self._stamp = None
+        self._img = None
+
+    @staticmethod
+    def split(seq: nn.Sequential):
+        lins = [m for m in seq if isinstance(m, nn.Linear)]
+        acts, mods = [], list(seq)
+        for i, m in enumerate(mods):
+            if isinstance(m, nn.Linear):
+                acts.append(mods[i + 1] if i + 1 < len(mods) and not isinstance(mods[i + 1], nn.Linear) else None)
+        return lins, acts
+
+    @classmethod
+    def for_encoder(cls, seq: nn.Sequential, F: int, max_in: int = 8):
+        lins, acts = cls.split(seq)
+        ok = F == 64 and len(lins) == 3 and lins[0].in_features <= max_in and \
+            [tuple(l.weight.shape) for l in lins[1:]] == [(64, 64), (64, 64)] and lins[0].out_features == 64 and \
+            all(not (isinstance(a, nn.PReLU) and a.weight.numel() != 1) for a in acts)
+        return cls(lins, acts, "encoder") if ok else None
+
+    @classmethod
+    def for_decoder(cls, seq: nn.Sequential, F: int):
+        lins, acts = cls.split(seq)
+        ok = F == 64 and len(lins) == 3 and [tuple(l.weight.shape) for l in lins] == [(64, 64), (64, 64), (2, 64)] and \
+            all(not (isinstance(a, nn.PReLU) and a.weight.numel() != 1) for a in acts)
+        return cls(lins, acts, "decoder") if ok else None
+
+    def tc_layers(self):
+        return {"encoder": self.linears[1:], "decoder": self.linears[:2], "linear": self.linears}[self.kind]
+
+    def images(self):
+        tl = self.tc_layers()
+        stamp = tuple((l.weight.data_ptr(), l.weight._version) for l in tl)
+        if stamp != self._stamp:
+            dev = tl[0].weight.device
+            nb = lib.hop_tc_image_bytes()
+            if self._img is None or self._img.device != dev:
+                self._img = torch.empty(len(tl), nb, dtype=torch.uint8, device=dev)
+            with torch.no_grad():
+                for i, l in enumerate(tl):
+                    lib.hop_tc_pack(l.weight.detach().contiguous(), self._img[i])
+            self._stamp = stamp
+        return [self._img[i] for i in range(len(tl))]
+
+    def _fill_tc(self, d: "lib.SweRowMlp", layer_ids):
+        imgs = self.images()
+        d.n_tc = len(layer_ids)
+        for j, li in enumerate(layer_ids):
+            lin, act = self.linears[li], self.acts[li]
+            d.img[j] = imgs[j].data_ptr()
+            d.bias[j] = None if lin.bias is None else lin.bias.data_ptr()
+            d.act[j] = ACT_CODES[activation_name_of(act)]
+            d.slope[j] = act.weight.data_ptr() if isinstance(act, nn.PReLU) else None
+
+    def encode(self, raw, raw_col0, raw_cols, with_wl, wl_cols, perm, row_lo, n_rows, out_rows):
+        d = lib.SweRowMlp()
+        lin0, act0 = self.linears[0], self.acts[0]
+        d.raw, d.raw_ld, d.raw_col0, d.raw_cols = raw.data_ptr(), raw.shape[1], raw_col0, raw_cols
+        d.with_wl, d.wl_col_a, d.wl_col_b = int(with_wl), wl_cols[0], wl_cols[1]
+        d.perm = None if perm is None else lib.ptr(perm, torch.int32)
+        d.w_first = lib.ptr(lin0.weight.detach().contiguous())
+        d.b_first = None if lin0.bias is None else lin0.bias.data_ptr()
+        d.act_first = ACT_CODES[activation_name_of(act0)]
+        d.slope_first = act0.weight.data_ptr() if isinstance(act0, nn.PReLU) else None
+        d.row_lo, d.n_rows = row_lo, n_rows
+        self._fill_tc(d, [1, 2])
+        d.out_rows = lib.ptr(out_rows)
+        lib.row_mlp_tc(d)
+
+    def linear(self, x_rows, row_lo, n_rows, out_rows):
+        d = lib.SweRowMlp()
+        d.x_rows, d.act_in = lib.ptr(x_rows), 0
+        d.row_lo, d.n_rows = row_lo, n_rows
+        self._fill_tc(d, [0])
+        d.out_rows = lib.ptr(out_rows)
+        lib.row_mlp_tc(d)
+
+    def decode(self, h, act_in, slope_in, x0, perm, n_nodes, previous_t, res_mode, res_w, eps, pred, step_ptr, pred_stride,
+               x_next):
+        d = lib.SweRowMlp()
+        d.x_rows, d.act_in = lib.ptr(h), act_in
+        d.slope_in = None if slope_in is None else slope_in.data_ptr()
+        d.row_lo, d.n_rows = 0, n_nodes
+        self._fill_tc(d, [0, 1])
+        lin, act = self.linears[2], self.acts[2]
+        d.head = 1
+        d.w_head = lib.ptr(lin.weight.detach().contiguous())
+        d.b_head = None if lin.bias is None else lin.bias.data_ptr()
+        d.act_head = ACT_CODES[activation_name_of(act)]
+        d.slope_head = act.weight.data_ptr() if isinstance(act, nn.PReLU) else None
+        d.x0, d.n_cols, d.previous_t = lib.ptr(x0), x0.shape[1], previous_t
+        d.head_perm = None if perm is None else lib.ptr(perm, torch.int32)
+        d.res_mode, d.eps = res_mode, float(eps)
+        d.res_w = None if res_w is None else lib.ptr(res_w)
+        d.pred = lib.ptr(pred)
+        d.step_ptr = None if step_ptr is None else lib.ptr(step_ptr, torch.int32)
+        d.pred_step_stride = pred_stride
+        d.x_next = None if x_next is None else lib.ptr(x_next)
+        lib.row_mlp_tc(d)
+
+
 def hop_backend() -> str:
     """'tc' (tcgen05 filter, default for F = 64) or 'ffma' (exact-fp32 CUDA cores)."""
     import os
@@ -253,6 +369,7 @@ class SweGnnLauncher:
         self.mlp = PackedMLP(module.edge_mlp, [(F, self.FP)] * nseg, two)
         self.filters = PackedFilters(list(module.filter_matrix), F, self.FP) if module.with_filter_matrix else None
         self.tc = PackedGateTC(module.edge_mlp) if PackedGateTC.eligible(module.edge_mlp, F) else None
+        self.w0_tc = RowMlpTC([module.filter_matrix[0]], [None], "linear") if (module.with_filter_matrix and F == 64) else None
 
     def gate(self, es, xs, xd_src, xd_dst, a, s_buf, dbg=None, ptab=None):
         m = self.m
@@ -289,13 +406,18 @@ class SweGnnLauncher:
         if m.with_filter_matrix:
             W = self.filters.tensors()
             # o_0 = x_d W0ᵀ on the destination rows and on every source row read by the hops
+            def w0(x, lo, n):
+                if self.w0_tc is not None and rowmlp_backend() == "tc":
+                    self.w0_tc.linear(x, lo, n, tmp_a)
+                else:
+                    lib.node_linear_fwd(x, lo, n, W[0], tmp_a, FP)
             if xd_dst is not None:
-                lib.node_linear_fwd(xd_dst, es.dst_lo, es.n_dst, W[0], tmp_a, FP)
+                w0(xd_dst, es.dst_lo, es.n_dst)
                 if es.src_lo != es.dst_lo:
-                    lib.node_linear_fwd(xd_src, es.src_lo, es.src_hi - es.src_lo, W[0], tmp_a, FP)
+                    w0(xd_src, es.src_lo, es.src_hi - es.src_lo)
                 o_src, o_dst = tmp_a, tmp_a
             else:
-                lib.node_linear_fwd(xd_src, es.src_lo, es.src_hi - es.src_lo, W[0], tmp_a, FP)
+                w0(xd_src, es.src_lo, es.src_hi - es.src_lo)
                 o_src, o_dst = tmp_a, None
         else:
             W = [None] * (K + 1)

@@ -43,6 +43,20 @@ class SweRows(C.Structure):
     _fields_ = [("n_seg", C.c_int32), ("_pad", C.c_int32), ("seg", SweSeg * SWE_MAX_SEGS)]
 
 
+class SweRowMlp(C.Structure):
+    _fields_ = [("x_rows", C.c_void_p), ("act_in", C.c_int32), ("_pad0", C.c_int32), ("slope_in", C.c_void_p),
+                ("raw", C.c_void_p), ("raw_ld", C.c_int32), ("raw_col0", C.c_int32), ("raw_cols", C.c_int32),
+                ("with_wl", C.c_int32), ("wl_col_a", C.c_int32), ("wl_col_b", C.c_int32), ("perm", C.c_void_p),
+                ("w_first", C.c_void_p), ("b_first", C.c_void_p), ("act_first", C.c_int32), ("_pad1", C.c_int32),
+                ("slope_first", C.c_void_p), ("row_lo", C.c_int32), ("_pad2", C.c_int32), ("n_rows", C.c_int64),
+                ("n_tc", C.c_int32), ("_pad3", C.c_int32), ("img", C.c_void_p * 2), ("bias", C.c_void_p * 2),
+                ("act", C.c_int32 * 2), ("slope", C.c_void_p * 2), ("out_rows", C.c_void_p),
+                ("head", C.c_int32), ("act_head", C.c_int32), ("w_head", C.c_void_p), ("b_head", C.c_void_p),
+                ("slope_head", C.c_void_p), ("x0", C.c_void_p), ("n_cols", C.c_int32), ("previous_t", C.c_int32),
+                ("head_perm", C.c_void_p), ("res_mode", C.c_int32), ("eps", C.c_float), ("res_w", C.c_void_p),
+                ("pred", C.c_void_p), ("step_ptr", C.c_void_p), ("pred_step_stride", C.c_int64), ("x_next", C.c_void_p)]
+
+
 _p, _i32, _i64, _f32, _sz = C.c_void_p, C.c_int32, C.c_int64, C.c_float, C.c_size_t
 _mlp = C.POINTER(SweMlp)
 _rows = C.POINTER(SweRows)
@@ -66,6 +80,7 @@ SIGNATURES = {
     "swe_gate_partials_tc": (C.c_int, [_p, _p, _i32, _i32, _p, _i32, _i32, _p, _p]),
     "swe_edge_gate_tc_dec_fwd": (C.c_int, [_p, _p, _p, _p, _p, _i64, _p, _i32, C.POINTER(C.c_int32), C.POINTER(C.c_void_p),
                                            _i32, _p, _p]),
+    "swe_row_mlp_tc": (C.c_int, [C.POINTER(SweRowMlp), _p]),
     "swe_hop_tc_image_bytes": (_sz, []),
     "swe_hop_tc_pack": (C.c_int, [_p, _p, _p]),
     "swe_propagate_hop_tc_fwd": (C.c_int, [_p, _p, _p, _p, _p, _i32, _i32, _p, _i32, _i32, _p, _i32, _p, _p, _p, _p]),
@@ -244,6 +259,10 @@ def edge_gate_tc_dec_fwd(p_src, p_dst, a, src, dst, n_edges, image, k1, acts, sl
     _check(load().swe_edge_gate_tc_dec_fwd(ptr(p_src), ptr(p_dst), ptr(a), ptr(src, torch.int32), ptr(dst, torch.int32),
                                            n_edges, image.data_ptr(), k1, act3, slope3, int(normalize), ptr(s_out),
                                            _stream()), "swe_edge_gate_tc_dec_fwd")
+
+
+def row_mlp_tc(desc: SweRowMlp):
+    _check(load().swe_row_mlp_tc(C.byref(desc), _stream()), "swe_row_mlp_tc")
 
 
 def hop_tc_image_bytes() -> int:

@@ -25,7 +25,7 @@ import torch.nn as nn
 from torch import Tensor
 
 from .. import lib
-from ..engine import PackedMLP, SweGnnLauncher, padded_width
+from ..engine import PackedMLP, RowMlpTC, SweGnnLauncher, gate_layer0, padded_width, rowmlp_backend
 from ..lib import ACT_CODES
 from ..plan import PlanCache, build_plan
 from .models import BaseFloodModel, activation_functions, make_mlp
@@ -97,7 +97,8 @@ class SWEGNN(nn.Module):
             a = widen(edge_attr)[es.eid.long()].contiguous()
         s_buf = torch.empty(max(es.n_edges, 1), FP, device=xd.device)
         ta, tb, out = torch.empty_like(xd), torch.empty_like(xd), torch.empty_like(xd)
-        ptab = (torch.empty(N, 2 * FP, device=xd.device), torch.empty(N, 2 * FP, device=xd.device)) if FP == 64 else None
+        ptab = (torch.empty(N, 2 * FP, device=xd.device), torch.empty(N, 2 * FP, device=xd.device)) \
+            if (FP == 64 and gate_layer0() == "dec") else None
         la.run(es, xs, xd, xd, a, s_buf, False, ta, tb, out, ptab=ptab)
         return out if FP == F else out[:, :F].contiguous()
 
@@ -127,6 +128,24 @@ class _EncodeDecodeMixin:
         self._plans = PlanCache()
         self._ws = {}
         self._edge_cache = None
+        self._edge_cache_ref = None
+        # tcgen05 row MLPs (F = 64, 3-layer encoders / decoder): None where the stack does not fit
+        self._tc_static = RowMlpTC.for_encoder(self.static_node_encoder, F)
+        self._tc_dynamic = RowMlpTC.for_encoder(self.dynamic_node_encoder, F)
+        self._tc_decoder = RowMlpTC.for_decoder(self.node_decoder, F)
+        self._tc_edge = RowMlpTC.for_encoder(self.edge_encoder, F) if self._pk_edge is not None else None
+
+    def _encode_nodes(self, x, plan, n_dyn_rows, xs, xd):
+        """static_node_encoder / dynamic_node_encoder (reference gnn.py:284-294)."""
+        n_static_raw = self.static_node_features - int(bool(self.with_WL))
+        if self._tc_static is not None and self._tc_dynamic is not None and rowmlp_backend() == "tc":
+            n_cols = x.shape[1]
+            self._tc_static.encode(x, 0, n_static_raw, self.with_WL, (n_static_raw - 1, n_cols - 2), plan.perm, 0,
+                                   plan.n_nodes, xs)
+            self._tc_dynamic.encode(x, n_static_raw, n_cols - n_static_raw, False, (0, 0), plan.perm, 0, n_dyn_rows, xd)
+        else:
+            lib.node_encode_fwd(x, plan.perm, plan.n_nodes, n_static_raw, self.with_WL, n_dyn_rows,
+                                self._pk_static.struct(), self._pk_dynamic.struct(), xs, xd, self._FP)
 
     def _check_input(self, graph):
         x = graph.x
@@ -145,6 +164,8 @@ class _EncodeDecodeMixin:
     def _workspace(self, plan, names):
         key = (plan.key, plan.n_nodes)
         ws = self._ws.get(key)
+        if ws is not None and ws.get("_plan") is not plan:      # same key, different plan object: a recycled address
+            ws = None
         if ws is None:
             dev = plan.edges[0].rowptr.device
             FP, N = self._FP, plan.n_nodes
@@ -152,9 +173,11 @@ class _EncodeDecodeMixin:
             ws["s"] = torch.empty(plan.max_edges, FP, dtype=torch.float32, device=dev)
             # per-node partial tables of the decomposed edge-MLP layer 0 (tcgen05 gate, F = 64)
             ws["ptab"] = (torch.empty(N, 2 * FP, dtype=torch.float32, device=dev),
-                          torch.empty(N, 2 * FP, dtype=torch.float32, device=dev)) if FP == 64 else None
+                          torch.empty(N, 2 * FP, dtype=torch.float32, device=dev)) \
+                if (FP == 64 and gate_layer0() == "dec") else None
             ws["a"] = None
-            if len(self._ws) >= 2:
+            ws["_plan"] = plan
+            if len(self._ws) >= 2 and key not in self._ws:
                 self._ws.pop(next(iter(self._ws)))
             self._ws[key] = ws
         return ws
@@ -170,8 +193,8 @@ class _EncodeDecodeMixin:
             return torch.cat(parts).contiguous()
         st = self._pk_edge.struct()
         ea = graph.edge_attr
-        stamp = (ea.data_ptr(), ea._version, tuple(ea.shape), self._pk_edge._stamp, plan.key)
-        if ws["a"] is not None and self._edge_cache == stamp:
+        stamp = (ea.data_ptr(), ea._version, tuple(ea.shape), self._pk_edge._stamp, plan.key, id(plan))
+        if ws["a"] is not None and self._edge_cache == stamp and self._edge_cache_ref is ea:
             return ws["a"]
         if ea.dtype != torch.float32 or not ea.is_contiguous():
             raise TypeError("edge_attr must be a contiguous float32 tensor")
@@ -179,13 +202,21 @@ class _EncodeDecodeMixin:
             ws["a"] = torch.empty(max(plan.n_edges_total, 1), self._FP, dtype=torch.float32, device=ea.device)
         for (lo, hi), es in zip(plan.edge_slices, plan.edges):
             if es.n_edges:
-                lib.edge_encode_fwd(ea[lo:hi], es.eid, es.n_edges, st, ws["a"][lo:hi], self._FP)
+                if self._tc_edge is not None and rowmlp_backend() == "tc":
+                    self._tc_edge.encode(ea[lo:hi], 0, ea.shape[1], False, (0, 0), es.eid, 0, es.n_edges, ws["a"][lo:hi])
+                else:
+                    lib.edge_encode_fwd(ea[lo:hi], es.eid, es.n_edges, st, ws["a"][lo:hi], self._FP)
         self._edge_cache = stamp
+        self._edge_cache_ref = ea            # identity, not just address: a freed tensor's address can be reused
         return ws["a"]
 
     def _decode(self, h, act_name, act_module, x, plan, pred, step_ptr=None, pred_stride=0, x_next=None):
         slope = act_module.weight if isinstance(act_module, nn.PReLU) else None
         res_w = self.residual_weights.detach().contiguous() if self._residual_mode() in (1, 2) else None
+        if self._tc_decoder is not None and rowmlp_backend() == "tc" and x.shape[1] <= 16:
+            self._tc_decoder.decode(h, ACT_CODES[act_name], slope, x, plan.perm, plan.n_nodes, self.previous_t,
+                                    self._residual_mode(), res_w, 1e-4, pred, step_ptr, pred_stride, x_next)
+            return
         lib.decode_head_fwd(h, ACT_CODES[act_name], slope, self._pk_decoder.struct(), x, plan.perm, plan.n_nodes,
                             self.previous_t, self._residual_mode(), res_w, 1e-4, pred, step_ptr, pred_stride,
                             x_next, self._FP)
@@ -268,8 +299,7 @@ class GNN(BaseFloodModel, _EncodeDecodeMixin):
         ws = self._workspace(plan, ["xs", "h0", "h1", "ta", "tb"])
         a = self._encoded_edges(plan, graph, ws)
         N = plan.n_nodes
-        lib.node_encode_fwd(x, plan.perm, N, self.static_node_features - self.with_WL, self.with_WL, N,
-                            self._pk_static.struct(), self._pk_dynamic.struct(), ws["xs"], ws["h0"], FP)
+        self._encode_nodes(x, plan, N, ws["xs"], ws["h0"])
         cur, nxt = ws["h0"], ws["h1"]
         act_mod = self.gnn_activation
         slope = act_mod.weight if isinstance(act_mod, nn.PReLU) else None
@@ -373,8 +403,7 @@ class MSGNN(BaseFloodModel, _EncodeDecodeMixin):
         ws = self._workspace(plan, ["xs", "cur", "down", "up", "ta", "tb"])
         a = self._encoded_edges(plan, graph, ws)
         xs, cur, down, up, ta, tb, s_buf = ws["xs"], ws["cur"], ws["down"], ws["up"], ws["ta"], ws["tb"], ws["s"]
-        lib.node_encode_fwd(x, plan.perm, plan.n_nodes, self.static_node_features - self.with_WL, self.with_WL,
-                            plan.scale_n[0], self._pk_static.struct(), self._pk_dynamic.struct(), xs, cur, FP)
+        self._encode_nodes(x, plan, plan.scale_n[0], xs, cur)
 
         def a_of(s):
             lo, hi = plan.edge_slices[s]

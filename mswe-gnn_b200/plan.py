@@ -162,13 +162,19 @@ class PlanCache:
 
     def get(self, graph, num_scales: int, multiscale: bool) -> GraphPlan:
         key = _topology_key(graph, multiscale)
-        plan = self._items.get(key)
-        if plan is None:
+        hit = self._items.get(key)
+        if hit is None:
             plan = build_plan(graph, num_scales, multiscale)
             if len(self._items) >= self.capacity:
                 self._items.pop(next(iter(self._items)))
+            # the key is built from data_ptr()s: keep the tensors alive for as long as the entry lives, otherwise
+            # the allocator may hand the same address to a DIFFERENT graph of the same shape and the key would lie
+            keep = [graph.edge_index] + ([getattr(graph, n) for n in ("node_ptr", "edge_ptr", "intra_mesh_edge_index",
+                                                                       "intra_edge_ptr")] if multiscale else [])
+            plan._key_tensors = keep
             self._items[key] = plan
-        return plan
+            return plan
+        return hit
 
     def clear(self):
         self._items.clear()

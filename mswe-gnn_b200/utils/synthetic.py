@@ -80,7 +80,7 @@ def _containment(nx: int, ny: int) -> np.ndarray:
 def make_tri_mesh(nx: int, ny: int, num_scales: int = 4, previous_t: int = 3, rollout_steps: int = 1,
                   wet: str = "random", wet_fraction: float = 0.3, inflow: float = 0.3,
                   seed: int = 0, link_ghosts: bool = False, orphan_every: int = 0,
-                  extra_parent_every: int = 0, dtype=torch.float32) -> Data:
+                  extra_parent_every: int = 0, dtype=torch.float32, with_y: bool = True) -> Data:
     """Multi-scale graph of ``tri(nx, ny)`` with ``num_scales`` levels.
 
     wet='random' : 30 % wet nodes with h,|q| ~ U(0,1) in every window slot (stress fixture).
@@ -137,7 +137,8 @@ def make_tri_mesh(nx: int, ny: int, num_scales: int = 4, previous_t: int = 3, ro
     x = torch.cat([area[:, None], dem[:, None], dyn], 1)
     node_BC = torch.tensor([int(node_ptr[1]) - 1], dtype=torch.long)
     BC = torch.full((1, previous_t, rollout_steps + 1), float(inflow), dtype=dtype)
-    y = torch.rand(N, 2, rollout_steps, generator=g1, dtype=dtype)
+    # targets (only the training step reads them; the rollout reads just their last dimension)
+    y = torch.rand(N, 2, rollout_steps, generator=g1, dtype=dtype) if with_y else torch.empty(0, 2, rollout_steps, dtype=dtype)
 
     data = Data(
         x=x,
