@@ -316,13 +316,15 @@ def run_ours(args):
     if partitioned:
         multi = (f"ONE mesh tri({nx},{ny}) = {N_global} nodes cut over {world} GPUs by blocks of coarsest cells "
                  f"(every level sharded, {halo_info['exchanges_per_step']} NCCL halo exchanges per step, "
-                 f"<= {halo_info['max_bytes_per_exchange']} B each); per-GPU work fixed at cfg3's size")
+                 f"<= {halo_info['max_bytes_per_exchange']} B each); " +
+                 ("per-GPU work fixed at cfg3's size (weak scaling)" if wl == "cfg3" else "fixed total mesh (strong scaling)"))
     elif world > 1:
         multi = "independent simulations per rank (replicas, no collective)"
     else:
         multi = "single GPU"
     line = {"metric": "mSWE-GNN rollout node-steps/sec", "value": value, "unit": "node-steps/s", "n_gpus": world,
-            "steps": K, "warmup": W, "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak",
+            "steps": K, "warmup": W, "ms_per_step": ms / K, "higher_is_better": True,
+            "scaling": "strong" if (partitioned and wl != "cfg3") else "weak",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": f"{wl}: default config.yaml mSWE-GNN (K=4,F=64,mlp_layers=3,S=4) autoregressive rollout on "
                                    f"tri({nx},{ny}) = {N_global} nodes ({N_nodes} owned per GPU); random-init weights seed 666; 30% wet nodes",
