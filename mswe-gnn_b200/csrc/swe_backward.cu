@@ -13,19 +13,20 @@ __device__ __forceinline__ int round4(int v) { return (v + 3) & ~3; }
 // ---------------------------------------------------------------------------------------------
 // row provider: dst[r][0:w_pad) = act(X_seg[row0 + r, :]) (zero beyond the segment width / n_rows)
 // ---------------------------------------------------------------------------------------------
+// columns [c0, c0 + w_pad) of the segment, rows [row0, row0 + n_tile_rows)
 __device__ __forceinline__ void load_seg_tile(float* __restrict__ dst, int ldd, const swe_seg_t& sg, long long row0,
-                                              long long n_rows, int w_pad) {
+                                              long long n_rows, int w_pad, int c0 = 0, int n_tile_rows = TM) {
     const float slope = (sg.act == SWE_ACT_PRELU && sg.slope) ? __ldg(sg.slope) : 0.f;
     const bool vec = (sg.ld % 4 == 0) && (sg.width % 4 == 0) && ((reinterpret_cast<uintptr_t>(sg.base) & 15u) == 0);
     if (vec) {
         const int qpr = w_pad / 4;
-        for (int idx = threadIdx.x; idx < TM * qpr; idx += NT) {
+        for (int idx = threadIdx.x; idx < n_tile_rows * qpr; idx += NT) {
             const int r = idx / qpr, q = idx % qpr;
             const long long g = row0 + r;
             float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (g < n_rows && 4 * q < sg.width) {
+            if (g < n_rows && c0 + 4 * q < sg.width) {
                 const long long sr = sg.idx ? (long long)__ldg(sg.idx + g) : g;
-                v = ldg4(sg.base + sr * sg.ld + 4 * q);
+                v = ldg4(sg.base + sr * sg.ld + c0 + 4 * q);
                 if (sg.act != SWE_ACT_NONE) {
                     v.x = act_apply(sg.act, v.x, slope); v.y = act_apply(sg.act, v.y, slope);
                     v.z = act_apply(sg.act, v.z, slope); v.w = act_apply(sg.act, v.w, slope);
@@ -34,18 +35,20 @@ __device__ __forceinline__ void load_seg_tile(float* __restrict__ dst, int ldd, 
             stg4(dst + r * ldd + 4 * q, v);
         }
     } else {
-        for (int idx = threadIdx.x; idx < TM * w_pad; idx += NT) {
+        for (int idx = threadIdx.x; idx < n_tile_rows * w_pad; idx += NT) {
             const int r = idx / w_pad, c = idx % w_pad;
             const long long g = row0 + r;
             float v = 0.f;
-            if (g < n_rows && c < sg.width) {
+            if (g < n_rows && c0 + c < sg.width) {
                 const long long sr = sg.idx ? (long long)__ldg(sg.idx + g) : g;
-                v = act_apply(sg.act, __ldg(sg.base + sr * sg.ld + c), slope);
+                v = act_apply(sg.act, __ldg(sg.base + sr * sg.ld + c0 + c), slope);
             }
             dst[r * ldd + c] = v;
         }
     }
 }
+
+constexpr int KSUB = 64;          // reduction extent staged at a time: keeps a CTA under 70 KB of shared memory (3 CTAs per SM)
 
 // ---------------------------------------------------------------------------------------------
 // pre = X · Wᵀ + b
@@ -55,8 +58,8 @@ __global__ void __launch_bounds__(NT) mlp_layer_fwd_kernel(const __grid_constant
                                                            const float* __restrict__ wt, const float* __restrict__ bias,
                                                            float* __restrict__ pre) {
     extern __shared__ __align__(16) float smem[];
-    float* A = smem;                       // [TM][132]
-    float* W = smem + TM * 132;            // [<=128][NO]
+    float* A = smem;                       // [TM][KSUB + 4]
+    float* W = smem + TM * (KSUB + 4);     // [KSUB][NO]
     const long long n_tiles = (n_rows + TM - 1) / TM;
     for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
         const long long row0 = tile * TM;
@@ -65,13 +68,16 @@ __global__ void __launch_bounds__(NT) mlp_layer_fwd_kernel(const __grid_constant
         int koff = 0;
         for (int j = 0; j < X.n_seg; ++j) {
             const int wp = round4(X.seg[j].width);
-            load_seg_tile(A, wp + 4, X.seg[j], row0, n_rows, wp);
-            block_cp_async(W, wt + (long long)koff * NO, wp * NO);
-            cp_async_commit();
-            cp_async_wait<0>();
-            __syncthreads();
-            dense_acc<NO>(acc, A, wp + 4, W, wp);
-            __syncthreads();
+            for (int c0 = 0; c0 < wp; c0 += KSUB) {
+                const int wc = min(KSUB, wp - c0);
+                load_seg_tile(A, KSUB + 4, X.seg[j], row0, n_rows, wc, c0);
+                block_cp_async(W, wt + (long long)(koff + c0) * NO, wc * NO);
+                cp_async_commit();
+                cp_async_wait<0>();
+                __syncthreads();
+                dense_acc<NO>(acc, A, KSUB + 4, W, wc);
+                __syncthreads();
+            }
             koff += wp;
         }
         dense_bias_act<NO>(acc, bias, SWE_ACT_NONE, 0.f);
@@ -88,51 +94,54 @@ __global__ void __launch_bounds__(NT) mlp_layer_bwd_dx_kernel(
     int n, const float* __restrict__ w, int w_ld, int k_off, int k_valid, float* __restrict__ dx, int accumulate,
     int write_delta, float* __restrict__ part) {
     extern __shared__ __align__(16) float smem[];
-    const int ldd = n + 4;
-    float* D = smem;                       // [TM][n+4]
-    float* Wb = smem + TM * ldd;           // [n][KO]
+    constexpr int LDD = KSUB + 4;
+    float* D = smem;                       // [TM][KSUB + 4]: delta columns [c0, c0 + KSUB)
+    float* Wb = smem + TM * LDD;           // [KSUB][KO]:     W rows     [c0, c0 + KSUB), columns k_off..
     __shared__ float red[NT / 32];
     const float slope = (act == SWE_ACT_PRELU && slope_p) ? __ldg(slope_p) : 0.f;
-    if (dx) {
-        for (int idx = threadIdx.x; idx < n * KO; idx += NT) {
-            const int nn = idx / KO, k = idx % KO;
-            Wb[idx] = (k < k_valid) ? __ldg(w + (long long)nn * w_ld + k_off + k) : 0.f;
-        }
-    }
-    float db_acc = 0.f, ds_acc = 0.f;
-    const int qpr = n / 4;
+    float db_acc0 = 0.f, db_acc1 = 0.f, ds_acc = 0.f;     // bias-gradient partials of columns t and KSUB + t (n <= 2 KSUB)
     const long long n_tiles = (n_rows + TM - 1) / TM;
     for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
         const long long row0 = tile * TM;
-        for (int idx = threadIdx.x; idx < TM * qpr; idx += NT) {
-            const int r = idx / qpr, q = idx % qpr;
-            const long long g = row0 + r;
-            float4 d = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (g < n_rows) {
-                d = *reinterpret_cast<const float4*>(dh + g * n + 4 * q);
-                if (pre) {
-                    const float4 p = ldg4(pre + g * n + 4 * q);
-                    if (act == SWE_ACT_PRELU) {
-                        ds_acc += (p.x > 0.f ? 0.f : d.x * p.x) + (p.y > 0.f ? 0.f : d.y * p.y) +
-                                  (p.z > 0.f ? 0.f : d.z * p.z) + (p.w > 0.f ? 0.f : d.w * p.w);
-                    }
-                    d.x *= act_grad(act, p.x, slope); d.y *= act_grad(act, p.y, slope);
-                    d.z *= act_grad(act, p.z, slope); d.w *= act_grad(act, p.w, slope);
-                    if (write_delta) *reinterpret_cast<float4*>(dh + g * n + 4 * q) = d;
+        float acc[DenseCfg<KO>::RM][8];
+        dense_zero<KO>(acc);
+        for (int c0 = 0; c0 < n; c0 += KSUB) {
+            const int nc = min(KSUB, n - c0), qpr = nc / 4;
+            if (dx) {
+                for (int idx = threadIdx.x; idx < nc * KO; idx += NT) {
+                    const int nn = idx / KO, k = idx % KO;
+                    Wb[idx] = (k < k_valid) ? __ldg(w + (long long)(c0 + nn) * w_ld + k_off + k) : 0.f;
                 }
             }
-            stg4(D + r * ldd + 4 * q, d);
-        }
-        __syncthreads();
-        if (part && threadIdx.x < n) {
-            float t = 0.f;
-            for (int r = 0; r < TM; ++r) t += D[r * ldd + threadIdx.x];
-            db_acc += t;
+            for (int idx = threadIdx.x; idx < TM * qpr; idx += NT) {
+                const int r = idx / qpr, q = idx % qpr;
+                const long long g = row0 + r;
+                float4 d = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (g < n_rows) {
+                    d = *reinterpret_cast<const float4*>(dh + g * n + c0 + 4 * q);
+                    if (pre) {
+                        const float4 p = ldg4(pre + g * n + c0 + 4 * q);
+                        if (act == SWE_ACT_PRELU) {
+                            ds_acc += (p.x > 0.f ? 0.f : d.x * p.x) + (p.y > 0.f ? 0.f : d.y * p.y) +
+                                      (p.z > 0.f ? 0.f : d.z * p.z) + (p.w > 0.f ? 0.f : d.w * p.w);
+                        }
+                        d.x *= act_grad(act, p.x, slope); d.y *= act_grad(act, p.y, slope);
+                        d.z *= act_grad(act, p.z, slope); d.w *= act_grad(act, p.w, slope);
+                        if (write_delta) *reinterpret_cast<float4*>(dh + g * n + c0 + 4 * q) = d;
+                    }
+                }
+                stg4(D + r * LDD + 4 * q, d);
+            }
+            __syncthreads();
+            if (part && (int)threadIdx.x < nc) {
+                float t = 0.f;
+                for (int r = 0; r < TM; ++r) t += D[r * LDD + threadIdx.x];
+                if (c0 == 0) db_acc0 += t; else db_acc1 += t;
+            }
+            if (dx) dense_acc<KO>(acc, D, LDD, Wb, nc);
+            __syncthreads();
         }
         if (dx) {
-            float acc[DenseCfg<KO>::RM][8];
-            dense_zero<KO>(acc);
-            dense_acc<KO>(acc, D, ldd, Wb, n);
             using C = DenseCfg<KO>;
             const int tx = threadIdx.x % C::TX, ty = threadIdx.x / C::TX;
 #pragma unroll
@@ -152,11 +161,12 @@ __global__ void __launch_bounds__(NT) mlp_layer_bwd_dx_kernel(
                 }
             }
         }
-        __syncthreads();
     }
     if (part) {
         float* my = part + (long long)blockIdx.x * (n + 1);
-        if (threadIdx.x < n) my[threadIdx.x] = db_acc;
+        const int t = (int)threadIdx.x;                       // (signed: n - KSUB is negative for narrow layers)
+        if (t < min(n, KSUB)) my[t] = db_acc0;
+        if (t < n - KSUB) my[KSUB + t] = db_acc1;
 #pragma unroll
         for (int off = 16; off >= 1; off >>= 1) ds_acc += __shfl_xor_sync(0xffffffffu, ds_acc, off);
         if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = ds_acc;
@@ -177,30 +187,31 @@ __global__ void __launch_bounds__(NT) mlp_layer_bwd_dw_kernel(const float* __res
                                                               const __grid_constant__ swe_rows_t X,
                                                               float* __restrict__ part) {
     extern __shared__ __align__(16) float smem[];
-    float* Dt = smem;                      // [TM (n index)][LDT (row index)]
-    float* Xs = smem + TM * LDT;           // [TM rows][KO]
-    for (int idx = threadIdx.x; idx < TM * LDT; idx += NT) Dt[idx] = 0.f;
+    constexpr int LDR = KSUB + 4;          // KSUB rows (the reduction extent) are staged at a time
+    float* Dt = smem;                      // [TM (n index)][KSUB + 4 (row index)]
+    float* Xs = smem + TM * LDR;           // [KSUB rows][KO]
+    for (int idx = threadIdx.x; idx < TM * LDR; idx += NT) Dt[idx] = 0.f;
     float acc[DenseCfg<KO>::RM][8];
     dense_zero<KO>(acc);
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int qpr = n / 4;
-    const long long n_tiles = (n_rows + TM - 1) / TM;
+    const long long n_tiles = (n_rows + KSUB - 1) / KSUB;
     __syncthreads();
     for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-        const long long row0 = tile * TM;
+        const long long row0 = tile * KSUB;
         // transposed load: lane = row (conflict-free shared stores), loop over 16-byte pieces of the row
-        for (int it = warp; it < (TM / 32) * qpr; it += NT / 32) {
+        for (int it = warp; it < (KSUB / 32) * qpr; it += NT / 32) {
             const int rb = it / qpr, q = it % qpr;
             const int r = rb * 32 + lane;
             const long long g = row0 + r;
             float4 d = make_float4(0.f, 0.f, 0.f, 0.f);
             if (g < n_rows) d = ldg4(delta + g * n + 4 * q);
-            Dt[(4 * q + 0) * LDT + r] = d.x; Dt[(4 * q + 1) * LDT + r] = d.y;
-            Dt[(4 * q + 2) * LDT + r] = d.z; Dt[(4 * q + 3) * LDT + r] = d.w;
+            Dt[(4 * q + 0) * LDR + r] = d.x; Dt[(4 * q + 1) * LDR + r] = d.y;
+            Dt[(4 * q + 2) * LDR + r] = d.z; Dt[(4 * q + 3) * LDR + r] = d.w;
         }
-        load_seg_tile(Xs, KO, X.seg[0], row0, n_rows, KO);
+        load_seg_tile(Xs, KO, X.seg[0], row0, n_rows, KO, 0, KSUB);
         __syncthreads();
-        dense_acc<KO>(acc, Dt, LDT, Xs, TM);
+        dense_acc<KO>(acc, Dt, LDR, Xs, KSUB);
         __syncthreads();
     }
     using C = DenseCfg<KO>;
@@ -660,15 +671,16 @@ extern "C" int swe_mlp_layer_fwd(const swe_rows_t* X, int64_t n_rows, const floa
     if (n_rows == 0) return 0;
     SWE_DISPATCH_W(n_out, {
         auto k = mlp_layer_fwd_kernel<WW>;
-        const size_t bytes = sizeof(float) * (size_t)(TM * 132 + 128 * WW);
+        const size_t bytes = sizeof(float) * (size_t)(TM * (KSUB + 4) + KSUB * WW);
         if (int r = opt_in(k, bytes)) return r;
-        k<<<rows_grid(n_rows, bytes > 110 * 1024 ? 1 : 2), NT, bytes, (cudaStream_t)stream>>>(*X, n_rows, wt, bias, pre);
+        k<<<rows_grid(n_rows, 3), NT, bytes, (cudaStream_t)stream>>>(*X, n_rows, wt, bias, pre);
     });
     return check_launch("mlp_layer_fwd");
 }
 
-extern "C" int swe_mlp_layer_bwd_dx_grid(int64_t n_rows) { return rows_grid(n_rows, 1); }
-extern "C" int swe_mlp_layer_bwd_dw_grid(int64_t n_rows) { return rows_grid(n_rows, 1); }
+static int dw_grid(long long n_rows) { return grid_for((n_rows + KSUB - 1) / KSUB, 3); }
+extern "C" int swe_mlp_layer_bwd_dx_grid(int64_t n_rows) { return rows_grid(n_rows, 3); }
+extern "C" int swe_mlp_layer_bwd_dw_grid(int64_t n_rows) { return dw_grid(n_rows); }
 
 extern "C" int swe_mlp_layer_bwd_dx(float* dh, const float* pre, int32_t act, const float* slope, int64_t n_rows,
                                     int32_t n, const float* w, int32_t w_ld, int32_t k_off, int32_t k_valid, int32_t ko,
@@ -678,12 +690,12 @@ extern "C" int swe_mlp_layer_bwd_dx(float* dh, const float* pre, int32_t act, co
     SWE_REQUIRE(!dx || (w && w_ld >= 1 && k_off >= 0 && k_valid >= 1 && k_valid <= ko), SWE_E_INVAL,
                 "mlp_layer_bwd_dx: bad weight block");
     SWE_REQUIRE(aligned16(dh) && (!pre || aligned16(pre)) && (!dx || aligned16(dx)), SWE_E_ALIGN, "mlp_layer_bwd_dx: unaligned buffer");
-    const int grid = rows_grid(n_rows, 1);
+    const int grid = rows_grid(n_rows, 3);
     if (grid_out) *grid_out = grid;
     if (n_rows == 0) return 0;
     SWE_DISPATCH_W(ko, {
         auto k = mlp_layer_bwd_dx_kernel<WW>;
-        const size_t bytes = sizeof(float) * (size_t)(TM * (n + 4) + n * WW);
+        const size_t bytes = sizeof(float) * (size_t)(TM * (KSUB + 4) + KSUB * WW);
         if (int r = opt_in(k, bytes)) return r;
         k<<<grid, NT, bytes, (cudaStream_t)stream>>>(dh, pre, act, slope, n_rows, n, w, w_ld, k_off, k_valid, dx,
                                                       accumulate, write_delta, part);
@@ -697,11 +709,11 @@ extern "C" int swe_mlp_layer_bwd_dw(const float* delta, int64_t n_rows, int32_t 
     SWE_REQUIRE(X->n_seg == 1 && X->seg[0].width <= ko, SWE_E_INVAL, "mlp_layer_bwd_dw: needs one segment no wider than ko");
     SWE_REQUIRE(delta && part && n_rows >= 0 && n >= 4 && n <= 128 && n % 4 == 0, SWE_E_INVAL, "mlp_layer_bwd_dw: bad arguments");
     SWE_REQUIRE(aligned16(delta) && aligned16(part), SWE_E_ALIGN, "mlp_layer_bwd_dw: unaligned buffer");
-    const int grid = rows_grid(n_rows, 1);
+    const int grid = dw_grid(n_rows);
     if (grid_out) *grid_out = grid;
     SWE_DISPATCH_W(ko, {
         auto k = mlp_layer_bwd_dw_kernel<WW>;
-        const size_t bytes = sizeof(float) * (size_t)(TM * LDT + TM * WW);
+        const size_t bytes = sizeof(float) * (size_t)(TM * (KSUB + 4) + KSUB * WW);
         if (int r = opt_in(k, bytes)) return r;
         k<<<grid, NT, bytes, (cudaStream_t)stream>>>(delta, n_rows, n, *X, part);
     });
