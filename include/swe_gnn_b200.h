@@ -310,6 +310,23 @@ int swe_mlp_layer_bwd_dw(const float* delta, int64_t n_rows, int32_t n, const sw
                          float* part, int32_t* grid_out, void* stream);
 int swe_mlp_layer_bwd_dw_grid(int64_t n_rows);
 
+/* Tensor-core (tcgen05, 3xTF32 = fp32-accurate products, fp32 accumulation in TMEM) forms of the two GEMMs above
+ * for the wide edge-MLP layers; same mathematics, relative error ~1e-6 instead of exact-fp32 summation order.
+ *   dx_tc: dx[r, 0:ko) (+)= delta[r, 0:n) · W[0:n, k_off : k_off + ko)  (columns >= k_valid give 0); delta is the
+ *          finished delta (run swe_mlp_layer_bwd_dx with dx == NULL first for delta and the bias partials);
+ *          n, ko in {64, 128}; columns [0, split) go to dx0 [n_rows, split], the rest to dx1 [n_rows, ko - split]
+ *          (split == ko: dx1 unused; otherwise split == 64, ko == 128: two 64-wide blocks in one pass).
+ *   dw_tc: part[cta][seg_col0 * n + n_i * w_seg + k] = Σ_{rows of this CTA} delta[r, n_i] · X_seg[r, k] for every
+ *          segment of the provider X (widths multiples of 32, none/relu/leakyrelu/prelu on load); n == 128 with a
+ *          provider up to 256 columns wide, or n == 64 with a 128-column provider.  Reduce each segment with
+ *          swe_reduce_partials(part, grid, n * width(X), seg_col0 * n, n_out * w_seg, w_seg, ...). */
+int swe_mlp_layer_bwd_dx_tc(const float* delta, int64_t n_rows, int32_t n, const float* w, int32_t w_ld,
+                            int32_t k_off, int32_t k_valid, int32_t ko, float* dx0, int32_t accumulate0, float* dx1,
+                            int32_t accumulate1, int32_t split, void* stream);
+int swe_mlp_layer_bwd_dw_tc(const float* delta, int64_t n_rows, int32_t n, const swe_rows_t* X, float* part,
+                            int32_t* grid_out, void* stream);
+int swe_mlp_layer_bwd_dw_tc_grid(int64_t n_rows);
+
 /* out[(j / ko) * ld_out + k_off + j % ko] += Σ_{c < n_parts, in order} part[c * part_stride + item_off + j]
  * for j < n_items with (j % ko) < k_valid. */
 int swe_reduce_partials(const float* part, int32_t n_parts, int64_t part_stride, int32_t item_off, int32_t n_items,

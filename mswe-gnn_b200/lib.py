@@ -99,6 +99,9 @@ SIGNATURES = {
     "swe_mlp_layer_bwd_dx_grid": (C.c_int, [_i64]),
     "swe_mlp_layer_bwd_dw": (C.c_int, [_p, _i64, _i32, _rows, _i32, _p, _pi32, _p]),
     "swe_mlp_layer_bwd_dw_grid": (C.c_int, [_i64]),
+    "swe_mlp_layer_bwd_dx_tc": (C.c_int, [_p, _i64, _i32, _p, _i32, _i32, _i32, _i32, _p, _i32, _p, _i32, _i32, _p]),
+    "swe_mlp_layer_bwd_dw_tc": (C.c_int, [_p, _i64, _i32, _rows, _p, _pi32, _p]),
+    "swe_mlp_layer_bwd_dw_tc_grid": (C.c_int, [_i64]),
     "swe_reduce_partials": (C.c_int, [_p, _i32, _i64, _i32, _i32, _i32, _i32, _p, _i32, _i32, _p]),
     "swe_gate_norm_fwd": (C.c_int, [_p, _i32, _p, _i32, _i64, _p, _i32, _p]),
     "swe_gate_norm_bwd": (C.c_int, [_p, _p, _i32, _p, _i32, _i64, _i32, _p]),
@@ -367,6 +370,23 @@ def mlp_layer_bwd_dw(delta, n_rows, n, rows: SweRows, ko, part):
 
 def mlp_layer_bwd_dw_grid(n_rows) -> int:
     return int(load().swe_mlp_layer_bwd_dw_grid(n_rows))
+
+
+def mlp_layer_bwd_dx_tc(delta, n_rows, n, w, w_ld, k_off, k_valid, ko, dx0, acc0, dx1=None, acc1=False, split=None):
+    _check(load().swe_mlp_layer_bwd_dx_tc(_addr(delta), n_rows, n, _addr(w), w_ld, k_off, k_valid, ko, _addr(dx0), int(acc0),
+                                          _addr(dx1), int(acc1), ko if split is None else split, _stream()),
+           "swe_mlp_layer_bwd_dx_tc")
+
+
+def mlp_layer_bwd_dw_tc(delta, n_rows, n, rows: SweRows, part):
+    g = C.c_int32(0)
+    _check(load().swe_mlp_layer_bwd_dw_tc(_addr(delta), n_rows, n, C.byref(rows), _addr(part), C.byref(g), _stream()),
+           "swe_mlp_layer_bwd_dw_tc")
+    return g.value
+
+
+def mlp_layer_bwd_dw_tc_grid(n_rows) -> int:
+    return int(load().swe_mlp_layer_bwd_dw_tc_grid(n_rows))
 
 
 def reduce_partials(part, n_parts, part_stride, item_off, n_items, ko, k_valid, out, ld_out, k_off):

@@ -1,0 +1,149 @@
+"""tcgen05 forms of the two backward GEMMs of a Linear (dx = delta·W, dW = deltaᵀ·X) against fp64 torch matmuls and
+the exact-fp32 CUDA-core kernels.  3xTF32 with fp32 accumulation: ~1e-6 relative (tolerance 1e-5 of the matrix norm)."""
+import pytest
+import torch
+
+import mswe_gnn_b200  # noqa: F401
+from mswe_gnn_b200 import lib
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+
+
+def _rel(a, b):
+    return ((a.double() - b.double()).norm() / b.double().norm().clamp_min(1e-30)).item()
+
+
+def _act_code(name):
+    return lib.ACT_CODES[None if name == "none" else name]
+
+
+@pytest.mark.parametrize("n_rows", [1, 97, 128, 4000, 150_001])
+@pytest.mark.parametrize("n,ko,split", [(128, 128, 128), (128, 64, 64), (64, 128, 128), (128, 128, 64)])
+def test_dx_tc_matches_fp64(n_rows, n, ko, split):
+    g = torch.Generator(device="cpu").manual_seed(n_rows * 7 + n + ko)
+    delta = torch.randn(n_rows, n, generator=g).to(DEV)
+    w_ld = 320
+    w = (torch.randn(n, w_ld, generator=g) * 0.1).to(DEV)
+    k_off, k_valid = 64, ko
+    ref = (delta.double() @ w.double()[:, k_off:k_off + ko]).float()
+    if split == ko:
+        dx = torch.full((n_rows, ko), float("nan"), device=DEV)
+        lib.mlp_layer_bwd_dx_tc(delta, n_rows, n, w, w_ld, k_off, k_valid, ko, dx, False)
+        torch.cuda.synchronize()
+        assert _rel(dx, ref) < 1e-5
+        # accumulate: a second pass doubles it
+        lib.mlp_layer_bwd_dx_tc(delta, n_rows, n, w, w_ld, k_off, k_valid, ko, dx, True)
+        torch.cuda.synchronize()
+        assert _rel(dx, 2 * ref) < 1e-5
+    else:
+        a = torch.full((n_rows, 64), float("nan"), device=DEV)
+        b = torch.ones(n_rows, 64, device=DEV)
+        lib.mlp_layer_bwd_dx_tc(delta, n_rows, n, w, w_ld, k_off, k_valid, ko, a, False, b, True, 64)
+        torch.cuda.synchronize()
+        assert _rel(a, ref[:, :64]) < 1e-5
+        assert _rel(b, ref[:, 64:] + 1) < 1e-5
+
+
+def test_dx_tc_zero_pads_invalid_columns():
+    n_rows, n, ko = 300, 128, 64
+    delta = torch.randn(n_rows, n, device=DEV)
+    w = torch.randn(n, 100, device=DEV)
+    dx = torch.empty(n_rows, ko, device=DEV)
+    lib.mlp_layer_bwd_dx_tc(delta, n_rows, n, w, 100, 60, 40, ko, dx, False)          # only 40 valid columns
+    ref = torch.zeros(n_rows, ko, device=DEV, dtype=torch.float64)
+    ref[:, :40] = delta.double() @ w.double()[:, 60:100]
+    torch.cuda.synchronize()
+    assert _rel(dx, ref) < 1e-5
+    assert (dx[:, 40:] == 0).all()
+
+
+def _reduce(part, grid, n, widths):
+    """Sum the per-CTA partials [grid][Σ n*w] -> list of [n, w] blocks (fp64 on the host side of the test)."""
+    tot = n * sum(widths)
+    p = part[: grid * tot].view(grid, tot).double().sum(0)
+    out, c = [], 0
+    for w in widths:
+        out.append(p[c * n: c * n + n * w].view(n, w))
+        c += w
+    return out
+
+
+@pytest.mark.parametrize("n_rows", [1, 31, 32, 4097, 200_003])
+def test_dw_tc_gathered_segments(n_rows):
+    """n = 128, provider = gathered node rows (two index maps) + a dense edge block: layer 0 of the edge MLP."""
+    g = torch.Generator(device="cpu").manual_seed(n_rows)
+    n_nodes = max(n_rows // 3, 4)
+    delta = torch.randn(n_rows, 128, generator=g).to(DEV)
+    xs = torch.randn(n_nodes, 64, generator=g).to(DEV)
+    xd = torch.randn(n_nodes, 64, generator=g).to(DEV)
+    a = torch.randn(n_rows, 64, generator=g).to(DEV)
+    src = torch.randint(0, n_nodes, (n_rows,), generator=g).to(torch.int32).to(DEV)
+    dst = torch.randint(0, n_nodes, (n_rows,), generator=g).to(torch.int32).to(DEV)
+    rows = lib.make_rows([(xs, src, 64, 64, 0, None), (xs, dst, 64, 64, 0, None), (xd, src, 64, 64, 0, None),
+                          (xd, dst, 64, 64, 0, None)])
+    grid = lib.mlp_layer_bwd_dw_tc_grid(n_rows)
+    part = torch.full((grid * 128 * 256,), float("nan"), device=DEV)
+    assert lib.mlp_layer_bwd_dw_tc(delta, n_rows, 128, rows, part) == grid
+    torch.cuda.synchronize()
+    blocks = _reduce(part, grid, 128, [64, 64, 64, 64])
+    X = [xs[src.long()], xs[dst.long()], xd[src.long()], xd[dst.long()]]
+    for b, x in zip(blocks, X):
+        assert _rel(b, delta.double().t() @ x.double()) < 1e-5
+    # the remaining 64-wide block on its own
+    rows = lib.make_rows([(a, None, 64, 64, 0, None)])
+    part = torch.full((grid * 128 * 64,), float("nan"), device=DEV)
+    lib.mlp_layer_bwd_dw_tc(delta, n_rows, 128, rows, part)
+    torch.cuda.synchronize()
+    (b,) = _reduce(part, grid, 128, [64])
+    assert _rel(b, delta.double().t() @ a.double()) < 1e-5
+
+
+@pytest.mark.parametrize("n,act", [(128, "prelu"), (64, "prelu"), (64, "relu"), (128, "none")])
+def test_dw_tc_activation_on_load(n, act):
+    """X = act(pre) 128 wide (layers 1 and 2 of the edge MLP; n = 64 runs with the operand roles swapped)."""
+    n_rows = 10_007
+    g = torch.Generator(device="cpu").manual_seed(5)
+    delta = torch.randn(n_rows, n, generator=g).to(DEV)
+    pre = torch.randn(n_rows, 128, generator=g).to(DEV)
+    slope = torch.tensor([0.3], device=DEV)
+    code = _act_code(act)
+    rows = lib.make_rows([(pre, None, 128, 128, code, slope if act == "prelu" else None)])
+    grid = lib.mlp_layer_bwd_dw_tc_grid(n_rows)
+    part = torch.full((grid * n * 128,), float("nan"), device=DEV)
+    lib.mlp_layer_bwd_dw_tc(delta, n_rows, n, rows, part)
+    torch.cuda.synchronize()
+    (b,) = _reduce(part, grid, n, [128])
+    x = pre.double()
+    x = {"prelu": torch.where(x > 0, x, 0.3 * x), "relu": x.clamp_min(0), "none": x}[act]
+    assert _rel(b, delta.double().t() @ x) < 1e-5
+    # and the deterministic device-side reduction the training step uses
+    gw = torch.zeros(n, 128, device=DEV)
+    lib.reduce_partials(part, grid, n * 128, 0, n * 128, 128, 128, gw, 128, 0)
+    torch.cuda.synchronize()
+    assert _rel(gw, delta.double().t() @ x) < 1e-5
+
+
+def test_dw_tc_is_deterministic():
+    n_rows = 50_000
+    delta = torch.randn(n_rows, 128, device=DEV)
+    pre = torch.randn(n_rows, 128, device=DEV)
+    rows = lib.make_rows([(pre, None, 128, 128, 0, None)])
+    grid = lib.mlp_layer_bwd_dw_tc_grid(n_rows)
+    outs = []
+    for _ in range(2):
+        part = torch.empty(grid * 128 * 128, device=DEV)
+        lib.mlp_layer_bwd_dw_tc(delta, n_rows, 128, rows, part)
+        torch.cuda.synchronize()
+        outs.append(part.clone())
+    assert torch.equal(outs[0], outs[1])
+
+
+def test_tc_rejects_unsupported_shapes():
+    delta = torch.randn(10, 96, device=DEV)
+    rows = lib.make_rows([(delta, None, 96, 96, 0, None)])
+    part = torch.empty(96 * 96, device=DEV)
+    with pytest.raises(RuntimeError):
+        lib.mlp_layer_bwd_dw_tc(delta, 10, 96, rows, part)
+    with pytest.raises(RuntimeError):
+        lib.mlp_layer_bwd_dx_tc(delta, 10, 96, delta, 96, 0, 64, 64, part, False)
