@@ -507,7 +507,9 @@ def run_train(args):
             "gpu_launches": launches,
             "roofline": {"bound": "tensor", "kernel": dom["name"], "achieved": dom["tflops"], "peak": pk["bf16"], "unit": "TFLOP/s",
                          "frac": dom["tflops"] / pk["bf16"], "traffic": None,
-                         "peak_source": pk["hbm_src"] + " (sustained bf16; the backward GEMMs run in exact fp32 on CUDA cores this round)"},
+                         "peak_source": pk["hbm_src"] + " (sustained bf16)",
+                         "note": "algorithmic FLOPs / time of the entry point with the largest share of the step; the wide edge-MLP "
+                                 "GEMMs run as 3xTF32 on tcgen05 (fp32-accurate), the narrow ones in exact fp32 on CUDA cores"},
             "kernels": sorted(kern.values(), key=lambda r: -r["ms_per_step"])[:12],
             "cpu_baseline": cpu}
     print(json.dumps(line), flush=True)
@@ -520,7 +522,7 @@ def profile_train_kernels(step_fn):
     from mswe_gnn_b200 import lib
     records, orig = [], {}
     names = [n[4:] for n in lib.SIGNATURES if n.startswith("swe_") and hasattr(lib, n[4:]) and callable(getattr(lib, n[4:]))
-             and n[4:] not in ("mlp_layer_bwd_dx_grid", "mlp_layer_bwd_dw_grid", "gate_tc_image_bytes", "hop_tc_image_bytes", "csr_build")]
+             and n[4:] not in ("mlp_layer_bwd_dx_grid", "mlp_layer_bwd_dw_grid", "mlp_layer_bwd_dw_tc_grid", "gate_tc_image_bytes", "hop_tc_image_bytes", "csr_build")]
 
     def wrap(name):
         fn = getattr(lib, name)
@@ -536,6 +538,12 @@ def profile_train_kernels(step_fn):
                 fl = 2.0 * a[4] * a[5] * a[10]
             elif name == "mlp_layer_bwd_dw":
                 fl = 2.0 * a[1] * a[2] * a[4]
+            elif name == "mlp_layer_bwd_dx_tc":
+                fl = 2.0 * a[1] * a[2] * a[7]
+            elif name == "mlp_layer_bwd_dw_tc":
+                fl = 2.0 * a[1] * a[2] * sum(a[3].seg[j].width for j in range(a[3].n_seg))
+            elif name == "edge_gate_tc_train_fwd":
+                fl = 2.0 * a[6] * (a[8] * 128 + 128 * 128 + 128 * 64)
             records.append((name, e0, e1, fl))
             return r
         setattr(lib, name, inner)

@@ -310,6 +310,13 @@ int swe_mlp_layer_bwd_dw(const float* delta, int64_t n_rows, int32_t n, const sw
                          float* part, int32_t* grid_out, void* stream);
 int swe_mlp_layer_bwd_dw_grid(int64_t n_rows);
 
+/* swe_edge_gate_tc_fwd that also stores the pre-activations of the three edge-MLP layers (pre1, pre2: [E, 128],
+ * pre3: [E, 64]; bias included, activation not applied) — the forward of the training step for the default model. */
+int swe_edge_gate_tc_train_fwd(const float* xs, const float* xd_src, const float* xd_dst, const float* a,
+                               const int32_t* src, const int32_t* dst, int64_t n_edges, const void* image, int32_t k1,
+                               const int32_t* act3, const float* const* slope3, int32_t normalize, float* pre1,
+                               float* pre2, float* pre3, float* s_out, void* stream);
+
 /* Tensor-core (tcgen05, 3xTF32 = fp32-accurate products, fp32 accumulation in TMEM) forms of the two GEMMs above
  * for the wide edge-MLP layers; same mathematics, relative error ~1e-6 instead of exact-fp32 summation order.
  *   dx_tc: dx[r, 0:ko) (+)= delta[r, 0:n) · W[0:n, k_off : k_off + ko)  (columns >= k_valid give 0); delta is the
@@ -317,8 +324,8 @@ int swe_mlp_layer_bwd_dw_grid(int64_t n_rows);
  *          n, ko in {64, 128}; columns [0, split) go to dx0 [n_rows, split], the rest to dx1 [n_rows, ko - split]
  *          (split == ko: dx1 unused; otherwise split == 64, ko == 128: two 64-wide blocks in one pass).
  *   dw_tc: part[cta][seg_col0 * n + n_i * w_seg + k] = Σ_{rows of this CTA} delta[r, n_i] · X_seg[r, k] for every
- *          segment of the provider X (widths multiples of 32, none/relu/leakyrelu/prelu on load); n == 128 with a
- *          provider up to 256 columns wide, or n == 64 with a 128-column provider.  Reduce each segment with
+ *          segment of the provider X (widths multiples of 32, none/relu/leakyrelu/prelu on load); n in {64, 128},
+ *          provider up to 256 columns wide.  Reduce each segment with
  *          swe_reduce_partials(part, grid, n * width(X), seg_col0 * n, n_out * w_seg, w_seg, ...). */
 int swe_mlp_layer_bwd_dx_tc(const float* delta, int64_t n_rows, int32_t n, const float* w, int32_t w_ld,
                             int32_t k_off, int32_t k_valid, int32_t ko, float* dx0, int32_t accumulate0, float* dx1,

@@ -37,6 +37,28 @@ def _tile_width(n: int) -> int:
     raise NotImplementedError(f"layer width {n} exceeds the largest kernel tile (128)")
 
 
+_TC_ACTS = (ACT_CODES[None], ACT_CODES["prelu"], ACT_CODES["relu"], ACT_CODES["leakyrelu"])
+
+
+def train_gemm_backend() -> str:
+    """'tc' (tcgen05 3xTF32 backward GEMMs for the wide edge-MLP layers, default) or 'ffma'."""
+    import os
+    return os.environ.get("MSWE_TRAIN_GEMM", "tc")
+
+
+def _tc_part(name: str) -> bool:
+    """MSWE_TRAIN_TC_PARTS selects which training GEMMs of the wide edge MLP use the tensor cores (3xTF32).
+
+    Default ``dx,dw``: both backward GEMMs; the forward stays on the exact-fp32 CUDA-core kernels, so the saved
+    pre-activations — and with them every PReLU/ReLU derivative mask — are those of the fp32 reference and the
+    gradients match the oracle to ~1e-5.  ``fwd,dx,dw`` also runs the forward on the tensor cores (the inference gate
+    kernel storing its pre-activations): 15 % faster per step, forward values within 3e-6, but the ~1e-6 relative
+    perturbation flips the derivative mask of the few pre-activations that close to the activation's kink, which
+    shows up as ~1e-3 relative L2 in the weight gradients (each flipped entry is an O(1) change of one summand)."""
+    import os
+    return train_gemm_backend() == "tc" and name in os.environ.get("MSWE_TRAIN_TC_PARTS", "dx,dw").split(",")
+
+
 def _r4(k: int) -> int:
     return (k + 3) // 4 * 4
 
@@ -164,10 +186,16 @@ class TrainMLP:
                  dx_accumulate=None):
         """Returns the list of first-layer input gradients (one [R, tile] tensor per block, None
         where ``need_dx`` is False).  ``dx_out[j]`` / ``dx_accumulate[j]`` let a block's gradient be
-        accumulated into an existing [R, tile] tensor."""
+        accumulated into an existing [R, tile] tensor.
+
+        Wide layers (64/128 outputs, inputs in 32-column multiples: the edge MLP of the default
+        model) run their two GEMMs on the tensor cores (``swe_mlp_layer_bwd_dx_tc/_dw_tc``);
+        everything else stays on the exact-fp32 CUDA-core kernels.  ``MSWE_TRAIN_GEMM=ffma``
+        forces the latter."""
         dev = dh.device
         if n_rows == 0:
             return [None] * len(self.blocks)
+        tc_dx_on, tc_dw_on = _tc_part("dx"), _tc_part("dw")
         for li in range(self.L - 1, -1, -1):
             lin = self.linears[li]
             n_out, k_in = lin.weight.shape
@@ -179,35 +207,87 @@ class TrainMLP:
             if li > 0:
                 ko = self.n_pad[li - 1]
                 dx = torch.empty(max(n_rows, 1), ko, dtype=torch.float32, device=dev)
-                lib.mlp_layer_bwd_dx(dh, pres[li], act, slope, n_rows, n, self.w_rm[li], self.w_rm[li].shape[1], 0, ko, ko,
-                                     dx, False, True, part)
-                rows = lib.make_rows([(pres[li - 1], None, ko, ko, self.act_code(li - 1), self.slope(li - 1))])
-                self._dw(dh, n_rows, n, rows, ko, gw, n_out, k_in, 0, k_in, dev)
+                prev_act = self.act_code(li - 1)
+                tc = tc_dx_on and n in (64, 128) and ko in (64, 128)
+                tc_dw = tc_dw_on and prev_act in _TC_ACTS and (n == 128 or (n == 64 and ko == 128))
+                if tc:
+                    # delta (in place) + bias / slope partials on CUDA cores (element-wise), the GEMM on tensor cores
+                    lib.mlp_layer_bwd_dx(dh, pres[li], act, slope, n_rows, n, self.w_rm[li], self.w_rm[li].shape[1], 0, 16, 16,
+                                         None, False, True, part)
+                    lib.mlp_layer_bwd_dx_tc(dh, n_rows, n, self.w_rm[li], self.w_rm[li].shape[1], 0, ko, ko, dx, False)
+                else:
+                    lib.mlp_layer_bwd_dx(dh, pres[li], act, slope, n_rows, n, self.w_rm[li], self.w_rm[li].shape[1], 0, ko, ko,
+                                         dx, False, True, part)
+                rows = lib.make_rows([(pres[li - 1], None, ko, ko, prev_act, self.slope(li - 1))])
+                if tc_dw:
+                    self._dw_tc(dh, n_rows, n, rows, [(0, ko, 0, k_in)], ko, gw, n_out, k_in, dev)
+                else:
+                    self._dw(dh, n_rows, n, rows, ko, gw, n_out, k_in, 0, k_in, dev)
                 results = None
             else:
-                results = []
-                c = 0
-                first = True
-                for j, ((off, wd), bp, seg) in enumerate(zip(self.blocks, self.block_pad, first_segs)):
-                    ko = _tile_width(bp)
-                    want = need_dx[j]
-                    dx = None
-                    acc = False
-                    if want:
+                nb = len(self.blocks)
+                wide = n == 128 and all(bp == wd and wd in (64, 128) for (_, wd), bp in zip(self.blocks, self.block_pad))
+                tc, tc_dw = tc_dx_on and wide, tc_dw_on and wide
+                results = [None] * nb
+                outs, accs = [None] * nb, [False] * nb
+                for j in range(nb):
+                    if need_dx[j]:
                         if dx_out is not None and dx_out[j] is not None:
-                            dx, acc = dx_out[j], bool(dx_accumulate[j])
+                            outs[j], accs[j] = dx_out[j], bool(dx_accumulate[j])
                         else:
-                            dx = torch.empty(max(n_rows, 1), ko, dtype=torch.float32, device=dev)
-                    if first or want:
-                        lib.mlp_layer_bwd_dx(dh, pres[0] if first else None, act if first else 0, slope if first else None,
-                                             n_rows, n, self.w_rm[0], self.w_rm[0].shape[1], c, bp, ko, dx, acc, True,
-                                             part if first else None)
-                        first = False
-                    b, i, ld, w = seg
-                    rows = lib.make_rows([(b, i, ld, w, 0, None)])
-                    self._dw(dh, n_rows, n, rows, ko, gw, n_out, k_in, off, wd, dev)
-                    results.append(dx)
-                    c += bp
+                            outs[j] = torch.empty(max(n_rows, 1), _tile_width(self.block_pad[j]), dtype=torch.float32,
+                                                  device=dev)
+                        results[j] = outs[j]
+                col0 = [0] * nb
+                for j in range(1, nb):
+                    col0[j] = col0[j - 1] + self.block_pad[j - 1]
+                ld0 = self.w_rm[0].shape[1]
+                if tc or tc_dw:
+                    lib.mlp_layer_bwd_dx(dh, pres[0], act, slope, n_rows, n, self.w_rm[0], ld0, 0, 16, 16, None, False, True,
+                                         part)
+                if tc:
+                    # input gradients: two 64-wide neighbours per pass where possible
+                    j = 0
+                    while j < nb:
+                        if outs[j] is None:
+                            j += 1
+                            continue
+                        wj = self.block_pad[j]
+                        if wj == 64 and j + 1 < nb and outs[j + 1] is not None and self.block_pad[j + 1] == 64:
+                            lib.mlp_layer_bwd_dx_tc(dh, n_rows, n, self.w_rm[0], ld0, col0[j], 128, 128, outs[j], accs[j],
+                                                    outs[j + 1], accs[j + 1], 64)
+                            j += 2
+                        else:
+                            lib.mlp_layer_bwd_dx_tc(dh, n_rows, n, self.w_rm[0], ld0, col0[j], wj, wj, outs[j], accs[j])
+                            j += 1
+                else:
+                    first = not tc_dw                       # (delta already finished when the dW side runs on tensor cores)
+                    for j in range(nb):
+                        bp = self.block_pad[j]
+                        if first or outs[j] is not None:
+                            lib.mlp_layer_bwd_dx(dh, pres[0] if first else None, act if first else 0, slope if first else None,
+                                                 n_rows, n, self.w_rm[0], ld0, col0[j], bp, _tile_width(bp), outs[j], accs[j],
+                                                 True, part if first else None)
+                            first = False
+                if tc_dw:
+                    # weight gradients: provider segments in groups of up to 256 columns
+                    j = 0
+                    while j < nb:
+                        grp, wsum = [], 0
+                        while j < nb and wsum + self.block_pad[j] <= 256:
+                            grp.append(j); wsum += self.block_pad[j]; j += 1
+                        rows = lib.make_rows([(first_segs[q][0], first_segs[q][1], first_segs[q][2], first_segs[q][3], 0, None)
+                                              for q in grp])
+                        items, c = [], 0
+                        for q in grp:
+                            off, wd = self.blocks[q]
+                            items.append((c, wd, off, wd)); c += wd
+                        self._dw_tc(dh, n_rows, n, rows, items, wsum, gw, n_out, k_in, dev)
+                else:
+                    for (off, wd), bp, seg in zip(self.blocks, self.block_pad, first_segs):
+                        b, i, ld, w = seg
+                        rows = lib.make_rows([(b, i, ld, w, 0, None)])
+                        self._dw(dh, n_rows, n, rows, _tile_width(bp), gw, n_out, k_in, off, wd, dev)
             # bias and PReLU slope gradients from the partials of the (first) dx call
             if lin.bias is not None:
                 lib.reduce_partials(part, grid, n + 1, 0, n_out, n_out, n_out, sink.of(lin.bias), n_out, 0)
@@ -216,6 +296,16 @@ class TrainMLP:
             if li > 0:
                 dh = dx
         return results
+
+    @staticmethod
+    def _dw_tc(delta, n_rows, n, rows, items, width, gw, n_out, k_in, dev):
+        """Tensor-core weight gradient of one provider group; ``items``: (column offset inside the group, segment
+        width, first column in the Linear weight, valid columns) per segment."""
+        grid = lib.mlp_layer_bwd_dw_tc_grid(n_rows)
+        part = torch.empty(max(grid, 1) * n * width, dtype=torch.float32, device=dev)
+        g = lib.mlp_layer_bwd_dw_tc(delta, n_rows, n, rows, part)
+        for c0, w, k_off, k_valid in items:
+            lib.reduce_partials(part, g, n * width, c0 * n, n_out * w, w, k_valid, gw, k_in, k_off)
 
     @staticmethod
     def _dw(delta, n_rows, n, rows, ko, gw, n_out, k_in, k_off, k_valid, dev):
@@ -273,10 +363,21 @@ def swegnn_forward_train(mod, es, xs: Arr, xd_src: Arr, xd_dst: Optional[Arr], a
         blocks.append((4 * F, F)); segs.append((a, None, F, F)); c.seg_kind.append("a")
     c.mlp = TrainMLP(mod.edge_mlp, blocks)
     c.segs = segs
-    c.pres = c.mlp.forward(segs, E, dev)
     c.s = torch.empty(max(E, 1), F, dtype=torch.float32, device=dev)
-    last = c.mlp.L - 1
-    lib.gate_norm_fwd(c.pres[last], c.mlp.act_code(last), c.mlp.slope(last), mod.normalize, E, c.s, F)
+    gate_tc = mod.launcher().tc if _tc_part("fwd") else None
+    if gate_tc is not None and all(c.mlp.act_code(i) in _TC_ACTS for i in range(3)):
+        # the default model (F = 64, 5F|4F -> 2F -> 2F -> F): the inference gate kernel on the tensor cores, in the
+        # variant that also stores the three pre-activations the backward needs
+        codes, slopes = gate_tc.acts_and_slopes()
+        c.pres = [torch.empty(max(E, 1), w, dtype=torch.float32, device=dev) for w in (2 * F, 2 * F, F)]
+        lib.edge_gate_tc_train_fwd(xs.addr, xd_src.addr, None if xd_dst is None else xd_dst.addr,
+                                   a if mod.edge_features > 0 else None, es.src, es.dst, E, gate_tc.image(),
+                                   gate_tc.linears[0].weight.shape[1], codes, slopes, mod.normalize, c.pres[0], c.pres[1],
+                                   c.pres[2], c.s)
+    else:
+        c.pres = c.mlp.forward(segs, E, dev)
+        last = c.mlp.L - 1
+        lib.gate_norm_fwd(c.pres[last], c.mlp.act_code(last), c.mlp.slope(last), mod.normalize, E, c.s, F)
     K = mod.K
     lo, n = es.dst_lo, es.n_dst
     c.o, c.agg = [], []

@@ -98,6 +98,7 @@ struct GateTcParams {
     int n_seg; int segs[5];
     const float* p_src; const float* p_dst;      // MODE 1: [*, 128] partial tables indexed by plan id
     float* p_out; int row_lo;                    // MODE 2: output table rows [row_lo, row_lo + n_edges)
+    float* pre_out[3];                           // TRAIN: pre-activations of the three layers ([E,128], [E,128], [E,64])
 };
 
 __device__ __forceinline__ int l1_chunk_segment(const GateTcParams& p, int i) {
@@ -131,7 +132,9 @@ __device__ __forceinline__ float leaky_slope(int act, const float* slope_p) {
 // depend on ONE node, so they are evaluated once per node (MODE 2 launches of this kernel, 2·128² MAC per node)
 // instead of once per edge (4·64·128 MAC per edge, ~3 edges per node); the per-edge layer-0 work shrinks from 10
 // K-chunks to the 2 of a_e (none for un-pool calls), and epilogue 1 adds P_src[r] + P_dst[c] in fp32.
-template <bool GENERIC, int MODE>
+// TRAIN: the forward of the training step — additionally stores every layer's pre-activation (what the backward
+// kernels differentiate through), otherwise identical.
+template <bool GENERIC, int MODE, bool TRAIN = false>
 __global__ void __launch_bounds__(N_THREADS, 1) edge_gate_tc_kernel(const __grid_constant__ GateTcParams p) {
     extern __shared__ unsigned char smem_raw[];
     // 1 KB alignment by OFFSETTING the shared array: integer arithmetic on the pointer value loses the address
@@ -293,6 +296,18 @@ __global__ void __launch_bounds__(N_THREADS, 1) edge_gate_tc_kernel(const __grid
 #pragma unroll
                     for (int j = 0; j < 32; ++j) d[j] = __uint_as_float(v[j]);
                 }
+                if (TRAIN) {
+                    const long long e = ((long long)blockIdx.x + (long long)i * gridDim.x) * TILE_ROWS + row;
+                    if (e < p.n_edges) {
+                        float* d = p.pre_out[layer] + e * GH + hf * 64 + cb * 32;
+#pragma unroll
+                        for (int j = 0; j < 32; j += 4) {
+                            const float4 b4 = *reinterpret_cast<const float4*>(bias + cb * 32 + j);
+                            stg4(d + j, make_float4(__uint_as_float(v[j]) + b4.x, __uint_as_float(v[j + 1]) + b4.y,
+                                                    __uint_as_float(v[j + 2]) + b4.z, __uint_as_float(v[j + 3]) + b4.w));
+                        }
+                    }
+                }
                 uint32_t lo[32];
 #pragma unroll
                 for (int j = 0; j < 32; j += 4) {
@@ -328,6 +343,20 @@ __global__ void __launch_bounds__(N_THREADS, 1) edge_gate_tc_kernel(const __grid
                 for (int j = 0; j < 32; ++j) { d[j] = __uint_as_float(v0[j]); d[32 + j] = __uint_as_float(v1[j]); }
             }
             const float* bias = s_bias + 256;
+            if (TRAIN) {
+                const long long e = ((long long)blockIdx.x + (long long)i * gridDim.x) * TILE_ROWS + row;
+                if (e < p.n_edges) {
+                    float* d = p.pre_out[2] + e * GF;
+#pragma unroll
+                    for (int j = 0; j < 32; j += 4) {
+                        const float4 b0 = *reinterpret_cast<const float4*>(bias + j), b1 = *reinterpret_cast<const float4*>(bias + 32 + j);
+                        stg4(d + j, make_float4(__uint_as_float(v0[j]) + b0.x, __uint_as_float(v0[j + 1]) + b0.y,
+                                                __uint_as_float(v0[j + 2]) + b0.z, __uint_as_float(v0[j + 3]) + b0.w));
+                        stg4(d + 32 + j, make_float4(__uint_as_float(v1[j]) + b1.x, __uint_as_float(v1[j + 1]) + b1.y,
+                                                     __uint_as_float(v1[j + 2]) + b1.z, __uint_as_float(v1[j + 3]) + b1.w));
+                    }
+                }
+            }
             float ss = 0.f;
 #pragma unroll
             for (int j = 0; j < 32; j += 4) {
@@ -560,7 +589,8 @@ static int gate_tc_launch(const tc::GateTcParams& p_in, int mode, void* stream) 
         for (int i = 0; i < 3; ++i)
             generic |= !(p.act[i] == SWE_ACT_NONE || p.act[i] == SWE_ACT_PRELU || p.act[i] == SWE_ACT_RELU || p.act[i] == SWE_ACT_LEAKYRELU);
     void (*kern)(const tc::GateTcParams) = nullptr;
-    if (mode == 0) kern = generic ? tc::edge_gate_tc_kernel<true, 0> : tc::edge_gate_tc_kernel<false, 0>;
+    if (mode == 0 && p.pre_out[0]) kern = generic ? tc::edge_gate_tc_kernel<true, 0, true> : tc::edge_gate_tc_kernel<false, 0, true>;
+    else if (mode == 0) kern = generic ? tc::edge_gate_tc_kernel<true, 0> : tc::edge_gate_tc_kernel<false, 0>;
     else if (mode == 1) kern = generic ? tc::edge_gate_tc_kernel<true, 1> : tc::edge_gate_tc_kernel<false, 1>;
     else kern = tc::edge_gate_tc_kernel<false, 2>;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc::GATE_TC_SMEM);
@@ -612,6 +642,32 @@ extern "C" int swe_edge_gate_tc_fwd_traced(const float* xs, const float* xd_src,
         if (sg < 3 || (sg == 3 && xd_dst) || (sg == 4 && a)) p.segs[p.n_seg++] = sg;
     if (int r = gate_tc_launch(p, 0, stream)) return r;
     return check_launch("edge_gate_tc_fwd");
+}
+
+// forward of the training step: s_ij plus the three pre-activations the backward differentiates through
+extern "C" int swe_edge_gate_tc_train_fwd(const float* xs, const float* xd_src, const float* xd_dst, const float* a,
+                                          const int32_t* src, const int32_t* dst, int64_t n_edges, const void* image,
+                                          int32_t k1, const int32_t* act3, const float* const* slope3, int32_t normalize,
+                                          float* pre1, float* pre2, float* pre3, float* s_out, void* stream) {
+    SWE_REQUIRE(xs && xd_src && src && dst && s_out && image && act3 && slope3 && pre1 && pre2 && pre3 && n_edges >= 0,
+                SWE_E_INVAL, "edge_gate_tc_train: bad arguments");
+    SWE_REQUIRE(aligned16(xs) && aligned16(xd_src) && aligned16(s_out) && aligned16(image) && (!a || aligned16(a)) &&
+                (!xd_dst || aligned16(xd_dst)) && aligned16(pre1) && aligned16(pre2) && aligned16(pre3), SWE_E_ALIGN,
+                "edge_gate_tc_train: unaligned buffer");
+    SWE_REQUIRE(k1 == (a ? 5 : 4) * tc::GF, SWE_E_UNSUPP, "edge_gate_tc_train: k1=%d does not match the inputs", k1);
+    if (n_edges == 0) return 0;
+    tc::GateTcParams p;
+    memset(&p, 0, sizeof(p));
+    p.xs = xs; p.xd_src = xd_src; p.xd_dst = xd_dst; p.a = a; p.src = src; p.dst = dst; p.n_edges = n_edges;
+    p.img = (const unsigned char*)image; p.n_l1_img = k1 / tc::KC;
+    for (int i = 0; i < 3; ++i) { p.act[i] = act3[i]; p.slope[i] = slope3[i]; }
+    p.normalize = normalize; p.s_out = s_out;
+    p.pre_out[0] = pre1; p.pre_out[1] = pre2; p.pre_out[2] = pre3;
+    p.n_seg = 0;
+    for (int sg = 0; sg < 5; ++sg)
+        if (sg < 3 || (sg == 3 && xd_dst) || (sg == 4 && a)) p.segs[p.n_seg++] = sg;
+    if (int r = gate_tc_launch(p, 0, stream)) return r;
+    return check_launch("edge_gate_tc_train_fwd");
 }
 
 // ---------------------------------------------------------------------------------------------

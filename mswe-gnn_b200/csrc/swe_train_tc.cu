@@ -102,8 +102,8 @@ struct DwBarriers { uint64_t full[DW_STAGES], empty[DW_STAGES], d_full; };
 constexpr size_t DW_TC_SMEM = 1024 + (size_t)DW_STAGES * DW_STAGE_BYTES + 2 * sizeof(ProvS) + sizeof(DwBarriers) + 32;
 
 struct DwTcParams {
-    swe_rows_t P, Q;            // P: total width 128; Q: total width qw (multiple of 32, <= 256)
-    int qw;
+    swe_rows_t P, Q;            // P: total width pw (64 or 128); Q: total width qw (multiple of 32, <= 256)
+    int pw, qw;
     long long n_rows;
     int n;                      // rows of dW (= width of delta)
     int swapped;                // 0: P = delta, Q = X;  1: P = X, Q = delta
@@ -131,25 +131,35 @@ __global__ void __launch_bounds__(TR_THREADS, 1) mlp_dw_tc_kernel(const __grid_c
         resolve_segs(p.P, prP);
         resolve_segs(p.Q, prQ);
     }
+    const int qw = p.qw, pw = p.pw;
+    if (pw < 128) {
+        // a 64-wide P occupies two of the four 32-feature panels; the MMA still reads M = 128: zero the rest once
+        for (int st = 0; st < DW_STAGES; ++st)
+            for (int half = 0; half < 2; ++half) {
+                float4* z = reinterpret_cast<float4*>(ring + (size_t)st * DW_STAGE_BYTES + half * DW_P_BYTES + 2 * DW_PANEL);
+                for (int i = threadIdx.x; i < 2 * DW_PANEL / 16; i += TR_THREADS) z[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+        fence_proxy_async_smem();
+    }
     if (warp == 8) tmem_alloc(tmem_holder, 256);
     tc_fence_before_sync();
     __syncthreads();
     tc_fence_after_sync();
     const uint32_t tmem_base = *tmem_holder;
-    const int qw = p.qw;
 
     if (warp < 8) {
         const int t = threadIdx.x;
         const int nq = qw / 32;                                  // Q chunks of 16 B per thread and stage
         const int qpr = qw / 4;                                  // 16-B chunks per Q row
+        const int npc = pw / 32, ppr = pw / 4;                   // the same for P
         float4 cp[4], cq[8], np[4], nq4[8];
         auto issue = [&](int i, float4 (&vp)[4], float4 (&vq)[8]) {
             const long long row0 = ((long long)blockIdx.x + (long long)i * gridDim.x) * DW_RS;
             const float* ap[4]; const float* aq[8];
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
-                const int q = t + TR_ROW_THREADS * j;
-                ap[j] = provider_addr(prP, row0 + (q >> 5), p.n_rows, (q & 31) * 4);
+                const int q = t + TR_ROW_THREADS * (j < npc ? j : 0);
+                ap[j] = provider_addr(prP, row0 + q / ppr, p.n_rows, (q % ppr) * 4);
             }
 #pragma unroll
             for (int j = 0; j < 8; ++j) {
@@ -157,7 +167,8 @@ __global__ void __launch_bounds__(TR_THREADS, 1) mlp_dw_tc_kernel(const __grid_c
                 aq[j] = provider_addr(prQ, row0 + q / qpr, p.n_rows, (q % qpr) * 4);
             }
 #pragma unroll
-            for (int j = 0; j < 4; ++j) vp[j] = ldg4(ap[j]);
+            for (int j = 0; j < 4; ++j)
+                if (j < npc) vp[j] = ldg4(ap[j]);
 #pragma unroll
             for (int j = 0; j < 8; ++j)
                 if (j < nq) vq[j] = ldg4(aq[j]);
@@ -168,20 +179,19 @@ __global__ void __launch_bounds__(TR_THREADS, 1) mlp_dw_tc_kernel(const __grid_c
 #pragma unroll
             for (int j = 0; j < 8; ++j) cq[j] = nq4[j] = make_float4(1.f, 2.f, 3.f, 4.f);
         }
-        if (n_my > 0 && !(p.debug & 2)) issue(0, cp, cq);
-#pragma unroll 1
-        for (int i = 0; i < n_my; ++i) {
-            if (i + 1 < n_my && !(p.debug & 2)) issue(i + 1, np, nq4);
+        auto store = [&](int i, const float4 (&vp)[4], const float4 (&vq)[8]) {
             const uint32_t slot = i % DW_STAGES;
             mbar_wait(&bar->empty[slot], ((i / DW_STAGES) & 1) ^ 1);
             unsigned char* st = ring + (size_t)slot * DW_STAGE_BYTES;
             const long long row0 = ((long long)blockIdx.x + (long long)i * gridDim.x) * DW_RS;
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
-                const int q = t + TR_ROW_THREADS * j;
-                const int row = q >> 5, ch = q & 31;
-                unsigned char* d = st + (ch >> 3) * DW_PANEL + mn32b_offset(row, ch & 7);
-                split_store4(d, d + DW_P_BYTES, provider_finish(prP, cp[j], row0 + row, p.n_rows, ch * 4));
+                if (j < npc) {
+                    const int q = t + TR_ROW_THREADS * j;
+                    const int row = q / ppr, ch = q % ppr;
+                    unsigned char* d = st + (ch >> 3) * DW_PANEL + mn32b_offset(row, ch & 7);
+                    split_store4(d, d + DW_P_BYTES, provider_finish(prP, vp[j], row0 + row, p.n_rows, ch * 4));
+                }
             }
 #pragma unroll
             for (int j = 0; j < 8; ++j) {
@@ -189,15 +199,25 @@ __global__ void __launch_bounds__(TR_THREADS, 1) mlp_dw_tc_kernel(const __grid_c
                     const int q = t + TR_ROW_THREADS * j;
                     const int row = q / qpr, ch = q % qpr;
                     unsigned char* d = st + 2 * DW_P_BYTES + (ch >> 3) * DW_PANEL + mn32b_offset(row, ch & 7);
-                    split_store4(d, d + DW_Q_BYTES, provider_finish(prQ, cq[j], row0 + row, p.n_rows, ch * 4));
+                    split_store4(d, d + DW_Q_BYTES, provider_finish(prQ, vq[j], row0 + row, p.n_rows, ch * 4));
                 }
             }
             fence_proxy_async_smem();
             mbar_arrive(&bar->full[slot]);
-#pragma unroll
-            for (int j = 0; j < 4; ++j) cp[j] = np[j];
-#pragma unroll
-            for (int j = 0; j < 8; ++j) cq[j] = nq4[j];
+        };
+        // two register sets, two stages of loads in flight: a set is re-issued (stage i + 2) as soon as it has
+        // been stored (stage i), while the other set's loads (stage i + 1) are still on their way
+        const bool ld = !(p.debug & 2);
+        if (ld && n_my > 0) issue(0, cp, cq);
+        if (ld && n_my > 1) issue(1, np, nq4);
+#pragma unroll 1
+        for (int i = 0; i < n_my; i += 2) {
+            store(i, cp, cq);
+            if (ld && i + 2 < n_my) issue(i + 2, cp, cq);
+            if (i + 1 < n_my) {
+                store(i + 1, np, nq4);
+                if (ld && i + 3 < n_my) issue(i + 3, np, nq4);
+            }
         }
         // ---- epilogue: TMEM lane m = feature of P, columns = features of Q -> per-CTA partial of dW
         if (n_my > 0) {
@@ -207,7 +227,7 @@ __global__ void __launch_bounds__(TR_THREADS, 1) mlp_dw_tc_kernel(const __grid_c
             const int m = qd * 32 + lane;
             const uint32_t lane_addr = tmem_base + ((uint32_t)(qd * 32) << 16);
             float* my = p.part + (long long)blockIdx.x * p.n * (p.swapped ? 128 : qw);
-            for (int pc = hf; pc < qw / 32; pc += 2) {
+            for (int pc = hf; pc < qw / 32 && m < pw; pc += 2) {
                 uint32_t v[32];
                 tmem_ld32(lane_addr + pc * 32, v);
                 tmem_wait_ld();
@@ -444,7 +464,7 @@ extern "C" int swe_mlp_layer_bwd_dw_tc(const float* delta, int64_t n_rows, int32
     SWE_REQUIRE(aligned16(delta) && aligned16(part), SWE_E_ALIGN, "mlp_layer_bwd_dw_tc: unaligned buffer");
     const int xw = provider_width_tc(X);
     SWE_REQUIRE(xw > 0, SWE_E_UNSUPP, "mlp_layer_bwd_dw_tc: provider segments must be 32-column multiples with a leaky-family activation");
-    SWE_REQUIRE((n == 128 && xw <= 256) || (n == 64 && xw == 128), SWE_E_UNSUPP,
+    SWE_REQUIRE((n == 128 || n == 64) && xw <= 256, SWE_E_UNSUPP,
                 "mlp_layer_bwd_dw_tc: unsupported shape n=%d, provider width %d", n, xw);
     if (grid_out) *grid_out = 0;
     if (n_rows == 0) return 0;
@@ -454,9 +474,10 @@ extern "C" int swe_mlp_layer_bwd_dw_tc(const float* delta, int64_t n_rows, int32
     memset(&D, 0, sizeof(D));
     D.n_seg = 1; D.seg[0].base = delta; D.seg[0].idx = nullptr; D.seg[0].slope = nullptr; D.seg[0].ld = n; D.seg[0].width = n;
     D.seg[0].act = SWE_ACT_NONE;
-    p.swapped = n == 64;
+    p.swapped = n == 64 && xw == 128;          // keep M = 128 fully used
     p.P = p.swapped ? *X : D;
     p.Q = p.swapped ? D : *X;
+    p.pw = p.swapped ? xw : n;
     p.qw = p.swapped ? n : xw;
     p.n_rows = n_rows; p.n = n; p.part = part; p.debug = g_train_tc_debug;
     cudaError_t e = cudaFuncSetAttribute(tc::mlp_dw_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc::DW_TC_SMEM);

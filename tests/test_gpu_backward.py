@@ -205,3 +205,25 @@ def test_training_step_on_a_batch_vs_oracle():
         if dt == torch.float64:
             assert abs(float(loss) - float(l.detach())) <= 2e-5 * max(1.0, abs(float(l.detach())))
     _check_grads(ours, refs[0], refs[1])
+
+
+def test_training_step_with_tensor_core_forward_opt_in(monkeypatch):
+    """MSWE_TRAIN_TC_PARTS=fwd,dx,dw: the forward of the edge MLP also runs as 3xTF32 on the tensor cores.  The loss
+    stays within 2e-5; the gradients are only required to agree to 2e-2 relative L2, because a ~1e-6 perturbation of
+    a pre-activation that lies that close to the PReLU kink flips its derivative (an O(1) change of one summand of
+    the weight gradient; with the exact-fp32 forward, the default, the same comparison holds to 2e-4)."""
+    monkeypatch.setenv("MSWE_TRAIN_TC_PARTS", "fwd,dx,dw")
+    ctor = dict(num_node_features=8, num_edge_features=1, num_scales=4, previous_t=3, **REF_CONFIG_MODELS)
+    data = make_tri_mesh(16, 16, 4, rollout_steps=1, seed=5)
+    import test_gpu_backward as me
+    orig = me._check_grads
+    monkeypatch.setattr(me, "_check_grads", lambda a, b, c: orig(a, b, c, floor=2e-2))
+    _train_compare("MSGNN", ctor, data, 1)
+
+
+def test_training_step_exact_fp32_path(monkeypatch):
+    """MSWE_TRAIN_GEMM=ffma: every training GEMM on the exact-fp32 CUDA-core kernels."""
+    monkeypatch.setenv("MSWE_TRAIN_GEMM", "ffma")
+    ctor = dict(num_node_features=8, num_edge_features=1, num_scales=4, previous_t=3, **REF_CONFIG_MODELS)
+    data = make_tri_mesh(16, 16, 4, rollout_steps=1, seed=5)
+    _train_compare("MSGNN", ctor, data, 1)

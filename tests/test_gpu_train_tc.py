@@ -99,27 +99,29 @@ def test_dw_tc_gathered_segments(n_rows):
     assert _rel(b, delta.double().t() @ a.double()) < 1e-5
 
 
-@pytest.mark.parametrize("n,act", [(128, "prelu"), (64, "prelu"), (64, "relu"), (128, "none")])
-def test_dw_tc_activation_on_load(n, act):
-    """X = act(pre) 128 wide (layers 1 and 2 of the edge MLP; n = 64 runs with the operand roles swapped)."""
+@pytest.mark.parametrize("n,act,xw", [(128, "prelu", 128), (64, "prelu", 128), (64, "relu", 128), (128, "none", 128),
+                                      (64, "prelu", 64), (64, "none", 192)])
+def test_dw_tc_activation_on_load(n, act, xw):
+    """X = act(pre) (layers 1 and 2 of the edge MLP; n = 64 against 128 columns runs with the operand roles
+    swapped, n = 64 otherwise as a zero-padded 128-row operand)."""
     n_rows = 10_007
     g = torch.Generator(device="cpu").manual_seed(5)
     delta = torch.randn(n_rows, n, generator=g).to(DEV)
-    pre = torch.randn(n_rows, 128, generator=g).to(DEV)
+    pre = torch.randn(n_rows, xw, generator=g).to(DEV)
     slope = torch.tensor([0.3], device=DEV)
     code = _act_code(act)
-    rows = lib.make_rows([(pre, None, 128, 128, code, slope if act == "prelu" else None)])
+    rows = lib.make_rows([(pre, None, xw, xw, code, slope if act == "prelu" else None)])
     grid = lib.mlp_layer_bwd_dw_tc_grid(n_rows)
-    part = torch.full((grid * n * 128,), float("nan"), device=DEV)
+    part = torch.full((grid * n * xw,), float("nan"), device=DEV)
     lib.mlp_layer_bwd_dw_tc(delta, n_rows, n, rows, part)
     torch.cuda.synchronize()
-    (b,) = _reduce(part, grid, n, [128])
+    (b,) = _reduce(part, grid, n, [xw])
     x = pre.double()
     x = {"prelu": torch.where(x > 0, x, 0.3 * x), "relu": x.clamp_min(0), "none": x}[act]
     assert _rel(b, delta.double().t() @ x) < 1e-5
     # and the deterministic device-side reduction the training step uses
-    gw = torch.zeros(n, 128, device=DEV)
-    lib.reduce_partials(part, grid, n * 128, 0, n * 128, 128, 128, gw, 128, 0)
+    gw = torch.zeros(n, xw, device=DEV)
+    lib.reduce_partials(part, grid, n * xw, 0, n * xw, xw, xw, gw, xw, 0)
     torch.cuda.synchronize()
     assert _rel(gw, delta.double().t() @ x) < 1e-5
 
