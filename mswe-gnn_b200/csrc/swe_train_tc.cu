@@ -94,6 +94,8 @@ __device__ __forceinline__ void split_store4(unsigned char* hi_p, unsigned char*
 constexpr int DW_RS = 32;                       // rows per stage = 4 MMA K-steps
 constexpr int DW_PANEL = DW_RS * 128;           // bytes of a [32 rows x 32 features] panel
 constexpr int DW_STAGES = 2;
+constexpr int DW_ROW_THREADS = 512;             // warps 0-15: staging + epilogue (the staging is instruction/latency bound)
+constexpr int DW_THREADS = DW_ROW_THREADS + 32; // + warp 16: MMA issuer
 constexpr int DW_P_BYTES = 4 * DW_PANEL;        // 128 features (hi or lo)
 constexpr int DW_Q_BYTES = 8 * DW_PANEL;        // 256 features (hi or lo)
 constexpr int DW_STAGE_BYTES = 2 * DW_P_BYTES + 2 * DW_Q_BYTES;      // 96 KB
@@ -111,7 +113,7 @@ struct DwTcParams {
     int debug;                  // bit 0: skip the MMAs, bit 1: skip the global loads (profiling aid)
 };
 
-__global__ void __launch_bounds__(TR_THREADS, 1) mlp_dw_tc_kernel(const __grid_constant__ DwTcParams p) {
+__global__ void __launch_bounds__(DW_THREADS, 1) mlp_dw_tc_kernel(const __grid_constant__ DwTcParams p) {
     extern __shared__ unsigned char smem_raw[];
     unsigned char* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
     unsigned char* ring = smem;
@@ -125,7 +127,7 @@ __global__ void __launch_bounds__(TR_THREADS, 1) mlp_dw_tc_kernel(const __grid_c
     const int n_my = (int)((n_stg_all - blockIdx.x + gridDim.x - 1) / gridDim.x);
 
     if (threadIdx.x == 0) {
-        for (int i = 0; i < DW_STAGES; ++i) { mbar_init(&bar->full[i], TR_ROW_THREADS); mbar_init(&bar->empty[i], 1); }
+        for (int i = 0; i < DW_STAGES; ++i) { mbar_init(&bar->full[i], DW_ROW_THREADS); mbar_init(&bar->empty[i], 1); }
         mbar_init(&bar->d_full, 1);
         fence_barrier_init();
         resolve_segs(p.P, prP);
@@ -137,66 +139,66 @@ __global__ void __launch_bounds__(TR_THREADS, 1) mlp_dw_tc_kernel(const __grid_c
         for (int st = 0; st < DW_STAGES; ++st)
             for (int half = 0; half < 2; ++half) {
                 float4* z = reinterpret_cast<float4*>(ring + (size_t)st * DW_STAGE_BYTES + half * DW_P_BYTES + 2 * DW_PANEL);
-                for (int i = threadIdx.x; i < 2 * DW_PANEL / 16; i += TR_THREADS) z[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+                for (int i = threadIdx.x; i < 2 * DW_PANEL / 16; i += DW_THREADS) z[i] = make_float4(0.f, 0.f, 0.f, 0.f);
             }
         fence_proxy_async_smem();
     }
-    if (warp == 8) tmem_alloc(tmem_holder, 256);
+    if (warp == DW_ROW_THREADS / 32) tmem_alloc(tmem_holder, 256);
     tc_fence_before_sync();
     __syncthreads();
     tc_fence_after_sync();
     const uint32_t tmem_base = *tmem_holder;
 
-    if (warp < 8) {
+    if (warp < DW_ROW_THREADS / 32) {
         const int t = threadIdx.x;
-        const int nq = qw / 32;                                  // Q chunks of 16 B per thread and stage
+        const int nq = qw / 64;                                  // Q chunks of 16 B per thread and stage
         const int qpr = qw / 4;                                  // 16-B chunks per Q row
-        const int npc = pw / 32, ppr = pw / 4;                   // the same for P
-        float4 cp[4], cq[8], np[4], nq4[8];
-        auto issue = [&](int i, float4 (&vp)[4], float4 (&vq)[8]) {
+        const int npc = pw / 64, ppr = pw / 4;                   // the same for P
+        float4 cp[2], cq[4], np[2], nq4[4];
+        auto issue = [&](int i, float4 (&vp)[2], float4 (&vq)[4]) {
             const long long row0 = ((long long)blockIdx.x + (long long)i * gridDim.x) * DW_RS;
-            const float* ap[4]; const float* aq[8];
+            const float* ap[2]; const float* aq[4];
 #pragma unroll
-            for (int j = 0; j < 4; ++j) {
-                const int q = t + TR_ROW_THREADS * (j < npc ? j : 0);
+            for (int j = 0; j < 2; ++j) {
+                const int q = t + DW_ROW_THREADS * (j < npc ? j : 0);
                 ap[j] = provider_addr(prP, row0 + q / ppr, p.n_rows, (q % ppr) * 4);
             }
 #pragma unroll
-            for (int j = 0; j < 8; ++j) {
-                const int q = t + TR_ROW_THREADS * (j < nq ? j : 0);
+            for (int j = 0; j < 4; ++j) {
+                const int q = t + DW_ROW_THREADS * (j < nq ? j : 0);
                 aq[j] = provider_addr(prQ, row0 + q / qpr, p.n_rows, (q % qpr) * 4);
             }
 #pragma unroll
-            for (int j = 0; j < 4; ++j)
+            for (int j = 0; j < 2; ++j)
                 if (j < npc) vp[j] = ldg4(ap[j]);
 #pragma unroll
-            for (int j = 0; j < 8; ++j)
+            for (int j = 0; j < 4; ++j)
                 if (j < nq) vq[j] = ldg4(aq[j]);
         };
         if (p.debug & 2) {
 #pragma unroll
-            for (int j = 0; j < 4; ++j) cp[j] = np[j] = make_float4(1.f, 2.f, 3.f, 4.f);
+            for (int j = 0; j < 2; ++j) cp[j] = np[j] = make_float4(1.f, 2.f, 3.f, 4.f);
 #pragma unroll
-            for (int j = 0; j < 8; ++j) cq[j] = nq4[j] = make_float4(1.f, 2.f, 3.f, 4.f);
+            for (int j = 0; j < 4; ++j) cq[j] = nq4[j] = make_float4(1.f, 2.f, 3.f, 4.f);
         }
-        auto store = [&](int i, const float4 (&vp)[4], const float4 (&vq)[8]) {
+        auto store = [&](int i, const float4 (&vp)[2], const float4 (&vq)[4]) {
             const uint32_t slot = i % DW_STAGES;
             mbar_wait(&bar->empty[slot], ((i / DW_STAGES) & 1) ^ 1);
             unsigned char* st = ring + (size_t)slot * DW_STAGE_BYTES;
             const long long row0 = ((long long)blockIdx.x + (long long)i * gridDim.x) * DW_RS;
 #pragma unroll
-            for (int j = 0; j < 4; ++j) {
+            for (int j = 0; j < 2; ++j) {
                 if (j < npc) {
-                    const int q = t + TR_ROW_THREADS * j;
+                    const int q = t + DW_ROW_THREADS * j;
                     const int row = q / ppr, ch = q % ppr;
                     unsigned char* d = st + (ch >> 3) * DW_PANEL + mn32b_offset(row, ch & 7);
                     split_store4(d, d + DW_P_BYTES, provider_finish(prP, vp[j], row0 + row, p.n_rows, ch * 4));
                 }
             }
 #pragma unroll
-            for (int j = 0; j < 8; ++j) {
+            for (int j = 0; j < 4; ++j) {
                 if (j < nq) {
-                    const int q = t + TR_ROW_THREADS * j;
+                    const int q = t + DW_ROW_THREADS * j;
                     const int row = q / qpr, ch = q % qpr;
                     unsigned char* d = st + 2 * DW_P_BYTES + (ch >> 3) * DW_PANEL + mn32b_offset(row, ch & 7);
                     split_store4(d, d + DW_Q_BYTES, provider_finish(prQ, vq[j], row0 + row, p.n_rows, ch * 4));
@@ -223,11 +225,11 @@ __global__ void __launch_bounds__(TR_THREADS, 1) mlp_dw_tc_kernel(const __grid_c
         if (n_my > 0) {
             mbar_wait(&bar->d_full, 0);
             tc_fence_after_sync();
-            const int qd = warp & 3, hf = warp >> 2;
+            const int qd = warp & 3, hf = warp >> 2;                  // lane quadrant, column-piece phase (0..3)
             const int m = qd * 32 + lane;
             const uint32_t lane_addr = tmem_base + ((uint32_t)(qd * 32) << 16);
             float* my = p.part + (long long)blockIdx.x * p.n * (p.swapped ? 128 : qw);
-            for (int pc = hf; pc < qw / 32 && m < pw; pc += 2) {
+            for (int pc = hf; pc < qw / 32 && m < pw; pc += 4) {
                 uint32_t v[32];
                 tmem_ld32(lane_addr + pc * 32, v);
                 tmem_wait_ld();
@@ -276,7 +278,7 @@ __global__ void __launch_bounds__(TR_THREADS, 1) mlp_dw_tc_kernel(const __grid_c
         if (n_my > 0) mma_commit(&bar->d_full);
     }
     __syncthreads();
-    if (warp == 8) tmem_dealloc(tmem_base, 256);
+    if (warp == DW_ROW_THREADS / 32) tmem_dealloc(tmem_base, 256);
 }
 
 // =============================================================================================
@@ -464,7 +466,7 @@ extern "C" int swe_mlp_layer_bwd_dw_tc(const float* delta, int64_t n_rows, int32
     SWE_REQUIRE(aligned16(delta) && aligned16(part), SWE_E_ALIGN, "mlp_layer_bwd_dw_tc: unaligned buffer");
     const int xw = provider_width_tc(X);
     SWE_REQUIRE(xw > 0, SWE_E_UNSUPP, "mlp_layer_bwd_dw_tc: provider segments must be 32-column multiples with a leaky-family activation");
-    SWE_REQUIRE((n == 128 || n == 64) && xw <= 256, SWE_E_UNSUPP,
+    SWE_REQUIRE((n == 128 || n == 64) && xw <= 256 && xw % 64 == 0, SWE_E_UNSUPP,
                 "mlp_layer_bwd_dw_tc: unsupported shape n=%d, provider width %d", n, xw);
     if (grid_out) *grid_out = 0;
     if (n_rows == 0) return 0;
@@ -483,7 +485,7 @@ extern "C" int swe_mlp_layer_bwd_dw_tc(const float* delta, int64_t n_rows, int32
     cudaError_t e = cudaFuncSetAttribute(tc::mlp_dw_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc::DW_TC_SMEM);
     if (e != cudaSuccess) { set_error("mlp_layer_bwd_dw_tc smem opt-in (%zu B): %s", tc::DW_TC_SMEM, cudaGetErrorString(e)); return (int)e; }
     const int grid = swe_mlp_layer_bwd_dw_tc_grid(n_rows);
-    tc::mlp_dw_tc_kernel<<<grid, tc::TR_THREADS, tc::DW_TC_SMEM, (cudaStream_t)stream>>>(p);
+    tc::mlp_dw_tc_kernel<<<grid, tc::DW_THREADS, tc::DW_TC_SMEM, (cudaStream_t)stream>>>(p);
     if (grid_out) *grid_out = grid;
     return check_launch("mlp_layer_bwd_dw_tc");
 }

@@ -215,9 +215,8 @@ def test_training_step_with_tensor_core_forward_opt_in(monkeypatch):
     monkeypatch.setenv("MSWE_TRAIN_TC_PARTS", "fwd,dx,dw")
     ctor = dict(num_node_features=8, num_edge_features=1, num_scales=4, previous_t=3, **REF_CONFIG_MODELS)
     data = make_tri_mesh(16, 16, 4, rollout_steps=1, seed=5)
-    import test_gpu_backward as me
-    orig = me._check_grads
-    monkeypatch.setattr(me, "_check_grads", lambda a, b, c: orig(a, b, c, floor=2e-2))
+    orig = _check_grads
+    monkeypatch.setitem(globals(), "_check_grads", lambda a, b, c: orig(a, b, c, floor=2e-2))
     _train_compare("MSGNN", ctor, data, 1)
 
 
