@@ -96,8 +96,8 @@ struct GateTcParams {
     // 3 x_d[c], 4 a_e); MODE 0: all present ones; MODE 1 (decomposed): only a_e, the node part comes from the
     // per-node partial tables; MODE 2 (partials): the kernel IS the producer of such a table for a node range
     int n_seg; int segs[5];
-    const float* p_src; const float* p_dst;      // MODE 1: [*, 128] partial tables indexed by plan id
-    float* p_out; int row_lo;                    // MODE 2: output table rows [row_lo, row_lo + n_edges)
+    const float* p_src; const float* p_dst;      // MODE 1: [*, 128] partial tables indexed by plan id; MODE 3: p_src = per-EDGE table
+    float* p_out; int row_lo;                    // MODE 2: output table rows [row_lo, row_lo + n_edges); src/dst given: per-edge table
     float* pre_out[3];                           // TRAIN: pre-activations of the three layers ([E,128], [E,128], [E,64])
 };
 
@@ -134,6 +134,12 @@ __device__ __forceinline__ float leaky_slope(int act, const float* slope_p) {
 // K-chunks to the 2 of a_e (none for un-pool calls), and epilogue 1 adds P_src[r] + P_dst[c] in fp32.
 // TRAIN: the forward of the training step — additionally stores every layer's pre-activation (what the backward
 // kernels differentiate through), otherwise identical.
+//
+// MODE 3 (static part hoisted out of the rollout): x_s and a_e — three of the five input blocks — do not change over the
+// steps of a rollout (static node features, mesh geometry, frozen weights), so their share of layer 0,
+// P[e] = A·x_s[r] + B·x_s[c] + E·a_e, is computed ONCE per rollout and call site into a per-edge table (a MODE 2 launch
+// gathering through src/dst) and every step multiplies only the x_d blocks: 4 K-chunks instead of 10 per tile (144
+// instead of 216 tcgen05.mma), streaming P[e] (512 B per edge, coalesced) in epilogue 1.
 template <bool GENERIC, int MODE, bool TRAIN = false>
 __global__ void __launch_bounds__(N_THREADS, 1) edge_gate_tc_kernel(const __grid_constant__ GateTcParams p) {
     extern __shared__ unsigned char smem_raw[];
@@ -191,11 +197,11 @@ __global__ void __launch_bounds__(N_THREADS, 1) edge_gate_tc_kernel(const __grid
             if (threadIdx.x < TILE_ROWS) {
                 long long e = e0 + threadIdx.x;
                 if (e >= p.n_edges) e = p.n_edges - 1;
-                ids[threadIdx.x] = MODE == 2 ? (int32_t)(p.row_lo + e) : __ldg(p.src + e);
+                ids[threadIdx.x] = (MODE == 2 && !p.src) ? (int32_t)(p.row_lo + e) : __ldg(p.src + e);
             } else {
                 long long e = e0 + threadIdx.x - TILE_ROWS;
                 if (e >= p.n_edges) e = p.n_edges - 1;
-                ids[threadIdx.x] = MODE == 2 ? (int32_t)(p.row_lo + e) : __ldg(p.dst + e);     // ids[128 + r]
+                ids[threadIdx.x] = (MODE == 2 && !p.src) ? (int32_t)(p.row_lo + e) : __ldg(p.dst + e);     // ids[128 + r]
             }
             asm volatile("bar.sync 1, 256;" ::: "memory");
         };
@@ -246,8 +252,15 @@ __global__ void __launch_bounds__(N_THREADS, 1) edge_gate_tc_kernel(const __grid
         auto epilogue_mid = [&](int layer, uint32_t ph, bool dump, int i) {
             // MODE 1, layer 0: the node part of W1·z comes from the per-node tables; fetch it before waiting for D
             float4 padd[16];
-            const bool with_p = MODE == 1 && layer == 0;
-            if (with_p) {
+            const bool with_p = (MODE == 1 || MODE == 3) && layer == 0;
+            if (MODE == 3 && layer == 0) {
+                // per-edge table in tile-transposed order [tile][column half][16-B chunk][row]: the 32 rows of a warp
+                // read 512 contiguous bytes per chunk (the table is padded to whole tiles)
+                const long long tile = (long long)blockIdx.x + (long long)i * gridDim.x;
+                const float* pe = p.p_src + tile * (TILE_ROWS * GH) + hf * (TILE_ROWS * 64) + row * 4;
+#pragma unroll
+                for (int j = 0; j < 16; ++j) padd[j] = ldg4_stream(pe + j * (TILE_ROWS * 4));
+            } else if (with_p) {
                 const int32_t* ids = s_ids + (i & 1) * 2 * TILE_ROWS;
                 const float* ps = p.p_src + (long long)ids[row] * GH + hf * 64;
                 const float* pd = p.p_dst + (long long)ids[TILE_ROWS + row] * GH + hf * 64;
@@ -409,18 +422,24 @@ __global__ void __launch_bounds__(N_THREADS, 1) edge_gate_tc_kernel(const __grid
                 const int buf = i & 1;
                 mbar_wait(&bar->d_full[buf], (uint32_t)(i >> 1) & 1);
                 tc_fence_after_sync();
-                const long long e = ((long long)blockIdx.x + (long long)i * gridDim.x) * TILE_ROWS + row;
-                float* o = p.p_out + ((long long)p.row_lo + e) * GH + hf * 64;
+                const long long tile = (long long)blockIdx.x + (long long)i * gridDim.x;
+                const long long e = tile * TILE_ROWS + row;
+                // per-node table: row-major [node][128]; per-edge table (src/dst given): the tile-transposed order
+                // MODE 3 reads (see there), all rows of the (padded) last tile included
+                const bool per_edge = p.src != nullptr;
+                float* o = per_edge ? p.p_out + tile * (TILE_ROWS * GH) + hf * (TILE_ROWS * 64) + row * 4
+                                    : p.p_out + ((long long)p.row_lo + e) * GH + hf * 64;
+                const int jstride = per_edge ? TILE_ROWS : 1;             // in 16-B chunks
 #pragma unroll
                 for (int cb = 0; cb < 2; ++cb) {
                     uint32_t v[32];
                     tmem_ld32(lane_addr + (buf ? COL_D_B : COL_D_A) + hf * 64 + cb * 32, v);
                     tmem_wait_ld();
-                    if (e < p.n_edges) {
+                    if (per_edge || e < p.n_edges) {
 #pragma unroll
                         for (int j = 0; j < 32; j += 4)
-                            stg4(o + cb * 32 + j, make_float4(__uint_as_float(v[j]), __uint_as_float(v[j + 1]),
-                                                              __uint_as_float(v[j + 2]), __uint_as_float(v[j + 3])));
+                            stg4(o + (cb * 8 + j / 4) * jstride * 4, make_float4(__uint_as_float(v[j]), __uint_as_float(v[j + 1]),
+                                                                                __uint_as_float(v[j + 2]), __uint_as_float(v[j + 3])));
                     }
                 }
                 tc_fence_before_sync();
@@ -592,6 +611,7 @@ static int gate_tc_launch(const tc::GateTcParams& p_in, int mode, void* stream) 
     if (mode == 0 && p.pre_out[0]) kern = generic ? tc::edge_gate_tc_kernel<true, 0, true> : tc::edge_gate_tc_kernel<false, 0, true>;
     else if (mode == 0) kern = generic ? tc::edge_gate_tc_kernel<true, 0> : tc::edge_gate_tc_kernel<false, 0>;
     else if (mode == 1) kern = generic ? tc::edge_gate_tc_kernel<true, 1> : tc::edge_gate_tc_kernel<false, 1>;
+    else if (mode == 3) kern = generic ? tc::edge_gate_tc_kernel<true, 3> : tc::edge_gate_tc_kernel<false, 3>;
     else kern = tc::edge_gate_tc_kernel<false, 2>;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc::GATE_TC_SMEM);
     if (e != cudaSuccess) { set_error("edge_gate_tc smem opt-in (%zu B): %s", tc::GATE_TC_SMEM, cudaGetErrorString(e)); return (int)e; }
@@ -642,6 +662,50 @@ extern "C" int swe_edge_gate_tc_fwd_traced(const float* xs, const float* xd_src,
         if (sg < 3 || (sg == 3 && xd_dst) || (sg == 4 && a)) p.segs[p.n_seg++] = sg;
     if (int r = gate_tc_launch(p, 0, stream)) return r;
     return check_launch("edge_gate_tc_fwd");
+}
+
+// ---------------------------------------------------------------------------------------------
+// static part of layer 0 hoisted out of the rollout (MODE 3, see the kernel comment)
+// ---------------------------------------------------------------------------------------------
+extern "C" int swe_gate_static_partials_tc(const float* xs, const float* a, const int32_t* src, const int32_t* dst,
+                                           int64_t n_edges, const void* image, int32_t k1, float* p_out, void* stream) {
+    SWE_REQUIRE(xs && src && dst && image && p_out && n_edges >= 0, SWE_E_INVAL, "gate_static_partials_tc: bad arguments");
+    SWE_REQUIRE(aligned16(xs) && aligned16(image) && aligned16(p_out) && (!a || aligned16(a)), SWE_E_ALIGN,
+                "gate_static_partials_tc: unaligned buffer");
+    SWE_REQUIRE(k1 == (a ? 5 : 4) * tc::GF, SWE_E_UNSUPP, "gate_static_partials_tc: k1=%d does not match the inputs", k1);
+    if (n_edges == 0) return 0;
+    tc::GateTcParams p;
+    memset(&p, 0, sizeof(p));
+    p.xs = xs; p.a = a; p.src = src; p.dst = dst; p.n_edges = n_edges; p.row_lo = 0; p.p_out = p_out;
+    p.img = (const unsigned char*)image; p.n_l1_img = k1 / tc::KC;
+    p.n_seg = 0;
+    p.segs[p.n_seg++] = 0; p.segs[p.n_seg++] = 1;
+    if (a) p.segs[p.n_seg++] = 4;
+    if (int r = gate_tc_launch(p, 2, stream)) return r;
+    return check_launch("gate_static_partials_tc");
+}
+
+extern "C" int swe_edge_gate_tc_stat_fwd(const float* p_edge, const float* xd_src, const float* xd_dst, const int32_t* src,
+                                         const int32_t* dst, int64_t n_edges, const void* image, int32_t k1,
+                                         const int32_t* act3, const float* const* slope3, int32_t normalize, float* s_out,
+                                         void* stream) {
+    SWE_REQUIRE(p_edge && xd_src && src && dst && s_out && image && act3 && slope3 && n_edges >= 0, SWE_E_INVAL,
+                "edge_gate_tc_stat: bad arguments");
+    SWE_REQUIRE(aligned16(p_edge) && aligned16(xd_src) && aligned16(s_out) && aligned16(image) && (!xd_dst || aligned16(xd_dst)),
+                SWE_E_ALIGN, "edge_gate_tc_stat: unaligned buffer");
+    SWE_REQUIRE(k1 == 4 * tc::GF || k1 == 5 * tc::GF, SWE_E_UNSUPP, "edge_gate_tc_stat: k1=%d", k1);
+    if (n_edges == 0) return 0;
+    tc::GateTcParams p;
+    memset(&p, 0, sizeof(p));
+    p.xd_src = xd_src; p.xd_dst = xd_dst; p.src = src; p.dst = dst; p.n_edges = n_edges; p.p_src = p_edge;
+    p.img = (const unsigned char*)image; p.n_l1_img = k1 / tc::KC;
+    for (int i = 0; i < 3; ++i) { p.act[i] = act3[i]; p.slope[i] = slope3[i]; }
+    p.normalize = normalize; p.s_out = s_out;
+    p.n_seg = 0;
+    p.segs[p.n_seg++] = 2;
+    if (xd_dst) p.segs[p.n_seg++] = 3;
+    if (int r = gate_tc_launch(p, 3, stream)) return r;
+    return check_launch("edge_gate_tc_stat_fwd");
 }
 
 // forward of the training step: s_ij plus the three pre-activations the backward differentiates through

@@ -27,6 +27,7 @@ from typing import Dict, List, Optional, Sequence, Tuple
 import numpy as np
 import torch
 
+from .engine import new_static_token, static_inputs
 from .utils.data import Data
 
 
@@ -301,14 +302,16 @@ class PartitionedRollout:
         self.bc = self.graph.BC.to(device, torch.float32).contiguous()
         self.n_static_raw = self.x.shape[1] - model.previous_t * NUM_WATER_VARS
         self.launches_per_step = 0
+        self._token = new_static_token()
 
     def _one_step(self):
         lib, m = self.lib, self.model
         c0 = lib.launch_count
         if self.node_BC.numel():
             lib.apply_bc(self.x, self.n_static_raw, m.previous_t, self.type_BC, self.node_BC, self.bc, self.step)
-        m._launch(self.plan, self.graph, self.x, self.preds, step_ptr=self.step,
-                  pred_stride=self.preds.shape[1] * 2, x_next=self.x, halo=self.halo)
+        with static_inputs(self._token):         # static columns, mesh part and weights are constant over the rollout
+            m._launch(self.plan, self.graph, self.x, self.preds, step_ptr=self.step,
+                      pred_stride=self.preds.shape[1] * 2, x_next=self.x, halo=self.halo)
         lib.step_advance(self.step)
         # the window shift wrote garbage into the halo rows of x: refresh them from their owners
         for s in range(self.part.num_scales):

@@ -15,6 +15,7 @@ from typing import Optional
 import torch
 
 from .. import lib
+from ..engine import new_static_token, static_inputs
 from ..utils.data import Batch, Data
 from ..utils.dataset import NUM_WATER_VARS, apply_boundary_condition, check_type_BC, use_prediction
 
@@ -97,6 +98,7 @@ class RolloutRunner:
         self.use_cuda_graph = use_cuda_graph and self.T > 2
         self._graph = None
         self.launches_per_step = 0
+        self._token = new_static_token()     # renewed whenever x (and with it, possibly, the static columns) is replaced
 
     def _one_step(self):
         c0 = lib.launch_count
@@ -106,13 +108,18 @@ class RolloutRunner:
     def _step_body(self):
         m = self.model
         lib.apply_bc(self.x, self.n_static_raw, m.previous_t, self.type_BC, self.node_BC, self.bc, self.step)
-        m._launch(self.plan, self.graph, self.x, self.preds, step_ptr=self.step,
-                  pred_stride=self.preds.shape[1] * NUM_WATER_VARS, x_next=self.x)
+        # the static columns of x, the mesh and (no_grad) the weights are constant over the steps of this loop
+        with static_inputs(self._token):
+            m._launch(self.plan, self.graph, self.x, self.preds, step_ptr=self.step,
+                      pred_stride=self.preds.shape[1] * NUM_WATER_VARS, x_next=self.x)
         lib.step_advance(self.step)
 
     def reset(self, x: Optional[torch.Tensor] = None):
         self.x.copy_(self.graph.x if x is None else x)
         self.step.zero_()
+        if x is not None:
+            self._token = new_static_token() # other static columns: the hoisted tables are recomputed (and the
+            self._graph = None               # captured step, which does not contain their producer, is re-captured)
 
     def run(self, n_steps: Optional[int] = None):
         """Advance `n_steps` (default: all remaining) steps; returns the prediction buffer

@@ -140,3 +140,68 @@ def test_gate_tc_decomposed_layer0_matches_exact_fp32_kernel(n_edge_feat, drop_d
     lo, cnt = n // 3, n // 2
     lib.gate_partials_tc(xs, xd, lo, cnt, tc.image(), k1, 0, p2)
     assert torch.equal(p2[lo:lo + cnt], p_src[lo:lo + cnt]) and float(p2[:lo].abs().max()) == 0 and float(p2[lo + cnt:].abs().max()) == 0
+
+
+@pytest.mark.parametrize("n_edge_feat,drop_dst,nx,ny", [(64, False, 60, 40), (0, False, 33, 21), (0, True, 33, 21), (64, False, 5, 3),
+                                                      (0, True, 400, 300), (64, False, 400, 300)])   # the last two: ~19 tiles per CTA
+def test_gate_tc_static_share_hoisted(n_edge_feat, drop_dst, nx, ny):
+    """Per-edge table of the static share of layer 0 (x_s[r], x_s[c], a_e — constant over a rollout) + the per-step
+    gate on the x_d blocks, against fp64, the exact-fp32 CUDA-core gate and the full tcgen05 gate."""
+    n, E, src, dst, xs, xd, a, mlp, k1 = _setup(n_edge_feat, seed=11, nx=nx, ny=ny)
+    tc = PackedGateTC(mlp)
+    codes, slopes = tc.acts_and_slopes()
+    xd_dst = None if drop_dst else xd
+    W1 = [m for m in mlp if isinstance(m, torch.nn.Linear)][0].weight.detach().double()
+    n_tiles = (E + 127) // 128
+    tab = torch.full((n_tiles * 128, 128), float("nan"), device=DEV)
+    lib.gate_static_partials_tc(xs, a, src, dst, E, tc.image(), k1, tab)
+    ref = xs.double()[src.long()] @ W1[:, 0:64].T + xs.double()[dst.long()] @ W1[:, 64:128].T
+    if n_edge_feat:
+        ref = ref + a.double() @ W1[:, 256:320].T
+    # internal order [tile][column half][16-byte chunk][row][4] -> [edge][128]
+    rowmajor = tab.view(n_tiles, 2, 16, 128, 4).permute(0, 3, 1, 2, 4).reshape(n_tiles * 128, 128)[:E]
+    assert float((rowmajor.double() - ref).abs().max()) < 2e-6 * float(ref.abs().max())
+    s_st = torch.full((E, 64), float("nan"), device=DEV)
+    lib.edge_gate_tc_stat_fwd(tab, xd, xd_dst, src, dst, E, tc.image(), k1, codes, slopes, True, s_st)
+    s_ff = torch.empty(E, 64, device=DEV)
+    pk = PackedMLP(mlp, [(64, 64)] * (5 if n_edge_feat else 4), {})
+    lib.edge_gate_fwd(xs, xd, xd_dst, a, src, dst, E, pk.struct(), True, s_ff, 64)
+    s_full = torch.empty(E, 64, device=DEV)
+    lib.edge_gate_tc_fwd(xs, xd, xd_dst, a, src, dst, E, tc.image(), k1, codes, slopes, True, s_full, None)
+    torch.cuda.synchronize()
+    assert bool(torch.isfinite(s_st).all())
+    assert float((s_st - s_ff).abs().max()) < 1e-5, float((s_st - s_ff).abs().max())
+    assert float((s_st - s_full).abs().max()) < 1e-5
+    # deterministic
+    s2 = torch.empty(E, 64, device=DEV)
+    lib.edge_gate_tc_stat_fwd(tab, xd, xd_dst, src, dst, E, tc.image(), k1, codes, slopes, True, s2)
+    torch.cuda.synchronize()
+    assert torch.equal(s2, s_st)
+
+
+def test_rollout_with_hoisted_static_share_matches_full_gate(monkeypatch):
+    """rollout_test (CUDA-graph loop) with the static share hoisted (default) against MSWE_GATE_L0=full, and a second
+    rollout from other static columns through RolloutRunner.reset(x): the tables must be rebuilt."""
+    from helpers import REF_CONFIG_MODELS, rel_l2
+    from mswe_gnn_b200.models.gnn import MSGNN
+    from mswe_gnn_b200.training.train import RolloutRunner
+    from mswe_gnn_b200.utils.synthetic import make_tri_mesh
+    ctor = dict(num_node_features=8, num_edge_features=1, num_scales=3, previous_t=3, **REF_CONFIG_MODELS)
+    m = MSGNN(**ctor).to(DEV).eval()
+    d = make_tri_mesh(40, 32, 3, rollout_steps=6, seed=3).to(DEV)
+    x2 = d.x.clone()
+    x2[:, :2] = torch.randn_like(x2[:, :2]) * 3.0                   # other static features, same dynamic state
+    out = {}
+    with torch.no_grad():
+        for mode in ("static", "full"):
+            monkeypatch.setenv("MSWE_GATE_L0", mode)
+            r = RolloutRunner(m, d, 6)
+            a = r.run().clone()
+            r.reset(x2)
+            b = r.run().clone()
+            out[mode] = (a, b)
+    for i in range(2):
+        e = rel_l2(out["static"][i], out["full"][i])
+        assert e < 5e-5, (i, e)                                     # 6 autoregressive steps: bounded drift
+    e = rel_l2(out["full"][0], out["full"][1])
+    assert e > 1e-4, e                                               # the two rollouts really differ

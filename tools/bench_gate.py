@@ -80,3 +80,28 @@ if os.environ.get("TRACE_DEC"):
         for tile in range(2, 6):
             for r, nm in enumerate(["rowA(w0)", "rowB(w4)", "mma"]):
                 print(tile, nm, [(int(v) - t0) if int(v) else None for v in t[r, tile, :6]])
+
+if os.environ.get("TRACE_STAT"):
+    import ctypes as C
+    l = lib.load()
+    l.swe_gate_tc_set_trace.argtypes = [C.c_void_p]
+    tab = torch.empty((E + 127) // 128 * 128, 128, device=DEV)
+    for name, fn in (("static partials (once per rollout)", lambda: lib.gate_static_partials_tc(xs, a, src, dst, E, img, 320, tab)),
+                     ("stat gate", lambda: lib.edge_gate_tc_stat_fwd(tab, xd, xd, src, dst, E, img, 320, codes, slopes, True, s)),
+                     ("full gate", lambda: lib.edge_gate_tc_fwd(xs, xd, xd, a, src, dst, E, img, 320, codes, slopes, True, s, None))):
+        for _ in range(3): fn()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(10): fn()
+        e1.record(); torch.cuda.synchronize()
+        print(f"{name}: {e0.elapsed_time(e1) / 10:.3f} ms")
+        trace = torch.zeros(3 * 128, dtype=torch.int64, device=DEV)
+        l.swe_gate_tc_set_trace(trace.data_ptr())
+        fn()
+        torch.cuda.synchronize()
+        t = trace.cpu().view(3, 16, 8)
+        t0 = int(t[0, 2, 0]) if int(t[0, 2, 0]) else int(t[2, 2, 0])
+        for tile in range(2, 6):
+            for r, nm in enumerate(["rowA(w0)", "rowB(w4)", "mma"]):
+                print("  ", tile, nm, [(int(v) - t0) if int(v) else None for v in t[r, tile, :6]])
