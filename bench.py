@@ -323,9 +323,7 @@ def run_ours(args):
                 "frac": dom["tflops"] / pk["bf16"], "traffic": traffic, "peak_source": pk["hbm_src"] + " (sustained bf16)",
                 "note": "algorithmic FLOPs of the reference edge MLP / time; executed as 3 TF32 MMAs per product (error-free "
                         "hi/lo splits for fp32 parity), and tcgen05 issues one 128x128x8 TF32 instruction per >= 94 cycles "
-                        "(tools/microbench/mma_rate.cu), so the ceiling of this formulation is ~0.19 of the bf16 peak; inside a "
-                        "rollout the x_s/a_e share of layer 0 (3 of its 5 input blocks) is hoisted into a per-edge table "
-                        "computed once, so 144 of the 216 MMAs per 128 edges are executed per step"}
+                        "(tools/microbench/mma_rate.cu), so the ceiling of this formulation is ~0.19 of the bf16 peak"}
     step_gbs = alg["total"] / (ms * 1e-3 / K) / 1e9
 
     cpu = None
@@ -598,7 +596,7 @@ def profile_kernels(runner, alg):
             elif name == "edge_gate_tc_dec_fwd":
                 meta = ("gate", int(a[5]), a[2] is not None)
             elif name == "edge_gate_tc_stat_fwd":                    # reference work of the call: the whole edge MLP
-                meta = ("gate", int(a[5]), int(a[7]) == 5 * F)
+                meta = ("gate", int(a[6]), int(a[8]) == 5 * F)
             records.append((name, e0, e1, meta))
             return r
         setattr(lib, name, inner)

@@ -310,16 +310,19 @@ int swe_mlp_layer_bwd_dw(const float* delta, int64_t n_rows, int32_t n, const sw
                          float* part, int32_t* grid_out, void* stream);
 int swe_mlp_layer_bwd_dw_grid(int64_t n_rows);
 
-/* Static share of the edge MLP's first layer, hoisted out of the rollout: x_s and a_e do not change over the steps
- * of a rollout (training/train.py:67-95 re-evaluates them every step), so P[e] = W1[:, x_s[r] | x_s[c] | a_e blocks] ·
- * (x_s[src[e]], x_s[dst[e]], a[e]) is computed once (no bias) into a table in an internal tile-transposed order
- * (128 floats per edge, padded to whole 128-edge tiles: p_out holds ceil(n_edges / 128) * 128 * 128 floats) ... */
+/* Static share of the edge MLP's first layer, hoisted out of the rollout: the encoded edge features a_e (and, for
+ * with_WL=False models, the encoded static node features x_s) do not change over the steps of a rollout
+ * (training/train.py:67-95 re-evaluates them every step), so P[e] = W1[:, a_e block] · a[e] (+ W1[:, x_s blocks] ·
+ * (x_s[src[e]], x_s[dst[e]]) when xs != NULL) is computed once (no bias) into a table in an internal tile-transposed
+ * order (128 floats per edge, padded to whole 128-edge tiles: p_out holds ceil(n_edges / 128) * 128 * 128 floats) ... */
 int swe_gate_static_partials_tc(const float* xs, const float* a, const int32_t* src, const int32_t* dst,
                                 int64_t n_edges, const void* image, int32_t k1, float* p_out, void* stream);
-/* ... and every step evaluates s_ij from P[e] plus the x_d blocks only (xd_dst NULL: un-pool call). */
-int swe_edge_gate_tc_stat_fwd(const float* p_edge, const float* xd_src, const float* xd_dst, const int32_t* src,
-                              const int32_t* dst, int64_t n_edges, const void* image, int32_t k1, const int32_t* act3,
-                              const float* const* slope3, int32_t normalize, float* s_out, void* stream);
+/* ... and every step evaluates s_ij from P[e] plus the remaining blocks: x_d (xd_dst NULL: un-pool call) and, when it
+ * is not part of the table (xs != NULL here: models with with_WL=True, whose x_s contains the current water level), x_s. */
+int swe_edge_gate_tc_stat_fwd(const float* p_edge, const float* xs, const float* xd_src, const float* xd_dst,
+                              const int32_t* src, const int32_t* dst, int64_t n_edges, const void* image, int32_t k1,
+                              const int32_t* act3, const float* const* slope3, int32_t normalize, float* s_out,
+                              void* stream);
 
 /* swe_edge_gate_tc_fwd that also stores the pre-activations of the three edge-MLP layers (pre1, pre2: [E, 128],
  * pre3: [E, 64]; bias included, activation not applied) — the forward of the training step for the default model. */

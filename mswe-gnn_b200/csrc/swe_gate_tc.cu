@@ -135,11 +135,12 @@ __device__ __forceinline__ float leaky_slope(int act, const float* slope_p) {
 // TRAIN: the forward of the training step — additionally stores every layer's pre-activation (what the backward
 // kernels differentiate through), otherwise identical.
 //
-// MODE 3 (static part hoisted out of the rollout): x_s and a_e — three of the five input blocks — do not change over the
-// steps of a rollout (static node features, mesh geometry, frozen weights), so their share of layer 0,
-// P[e] = A·x_s[r] + B·x_s[c] + E·a_e, is computed ONCE per rollout and call site into a per-edge table (a MODE 2 launch
-// gathering through src/dst) and every step multiplies only the x_d blocks: 4 K-chunks instead of 10 per tile (144
-// instead of 216 tcgen05.mma), streaming P[e] (512 B per edge, coalesced) in epilogue 1.
+// MODE 3 (static part hoisted out of the rollout): the encoded edge features a_e — and, for models built with
+// with_WL=False, the encoded static node features x_s too — do not change over the steps of a rollout (mesh geometry,
+// static inputs, frozen weights), so their share of layer 0, P[e] = E·a_e (+ A·x_s[r] + B·x_s[c]), is computed ONCE per
+// rollout and call site into a per-edge table (a MODE 2 launch gathering through src/dst) and every step multiplies only
+// the other blocks: 8 (or 4) K-chunks instead of 10 per tile, streaming P[e] (512 B per edge, coalesced) in epilogue 1.
+// With with_WL=True (config.yaml) x_s contains the water level of the current step and is NOT static.
 template <bool GENERIC, int MODE, bool TRAIN = false>
 __global__ void __launch_bounds__(N_THREADS, 1) edge_gate_tc_kernel(const __grid_constant__ GateTcParams p) {
     extern __shared__ unsigned char smem_raw[];
@@ -669,39 +670,41 @@ extern "C" int swe_edge_gate_tc_fwd_traced(const float* xs, const float* xd_src,
 // ---------------------------------------------------------------------------------------------
 extern "C" int swe_gate_static_partials_tc(const float* xs, const float* a, const int32_t* src, const int32_t* dst,
                                            int64_t n_edges, const void* image, int32_t k1, float* p_out, void* stream) {
-    SWE_REQUIRE(xs && src && dst && image && p_out && n_edges >= 0, SWE_E_INVAL, "gate_static_partials_tc: bad arguments");
-    SWE_REQUIRE(aligned16(xs) && aligned16(image) && aligned16(p_out) && (!a || aligned16(a)), SWE_E_ALIGN,
+    SWE_REQUIRE((xs || a) && src && dst && image && p_out && n_edges >= 0, SWE_E_INVAL, "gate_static_partials_tc: bad arguments");
+    SWE_REQUIRE((!xs || aligned16(xs)) && aligned16(image) && aligned16(p_out) && (!a || aligned16(a)), SWE_E_ALIGN,
                 "gate_static_partials_tc: unaligned buffer");
-    SWE_REQUIRE(k1 == (a ? 5 : 4) * tc::GF, SWE_E_UNSUPP, "gate_static_partials_tc: k1=%d does not match the inputs", k1);
+    SWE_REQUIRE(k1 == 4 * tc::GF || k1 == 5 * tc::GF, SWE_E_UNSUPP, "gate_static_partials_tc: k1=%d", k1);
+    SWE_REQUIRE(!a || k1 == 5 * tc::GF, SWE_E_UNSUPP, "gate_static_partials_tc: edge features need k1 = 320");
     if (n_edges == 0) return 0;
     tc::GateTcParams p;
     memset(&p, 0, sizeof(p));
     p.xs = xs; p.a = a; p.src = src; p.dst = dst; p.n_edges = n_edges; p.row_lo = 0; p.p_out = p_out;
     p.img = (const unsigned char*)image; p.n_l1_img = k1 / tc::KC;
     p.n_seg = 0;
-    p.segs[p.n_seg++] = 0; p.segs[p.n_seg++] = 1;
+    if (xs) { p.segs[p.n_seg++] = 0; p.segs[p.n_seg++] = 1; }
     if (a) p.segs[p.n_seg++] = 4;
     if (int r = gate_tc_launch(p, 2, stream)) return r;
     return check_launch("gate_static_partials_tc");
 }
 
-extern "C" int swe_edge_gate_tc_stat_fwd(const float* p_edge, const float* xd_src, const float* xd_dst, const int32_t* src,
-                                         const int32_t* dst, int64_t n_edges, const void* image, int32_t k1,
-                                         const int32_t* act3, const float* const* slope3, int32_t normalize, float* s_out,
-                                         void* stream) {
+extern "C" int swe_edge_gate_tc_stat_fwd(const float* p_edge, const float* xs, const float* xd_src, const float* xd_dst,
+                                         const int32_t* src, const int32_t* dst, int64_t n_edges, const void* image,
+                                         int32_t k1, const int32_t* act3, const float* const* slope3, int32_t normalize,
+                                         float* s_out, void* stream) {
     SWE_REQUIRE(p_edge && xd_src && src && dst && s_out && image && act3 && slope3 && n_edges >= 0, SWE_E_INVAL,
                 "edge_gate_tc_stat: bad arguments");
-    SWE_REQUIRE(aligned16(p_edge) && aligned16(xd_src) && aligned16(s_out) && aligned16(image) && (!xd_dst || aligned16(xd_dst)),
-                SWE_E_ALIGN, "edge_gate_tc_stat: unaligned buffer");
+    SWE_REQUIRE(aligned16(p_edge) && aligned16(xd_src) && aligned16(s_out) && aligned16(image) && (!xd_dst || aligned16(xd_dst)) &&
+                (!xs || aligned16(xs)), SWE_E_ALIGN, "edge_gate_tc_stat: unaligned buffer");
     SWE_REQUIRE(k1 == 4 * tc::GF || k1 == 5 * tc::GF, SWE_E_UNSUPP, "edge_gate_tc_stat: k1=%d", k1);
     if (n_edges == 0) return 0;
     tc::GateTcParams p;
     memset(&p, 0, sizeof(p));
-    p.xd_src = xd_src; p.xd_dst = xd_dst; p.src = src; p.dst = dst; p.n_edges = n_edges; p.p_src = p_edge;
+    p.xs = xs; p.xd_src = xd_src; p.xd_dst = xd_dst; p.src = src; p.dst = dst; p.n_edges = n_edges; p.p_src = p_edge;
     p.img = (const unsigned char*)image; p.n_l1_img = k1 / tc::KC;
     for (int i = 0; i < 3; ++i) { p.act[i] = act3[i]; p.slope[i] = slope3[i]; }
     p.normalize = normalize; p.s_out = s_out;
     p.n_seg = 0;
+    if (xs) { p.segs[p.n_seg++] = 0; p.segs[p.n_seg++] = 1; }      // x_s is not static (with_WL): multiplied every step
     p.segs[p.n_seg++] = 2;
     if (xd_dst) p.segs[p.n_seg++] = 3;
     if (int r = gate_tc_launch(p, 3, stream)) return r;

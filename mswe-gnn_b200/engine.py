@@ -339,6 +339,7 @@ def hop_backend() -> str:
 
 
 _STATIC_TOKEN = None
+_XS_STATIC = False
 _TOKEN_COUNTER = [0]
 _PSTAT_BYTES = [0]                 # bytes held by all hoisted static-partial tables of this process
 
@@ -350,28 +351,33 @@ def new_static_token() -> int:
 
 
 class static_inputs:
-    """Context manager a rollout loop puts around its steps: inside it the static node features x_s, the edge features
-    and the weights are the same on every call, identified by `token` (anything hashable; a new token = new inputs).
-    The tcgen05 gate then evaluates their share of the first edge-MLP layer once per token (``gate_layer0() ==
-    'static'``) instead of once per step."""
+    """Context manager a rollout loop puts around its steps: inside it the edge features, the static input columns and
+    the weights are the same on every call, identified by `token` (a new token = new inputs).  `xs_static` says
+    whether the ENCODED static node features x_s are constant too: true for models built with with_WL=False; with
+    with_WL=True (config.yaml) x_s is encoded from the current water level and changes every step.
+    The tcgen05 gate then evaluates the share of the first edge-MLP layer that belongs to the constant blocks once
+    per token (``gate_layer0() == 'static'``) instead of once per step."""
 
-    def __init__(self, token):
-        self.token = token
+    def __init__(self, token, xs_static: bool = False):
+        self.token, self.xs_static = token, bool(xs_static)
 
     def __enter__(self):
-        global _STATIC_TOKEN
-        self._old, _STATIC_TOKEN = _STATIC_TOKEN, self.token
+        global _STATIC_TOKEN, _XS_STATIC
+        self._old = (_STATIC_TOKEN, _XS_STATIC)
+        _STATIC_TOKEN, _XS_STATIC = self.token, self.xs_static
 
     def __exit__(self, *exc):
-        global _STATIC_TOKEN
-        _STATIC_TOKEN = self._old
+        global _STATIC_TOKEN, _XS_STATIC
+        _STATIC_TOKEN, _XS_STATIC = self._old
         return False
 
 
 def gate_layer0() -> str:
-    """'static' (default): inside a rollout (``static_inputs``) the x_s / a_e share of layer 0 is hoisted into a per-edge
-    table computed once, the per-step gate multiplies only the x_d blocks (144 instead of 216 MMAs per 128 edges);
-    outside a rollout this is 'full'.
+    """'static' (default): inside a rollout (``static_inputs``) of a model built with with_WL=False the share of layer 0
+    that belongs to the constant input blocks (x_s[r], x_s[c], a_e) is hoisted into a per-edge table computed once;
+    the per-step gate multiplies only the x_d blocks (144 instead of 216 MMAs per 128 edges: 1.66 vs 2.10 ms per 3 M
+    edges).  With with_WL=True (config.yaml) x_s is encoded from the current water level, nothing worth hoisting is
+    constant, and this is 'full' — as it is outside a rollout.
     'full': every edge multiplies its whole 5F-wide input on the tensor core; 'dec': layer 0 is
     decomposed into per-node partial tables (swe_gate_partials_tc) + the edge part.  Measured on cfg3 (r01d): the
     decomposed gate itself is 11 % faster (5.82 vs 6.52 ms/step) but the tables cost 2.70 ms/step, because the
@@ -410,7 +416,8 @@ class SweGnnLauncher:
         or None when it does not fit comfortably in device memory (the full gate is used then)."""
         if es.n_edges == 0:
             return None
-        stamp = (_STATIC_TOKEN, self.tc._stamp, xs.data_ptr(), 0 if a is None else a.data_ptr())
+        stamp = (_STATIC_TOKEN, self.tc._stamp, 0 if xs is None else xs.data_ptr(), 0 if a is None else a.data_ptr())
+        dev = (xs if xs is not None else a).device
         ent = self._pstat.get(id(es))
         if ent is not None and ent[0] == stamp and ent[1] is es:
             return ent[2]
@@ -418,10 +425,10 @@ class SweGnnLauncher:
         if tab is None:
             rows = (es.n_edges + 127) // 128 * 128         # whole 128-edge tiles (internal tile-transposed order)
             need = rows * 128 * 4
-            free, total = torch.cuda.mem_get_info(xs.device)
+            free, total = torch.cuda.mem_get_info(dev)
             if need > 0.25 * free or _PSTAT_BYTES[0] + need > 0.35 * total:
                 return None
-            tab = torch.empty(rows, 128, dtype=torch.float32, device=xs.device)
+            tab = torch.empty(rows, 128, dtype=torch.float32, device=dev)
             _PSTAT_BYTES[0] += need
         lib.gate_static_partials_tc(xs, a, es.src, es.dst, es.n_edges, img, k1, tab)
         if len(self._pstat) >= 4 and id(es) not in self._pstat:
@@ -437,11 +444,13 @@ class SweGnnLauncher:
             k1 = self.tc.linears[0].weight.shape[1]
             img = self.tc.image()
             mode = gate_layer0()
-            if mode == "static" and dbg is None and _STATIC_TOKEN is not None:
-                tab = self._static_partials(es, xs, a, img, k1)
+            # (hoisting a_e alone — all that is constant when x_s carries the water level — was measured on cfg3:
+            #  2.13 vs 2.10 ms per 3 M edges, the table read costs what the 24 saved MMAs give; not taken)
+            if mode == "static" and dbg is None and _STATIC_TOKEN is not None and _XS_STATIC:
+                tab = self._static_partials(es, xs if _XS_STATIC else None, a, img, k1)
                 if tab is not None:
-                    lib.edge_gate_tc_stat_fwd(tab, xd_src, xd_dst, es.src, es.dst, es.n_edges, img, k1, codes, slopes,
-                                              m.normalize, s_buf)
+                    lib.edge_gate_tc_stat_fwd(tab, None if _XS_STATIC else xs, xd_src, xd_dst, es.src, es.dst, es.n_edges,
+                                              img, k1, codes, slopes, m.normalize, s_buf)
                     return
             if ptab is not None and dbg is None and mode == "dec":
                 p_src, p_dst = ptab

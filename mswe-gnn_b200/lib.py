@@ -100,7 +100,7 @@ SIGNATURES = {
     "swe_mlp_layer_bwd_dw": (C.c_int, [_p, _i64, _i32, _rows, _i32, _p, _pi32, _p]),
     "swe_mlp_layer_bwd_dw_grid": (C.c_int, [_i64]),
     "swe_gate_static_partials_tc": (C.c_int, [_p, _p, _p, _p, _i64, _p, _i32, _p, _p]),
-    "swe_edge_gate_tc_stat_fwd": (C.c_int, [_p, _p, _p, _p, _p, _i64, _p, _i32, C.POINTER(C.c_int32),
+    "swe_edge_gate_tc_stat_fwd": (C.c_int, [_p, _p, _p, _p, _p, _p, _i64, _p, _i32, C.POINTER(C.c_int32),
                                             C.POINTER(C.c_void_p), _i32, _p, _p]),
     "swe_edge_gate_tc_train_fwd": (C.c_int, [_p, _p, _p, _p, _p, _p, _i64, _p, _i32, C.POINTER(C.c_int32),
                                              C.POINTER(C.c_void_p), _i32, _p, _p, _p, _p, _p]),
@@ -249,10 +249,10 @@ def gate_static_partials_tc(xs, a, src, dst, n_edges, image, k1, p_out):
                                               image.data_ptr(), k1, ptr(p_out), _stream()), "swe_gate_static_partials_tc")
 
 
-def edge_gate_tc_stat_fwd(p_edge, xd_src, xd_dst, src, dst, n_edges, image, k1, acts, slopes, normalize, s_out):
+def edge_gate_tc_stat_fwd(p_edge, xs, xd_src, xd_dst, src, dst, n_edges, image, k1, acts, slopes, normalize, s_out):
     act3 = (C.c_int32 * 3)(*acts)
     slope3 = (C.c_void_p * 3)(*[None if s is None else ptr(s) for s in slopes])
-    _check(load().swe_edge_gate_tc_stat_fwd(ptr(p_edge), ptr(xd_src), ptr(xd_dst), ptr(src, torch.int32),
+    _check(load().swe_edge_gate_tc_stat_fwd(ptr(p_edge), ptr(xs), ptr(xd_src), ptr(xd_dst), ptr(src, torch.int32),
                                             ptr(dst, torch.int32), n_edges, image.data_ptr(), k1, act3, slope3,
                                             int(normalize), ptr(s_out), _stream()), "swe_edge_gate_tc_stat_fwd")
 

@@ -140,8 +140,16 @@ class _EncodeDecodeMixin:
         n_static_raw = self.static_node_features - int(bool(self.with_WL))
         if self._tc_static is not None and self._tc_dynamic is not None and rowmlp_backend() == "tc":
             n_cols = x.shape[1]
-            self._tc_static.encode(x, 0, n_static_raw, self.with_WL, (n_static_raw - 1, n_cols - 2), plan.perm, 0,
-                                   plan.n_nodes, xs)
+            # inside a rollout (engine.static_inputs) the static columns and the encoder weights do not change:
+            # without the water-level input, x_s is encoded on the first step only
+            from .. import engine
+            tok = engine._STATIC_TOKEN if engine._XS_STATIC else None
+            stamp = None if tok is None else (tok, xs.data_ptr(), id(plan), tuple(
+                (p.data_ptr(), p._version) for p in self.static_node_encoder.parameters()))
+            if stamp is None or stamp != getattr(self, "_xs_stamp", None):
+                self._tc_static.encode(x, 0, n_static_raw, self.with_WL, (n_static_raw - 1, n_cols - 2), plan.perm, 0,
+                                       plan.n_nodes, xs)
+                self._xs_stamp = stamp
             self._tc_dynamic.encode(x, n_static_raw, n_cols - n_static_raw, False, (0, 0), plan.perm, 0, n_dyn_rows, xd)
         else:
             lib.node_encode_fwd(x, plan.perm, plan.n_nodes, n_static_raw, self.with_WL, n_dyn_rows,

@@ -309,7 +309,7 @@ class PartitionedRollout:
         c0 = lib.launch_count
         if self.node_BC.numel():
             lib.apply_bc(self.x, self.n_static_raw, m.previous_t, self.type_BC, self.node_BC, self.bc, self.step)
-        with static_inputs(self._token):         # static columns, mesh part and weights are constant over the rollout
+        with static_inputs(self._token, xs_static=not m.with_WL):         # static columns, mesh part and weights are constant over the rollout
             m._launch(self.plan, self.graph, self.x, self.preds, step_ptr=self.step,
                       pred_stride=self.preds.shape[1] * 2, x_next=self.x, halo=self.halo)
         lib.step_advance(self.step)

@@ -109,7 +109,7 @@ class RolloutRunner:
         m = self.model
         lib.apply_bc(self.x, self.n_static_raw, m.previous_t, self.type_BC, self.node_BC, self.bc, self.step)
         # the static columns of x, the mesh and (no_grad) the weights are constant over the steps of this loop
-        with static_inputs(self._token):
+        with static_inputs(self._token, xs_static=not m.with_WL):
             m._launch(self.plan, self.graph, self.x, self.preds, step_ptr=self.step,
                       pred_stride=self.preds.shape[1] * NUM_WATER_VARS, x_next=self.x)
         lib.step_advance(self.step)

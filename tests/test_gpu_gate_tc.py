@@ -142,11 +142,15 @@ def test_gate_tc_decomposed_layer0_matches_exact_fp32_kernel(n_edge_feat, drop_d
     assert torch.equal(p2[lo:lo + cnt], p_src[lo:lo + cnt]) and float(p2[:lo].abs().max()) == 0 and float(p2[lo + cnt:].abs().max()) == 0
 
 
+@pytest.mark.parametrize("hoist_xs", [False, True])
 @pytest.mark.parametrize("n_edge_feat,drop_dst,nx,ny", [(64, False, 60, 40), (0, False, 33, 21), (0, True, 33, 21), (64, False, 5, 3),
                                                       (0, True, 400, 300), (64, False, 400, 300)])   # the last two: ~19 tiles per CTA
-def test_gate_tc_static_share_hoisted(n_edge_feat, drop_dst, nx, ny):
-    """Per-edge table of the static share of layer 0 (x_s[r], x_s[c], a_e — constant over a rollout) + the per-step
-    gate on the x_d blocks, against fp64, the exact-fp32 CUDA-core gate and the full tcgen05 gate."""
+def test_gate_tc_static_share_hoisted(n_edge_feat, drop_dst, nx, ny, hoist_xs):
+    """Per-edge table of the static share of layer 0 (a_e; with hoist_xs also x_s[r], x_s[c] — constant over a rollout
+    of a with_WL=False model) + the per-step gate on the remaining blocks, against fp64, the exact-fp32 CUDA-core
+    gate and the full tcgen05 gate."""
+    if not hoist_xs and not n_edge_feat:
+        pytest.skip("nothing to hoist")
     n, E, src, dst, xs, xd, a, mlp, k1 = _setup(n_edge_feat, seed=11, nx=nx, ny=ny)
     tc = PackedGateTC(mlp)
     codes, slopes = tc.acts_and_slopes()
@@ -154,15 +158,18 @@ def test_gate_tc_static_share_hoisted(n_edge_feat, drop_dst, nx, ny):
     W1 = [m for m in mlp if isinstance(m, torch.nn.Linear)][0].weight.detach().double()
     n_tiles = (E + 127) // 128
     tab = torch.full((n_tiles * 128, 128), float("nan"), device=DEV)
-    lib.gate_static_partials_tc(xs, a, src, dst, E, tc.image(), k1, tab)
-    ref = xs.double()[src.long()] @ W1[:, 0:64].T + xs.double()[dst.long()] @ W1[:, 64:128].T
+    lib.gate_static_partials_tc(xs if hoist_xs else None, a, src, dst, E, tc.image(), k1, tab)
+    ref = torch.zeros(E, 128, dtype=torch.float64, device=DEV)
+    if hoist_xs:
+        ref = ref + xs.double()[src.long()] @ W1[:, 0:64].T + xs.double()[dst.long()] @ W1[:, 64:128].T
     if n_edge_feat:
         ref = ref + a.double() @ W1[:, 256:320].T
     # internal order [tile][column half][16-byte chunk][row][4] -> [edge][128]
     rowmajor = tab.view(n_tiles, 2, 16, 128, 4).permute(0, 3, 1, 2, 4).reshape(n_tiles * 128, 128)[:E]
     assert float((rowmajor.double() - ref).abs().max()) < 2e-6 * float(ref.abs().max())
     s_st = torch.full((E, 64), float("nan"), device=DEV)
-    lib.edge_gate_tc_stat_fwd(tab, xd, xd_dst, src, dst, E, tc.image(), k1, codes, slopes, True, s_st)
+    xs_step = None if hoist_xs else xs
+    lib.edge_gate_tc_stat_fwd(tab, xs_step, xd, xd_dst, src, dst, E, tc.image(), k1, codes, slopes, True, s_st)
     s_ff = torch.empty(E, 64, device=DEV)
     pk = PackedMLP(mlp, [(64, 64)] * (5 if n_edge_feat else 4), {})
     lib.edge_gate_fwd(xs, xd, xd_dst, a, src, dst, E, pk.struct(), True, s_ff, 64)
@@ -174,20 +181,27 @@ def test_gate_tc_static_share_hoisted(n_edge_feat, drop_dst, nx, ny):
     assert float((s_st - s_full).abs().max()) < 1e-5
     # deterministic
     s2 = torch.empty(E, 64, device=DEV)
-    lib.edge_gate_tc_stat_fwd(tab, xd, xd_dst, src, dst, E, tc.image(), k1, codes, slopes, True, s2)
+    lib.edge_gate_tc_stat_fwd(tab, xs_step, xd, xd_dst, src, dst, E, tc.image(), k1, codes, slopes, True, s2)
     torch.cuda.synchronize()
     assert torch.equal(s2, s_st)
 
 
-def test_rollout_with_hoisted_static_share_matches_full_gate(monkeypatch):
+@pytest.mark.parametrize("with_WL", [True, False])
+def test_rollout_with_hoisted_static_share_matches_full_gate(monkeypatch, with_WL):
     """rollout_test (CUDA-graph loop) with the static share hoisted (default) against MSWE_GATE_L0=full, and a second
-    rollout from other static columns through RolloutRunner.reset(x): the tables must be rebuilt."""
+    rollout from other static columns through RolloutRunner.reset(x): the tables must be rebuilt.  with_WL=True
+    (config.yaml): x_s is encoded from the current water level, only a_e is hoisted; the boundary inflow below makes
+    the water level change by O(1) over the steps, so a table wrongly built from x_s would show."""
     from helpers import REF_CONFIG_MODELS, rel_l2
     from mswe_gnn_b200.models.gnn import MSGNN
     from mswe_gnn_b200.training.train import RolloutRunner
     from mswe_gnn_b200.utils.synthetic import make_tri_mesh
     ctor = dict(num_node_features=8, num_edge_features=1, num_scales=3, previous_t=3, **REF_CONFIG_MODELS)
+    ctor["with_WL"] = with_WL
     m = MSGNN(**ctor).to(DEV).eval()
+    with torch.no_grad():                                            # a decoder that moves the water depth a lot
+        for p_ in m.node_decoder.parameters():
+            p_.mul_(4.0)
     d = make_tri_mesh(40, 32, 3, rollout_steps=6, seed=3).to(DEV)
     x2 = d.x.clone()
     x2[:, :2] = torch.randn_like(x2[:, :2]) * 3.0                   # other static features, same dynamic state
@@ -205,3 +219,5 @@ def test_rollout_with_hoisted_static_share_matches_full_gate(monkeypatch):
         assert e < 5e-5, (i, e)                                     # 6 autoregressive steps: bounded drift
     e = rel_l2(out["full"][0], out["full"][1])
     assert e > 1e-4, e                                               # the two rollouts really differ
+    depth = out["full"][0][:, :, 0]
+    assert float((depth[-1] - depth[0]).abs().max()) > 1e-2          # and the water level really moves

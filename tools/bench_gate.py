@@ -86,8 +86,8 @@ if os.environ.get("TRACE_STAT"):
     l = lib.load()
     l.swe_gate_tc_set_trace.argtypes = [C.c_void_p]
     tab = torch.empty((E + 127) // 128 * 128, 128, device=DEV)
-    for name, fn in (("static partials (once per rollout)", lambda: lib.gate_static_partials_tc(xs, a, src, dst, E, img, 320, tab)),
-                     ("stat gate", lambda: lib.edge_gate_tc_stat_fwd(tab, xd, xd, src, dst, E, img, 320, codes, slopes, True, s)),
+    for name, fn in (("static partials (once per rollout)", lambda: lib.gate_static_partials_tc(None, a, src, dst, E, img, 320, tab)),
+                     ("stat gate (a_e hoisted)", lambda: lib.edge_gate_tc_stat_fwd(tab, xs, xd, xd, src, dst, E, img, 320, codes, slopes, True, s)),
                      ("full gate", lambda: lib.edge_gate_tc_fwd(xs, xd, xd, a, src, dst, E, img, 320, codes, slopes, True, s, None))):
         for _ in range(3): fn()
         torch.cuda.synchronize()
