@@ -538,6 +538,8 @@ def profile_train_kernels(step_fn):
                 fl = 2.0 * a[4] * a[5] * a[10]
             elif name == "mlp_layer_bwd_dw":
                 fl = 2.0 * a[1] * a[2] * a[4]
+            elif name == "mlp_layer_fwd":
+                fl = 2.0 * a[1] * a[4] * sum(a[0].seg[j].width for j in range(a[0].n_seg))
             elif name == "mlp_layer_bwd_dx_tc":
                 fl = 2.0 * a[1] * a[2] * a[7]
             elif name == "mlp_layer_bwd_dw_tc":

@@ -325,11 +325,21 @@ int swe_edge_gate_tc_stat_fwd(const float* p_edge, const float* xs, const float*
                               void* stream);
 
 /* swe_edge_gate_tc_fwd that also stores the pre-activations of the three edge-MLP layers (pre1, pre2: [E, 128],
- * pre3: [E, 64]; bias included, activation not applied) — the forward of the training step for the default model. */
+ * pre3: [E, 64]; bias included, activation not applied) — the forward of the training step for the default model.
+ * fix_count != NULL: [3] counters (zeroed by the caller) and fix_lists [3][fix_cap] receive, per layer, the entries
+ * (edge << 8 | column) with |pre| < fix_tau * max(1, max |pre| of the row piece): candidates for a wrong sign. */
 int swe_edge_gate_tc_train_fwd(const float* xs, const float* xd_src, const float* xd_dst, const float* a,
                                const int32_t* src, const int32_t* dst, int64_t n_edges, const void* image, int32_t k1,
                                const int32_t* act3, const float* const* slope3, int32_t normalize, float* pre1,
-                               float* pre2, float* pre3, float* s_out, void* stream);
+                               float* pre2, float* pre3, float* s_out, unsigned long long* fix_lists,
+                               int32_t* fix_count, int32_t fix_cap, float fix_tau, void* stream);
+/* Recomputes the listed pre-activations in exact fp32 (w1 [128, k1], w2 [128, 128], w3 [64, 128]: torch Linear
+ * layout), layer by layer, so that the backward's derivative masks (v > 0) are those of an fp32 forward. */
+int swe_gate_fix_preacts(const float* xs, const float* xd_src, const float* xd_dst, const float* a, const int32_t* src,
+                         const int32_t* dst, const float* w1, const float* b1, const float* w2, const float* b2,
+                         const float* w3, const float* b3, int32_t k1, const int32_t* act3, const float* const* slope3,
+                         float* pre1, float* pre2, float* pre3, const unsigned long long* fix_lists,
+                         const int32_t* fix_count, int32_t fix_cap, void* stream);
 
 /* Tensor-core (tcgen05, 3xTF32 = fp32-accurate products, fp32 accumulation in TMEM) forms of the two GEMMs above
  * for the wide edge-MLP layers; same mathematics, relative error ~1e-6 instead of exact-fp32 summation order.

@@ -49,14 +49,34 @@ def train_gemm_backend() -> str:
 def _tc_part(name: str) -> bool:
     """MSWE_TRAIN_TC_PARTS selects which training GEMMs of the wide edge MLP use the tensor cores (3xTF32).
 
-    Default ``dx,dw``: both backward GEMMs; the forward stays on the exact-fp32 CUDA-core kernels, so the saved
-    pre-activations — and with them every PReLU/ReLU derivative mask — are those of the fp32 reference and the
-    gradients match the oracle to ~1e-5.  ``fwd,dx,dw`` also runs the forward on the tensor cores (the inference gate
-    kernel storing its pre-activations): 15 % faster per step, forward values within 3e-6, but the ~1e-6 relative
-    perturbation flips the derivative mask of the few pre-activations that close to the activation's kink, which
-    shows up as ~1e-3 relative L2 in the weight gradients (each flipped entry is an O(1) change of one summand)."""
+    Default ``fwd,dx,dw``: the forward (the inference gate kernel in the variant that stores its pre-activations)
+    and both backward GEMMs.  The forward's ~3e-6 error would flip the PReLU/ReLU derivative mask of the few
+    pre-activations that close to the kink — an O(1) change of one summand each, ~1e-3 relative L2 in the weight
+    gradients — so those entries are listed by the kernel and re-evaluated in exact fp32 (``swe_gate_fix_preacts``,
+    ``MSWE_TRAIN_FIX_TAU``); with that the gradients match the fp32 oracle to ~1e-5 like the all-CUDA-core path."""
     import os
-    return train_gemm_backend() == "tc" and name in os.environ.get("MSWE_TRAIN_TC_PARTS", "dx,dw").split(",")
+    return train_gemm_backend() == "tc" and name in os.environ.get("MSWE_TRAIN_TC_PARTS", "fwd,dx,dw").split(",")
+
+
+_FIX_BUF = {}
+
+
+def _fix_tau() -> float:
+    """|pre| below tau * max(1, row max) is re-evaluated in exact fp32 after the tensor-core forward (0 = off)."""
+    import os
+    return float(os.environ.get("MSWE_TRAIN_FIX_TAU", "1e-4"))
+
+
+def _fix_buffers(n_edges: int, dev):
+    """Work lists of swe_edge_gate_tc_train_fwd / swe_gate_fix_preacts: [3][cap] entries + zeroed [3] counters."""
+    cap = max(1 << 16, n_edges // 2)
+    key = str(dev)
+    buf = _FIX_BUF.get(key)
+    if buf is None or buf[2] < cap:
+        buf = (torch.empty(3 * cap, dtype=torch.int64, device=dev), torch.zeros(4, dtype=torch.int32, device=dev), cap)
+        _FIX_BUF[key] = buf
+    buf[1].zero_()
+    return buf
 
 
 def _r4(k: int) -> int:
@@ -370,10 +390,21 @@ def swegnn_forward_train(mod, es, xs: Arr, xd_src: Arr, xd_dst: Optional[Arr], a
         # variant that also stores the three pre-activations the backward needs
         codes, slopes = gate_tc.acts_and_slopes()
         c.pres = [torch.empty(max(E, 1), w, dtype=torch.float32, device=dev) for w in (2 * F, 2 * F, F)]
-        lib.edge_gate_tc_train_fwd(xs.addr, xd_src.addr, None if xd_dst is None else xd_dst.addr,
-                                   a if mod.edge_features > 0 else None, es.src, es.dst, E, gate_tc.image(),
-                                   gate_tc.linears[0].weight.shape[1], codes, slopes, mod.normalize, c.pres[0], c.pres[1],
-                                   c.pres[2], c.s)
+        a_in = a if mod.edge_features > 0 else None
+        xd_dst_addr = None if xd_dst is None else xd_dst.addr
+        k1 = gate_tc.linears[0].weight.shape[1]
+        tau = _fix_tau()
+        lists, count, cap = _fix_buffers(E, dev) if tau > 0 else (None, None, 0)
+        lib.edge_gate_tc_train_fwd(xs.addr, xd_src.addr, xd_dst_addr, a_in, es.src, es.dst, E, gate_tc.image(), k1, codes,
+                                   slopes, mod.normalize, c.pres[0], c.pres[1], c.pres[2], c.s, lists, count, cap, tau)
+        if tau > 0 and E > 0:
+            # the few pre-activations that lie within the 3xTF32 error of the activation's kink are re-evaluated in
+            # exact fp32, so that the derivative masks of the backward are those of the fp32 reference
+            l1, l2, l3 = gate_tc.linears
+            wb = [t.detach().contiguous() if t is not None else None
+                  for t in (l1.weight, l1.bias, l2.weight, l2.bias, l3.weight, l3.bias)]
+            lib.gate_fix_preacts(xs.addr, xd_src.addr, xd_dst_addr, a_in, es.src, es.dst, *wb, k1, codes, slopes, c.pres[0],
+                                 c.pres[1], c.pres[2], lists, count, cap)
     else:
         c.pres = c.mlp.forward(segs, E, dev)
         last = c.mlp.L - 1

@@ -99,6 +99,9 @@ struct GateTcParams {
     const float* p_src; const float* p_dst;      // MODE 1: [*, 128] partial tables indexed by plan id; MODE 3: p_src = per-EDGE table
     float* p_out; int row_lo;                    // MODE 2: output table rows [row_lo, row_lo + n_edges); src/dst given: per-edge table
     float* pre_out[3];                           // TRAIN: pre-activations of the three layers ([E,128], [E,128], [E,64])
+    // TRAIN: work lists of the pre-activations that lie within the 3xTF32 error of the activation's kink (|pre| < tau):
+    // entry = edge << 8 | column; swe_gate_fix_preacts re-evaluates exactly those in exact fp32 (see there)
+    unsigned long long* fix_list[3]; int* fix_count; int fix_cap; float fix_tau;
 };
 
 __device__ __forceinline__ int l1_chunk_segment(const GateTcParams& p, int i) {
@@ -314,11 +317,29 @@ __global__ void __launch_bounds__(N_THREADS, 1) edge_gate_tc_kernel(const __grid
                     const long long e = ((long long)blockIdx.x + (long long)i * gridDim.x) * TILE_ROWS + row;
                     if (e < p.n_edges) {
                         float* d = p.pre_out[layer] + e * GH + hf * 64 + cb * 32;
+                        float mn = 3.4e38f, mx = 0.f;
 #pragma unroll
                         for (int j = 0; j < 32; j += 4) {
                             const float4 b4 = *reinterpret_cast<const float4*>(bias + cb * 32 + j);
-                            stg4(d + j, make_float4(__uint_as_float(v[j]) + b4.x, __uint_as_float(v[j + 1]) + b4.y,
-                                                    __uint_as_float(v[j + 2]) + b4.z, __uint_as_float(v[j + 3]) + b4.w));
+                            const float4 q = make_float4(__uint_as_float(v[j]) + b4.x, __uint_as_float(v[j + 1]) + b4.y,
+                                                         __uint_as_float(v[j + 2]) + b4.z, __uint_as_float(v[j + 3]) + b4.w);
+                            stg4(d + j, q);
+                            mn = fminf(fminf(mn, fminf(fabsf(q.x), fabsf(q.y))), fminf(fabsf(q.z), fabsf(q.w)));
+                            mx = fmaxf(fmaxf(mx, fmaxf(fabsf(q.x), fabsf(q.y))), fmaxf(fabsf(q.z), fabsf(q.w)));
+                        }
+                        const float tau = p.fix_tau * fmaxf(1.f, mx);
+                        if (p.fix_count && mn < tau) {                  // rare: some pre-activation sits on the kink
+                            uint32_t mask = 0;
+#pragma unroll
+                            for (int j = 0; j < 32; ++j)
+                                mask |= (fabsf(__uint_as_float(v[j]) + bias[cb * 32 + j]) < tau ? 1u : 0u) << j;
+                            while (mask) {
+                                const int j = __ffs(mask) - 1;
+                                mask &= mask - 1;
+                                const int k = atomicAdd(p.fix_count + layer, 1);
+                                if (k < p.fix_cap)
+                                    p.fix_list[layer][k] = ((unsigned long long)e << 8) | (unsigned)(hf * 64 + cb * 32 + j);
+                            }
                         }
                     }
                 }
@@ -361,13 +382,35 @@ __global__ void __launch_bounds__(N_THREADS, 1) edge_gate_tc_kernel(const __grid
                 const long long e = ((long long)blockIdx.x + (long long)i * gridDim.x) * TILE_ROWS + row;
                 if (e < p.n_edges) {
                     float* d = p.pre_out[2] + e * GF;
+                    float mn = 3.4e38f, mx = 0.f;
 #pragma unroll
                     for (int j = 0; j < 32; j += 4) {
                         const float4 b0 = *reinterpret_cast<const float4*>(bias + j), b1 = *reinterpret_cast<const float4*>(bias + 32 + j);
-                        stg4(d + j, make_float4(__uint_as_float(v0[j]) + b0.x, __uint_as_float(v0[j + 1]) + b0.y,
-                                                __uint_as_float(v0[j + 2]) + b0.z, __uint_as_float(v0[j + 3]) + b0.w));
-                        stg4(d + 32 + j, make_float4(__uint_as_float(v1[j]) + b1.x, __uint_as_float(v1[j + 1]) + b1.y,
-                                                     __uint_as_float(v1[j + 2]) + b1.z, __uint_as_float(v1[j + 3]) + b1.w));
+                        const float4 q0 = make_float4(__uint_as_float(v0[j]) + b0.x, __uint_as_float(v0[j + 1]) + b0.y,
+                                                      __uint_as_float(v0[j + 2]) + b0.z, __uint_as_float(v0[j + 3]) + b0.w);
+                        const float4 q1 = make_float4(__uint_as_float(v1[j]) + b1.x, __uint_as_float(v1[j + 1]) + b1.y,
+                                                      __uint_as_float(v1[j + 2]) + b1.z, __uint_as_float(v1[j + 3]) + b1.w);
+                        stg4(d + j, q0);
+                        stg4(d + 32 + j, q1);
+                        mn = fminf(fminf(mn, fminf(fabsf(q0.x), fabsf(q0.y))), fminf(fabsf(q0.z), fabsf(q0.w)));
+                        mn = fminf(fminf(mn, fminf(fabsf(q1.x), fabsf(q1.y))), fminf(fabsf(q1.z), fabsf(q1.w)));
+                        mx = fmaxf(fmaxf(mx, fmaxf(fabsf(q0.x), fabsf(q0.y))), fmaxf(fabsf(q0.z), fabsf(q0.w)));
+                        mx = fmaxf(fmaxf(mx, fmaxf(fabsf(q1.x), fabsf(q1.y))), fmaxf(fabsf(q1.z), fabsf(q1.w)));
+                    }
+                    const float tau = p.fix_tau * fmaxf(1.f, mx);
+                    if (p.fix_count && mn < tau) {
+                        unsigned long long mask = 0;
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) {
+                            mask |= (unsigned long long)(fabsf(__uint_as_float(v0[j]) + bias[j]) < tau ? 1u : 0u) << j;
+                            mask |= (unsigned long long)(fabsf(__uint_as_float(v1[j]) + bias[32 + j]) < tau ? 1u : 0u) << (32 + j);
+                        }
+                        while (mask) {
+                            const int j = __ffsll((long long)mask) - 1;
+                            mask &= mask - 1;
+                            const int k = atomicAdd(p.fix_count + 2, 1);
+                            if (k < p.fix_cap) p.fix_list[2][k] = ((unsigned long long)e << 8) | (unsigned)j;
+                        }
                     }
                 }
             }
@@ -711,13 +754,96 @@ extern "C" int swe_edge_gate_tc_stat_fwd(const float* p_edge, const float* xs, c
     return check_launch("edge_gate_tc_stat_fwd");
 }
 
+// ---------------------------------------------------------------------------------------------
+// exact-fp32 re-evaluation of the pre-activations flagged by the TRAIN forward (one warp per entry)
+// ---------------------------------------------------------------------------------------------
+namespace swe { namespace tc {
+struct FixParams {
+    const float* xs; const float* xd_src; const float* xd_dst; const float* a;
+    const int32_t* src; const int32_t* dst;
+    const float* w[3]; const float* b[3]; int k1;
+    int act[3]; const float* slope[3];
+    float* pre[3];
+    const unsigned long long* list; const int* count; int cap;
+};
+template <int LAYER>
+__global__ void __launch_bounds__(256) gate_fix_kernel(const __grid_constant__ FixParams p) {
+    const int lane = threadIdx.x & 31;
+    const int n = min(*p.count, p.cap);
+    const int warps = (gridDim.x * blockDim.x) >> 5;
+    for (int it = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; it < n; it += warps) {
+        const unsigned long long ent = p.list[it];
+        const long long e = (long long)(ent >> 8);
+        const int col = (int)(ent & 255u);
+        float acc = 0.f;
+        if (LAYER == 0) {
+            const float* wr = p.w[0] + (long long)col * p.k1;
+            const long long r = __ldg(p.src + e), c = __ldg(p.dst + e);
+#pragma unroll
+            for (int sg = 0; sg < 5; ++sg) {
+                const float* z = sg == 0 ? p.xs + r * GF : sg == 1 ? p.xs + c * GF : sg == 2 ? p.xd_src + r * GF
+                               : sg == 3 ? (p.xd_dst ? p.xd_dst + c * GF : nullptr) : (p.a ? p.a + e * GF : nullptr);
+                if (z) {
+                    const float2 zv = *reinterpret_cast<const float2*>(z + 2 * lane);
+                    const float2 wv = *reinterpret_cast<const float2*>(wr + sg * GF + 2 * lane);
+                    acc = fmaf(zv.x, wv.x, acc); acc = fmaf(zv.y, wv.y, acc);
+                }
+            }
+        } else {
+            const float sl = (p.act[LAYER - 1] == SWE_ACT_PRELU && p.slope[LAYER - 1]) ? __ldg(p.slope[LAYER - 1]) : 0.f;
+            const float4 h = *reinterpret_cast<const float4*>(p.pre[LAYER - 1] + e * GH + 4 * lane);
+            const float4 wv = *reinterpret_cast<const float4*>(p.w[LAYER] + (long long)col * GH + 4 * lane);
+            acc = fmaf(act_apply(p.act[LAYER - 1], h.x, sl), wv.x, acc); acc = fmaf(act_apply(p.act[LAYER - 1], h.y, sl), wv.y, acc);
+            acc = fmaf(act_apply(p.act[LAYER - 1], h.z, sl), wv.z, acc); acc = fmaf(act_apply(p.act[LAYER - 1], h.w, sl), wv.w, acc);
+        }
+#pragma unroll
+        for (int off = 16; off >= 1; off >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, off);
+        if (lane == 0) p.pre[LAYER][e * (LAYER == 2 ? GF : GH) + col] = acc + (p.b[LAYER] ? __ldg(p.b[LAYER] + col) : 0.f);
+    }
+}
+}}  // namespace swe::tc
+
+// The tensor-core forward evaluates a pre-activation to ~3e-6 (3xTF32); an entry that close to 0 may come out with the
+// other sign, and the backward's derivative mask (PReLU / ReLU: v > 0) would then differ from the fp32 reference's in
+// an O(1) way for that summand.  swe_edge_gate_tc_train_fwd therefore lists every |pre| < tau * max(1, row max) and
+// this call recomputes exactly those (typically 1e-4 of all entries) with fp32 FMAs, layer by layer (a layer-l entry is
+// recomputed from the already repaired pre-activations of layer l-1, so the result does not depend on the order in
+// which the lists were filled: bit-reproducible).
+extern "C" int swe_gate_fix_preacts(const float* xs, const float* xd_src, const float* xd_dst, const float* a,
+                                    const int32_t* src, const int32_t* dst, const float* w1, const float* b1,
+                                    const float* w2, const float* b2, const float* w3, const float* b3, int32_t k1,
+                                    const int32_t* act3, const float* const* slope3, float* pre1, float* pre2, float* pre3,
+                                    const unsigned long long* fix_lists, const int32_t* fix_count, int32_t fix_cap,
+                                    void* stream) {
+    SWE_REQUIRE(xs && xd_src && src && dst && w1 && w2 && w3 && act3 && slope3 && pre1 && pre2 && pre3 && fix_lists &&
+                fix_count && fix_cap > 0, SWE_E_INVAL, "gate_fix_preacts: bad arguments");
+    SWE_REQUIRE(k1 == (a ? 5 : 4) * tc::GF, SWE_E_UNSUPP, "gate_fix_preacts: k1=%d does not match the inputs", k1);
+    tc::FixParams p;
+    memset(&p, 0, sizeof(p));
+    p.xs = xs; p.xd_src = xd_src; p.xd_dst = xd_dst; p.a = a; p.src = src; p.dst = dst;
+    p.w[0] = w1; p.w[1] = w2; p.w[2] = w3; p.b[0] = b1; p.b[1] = b2; p.b[2] = b3; p.k1 = k1;
+    for (int i = 0; i < 3; ++i) { p.act[i] = act3[i]; p.slope[i] = slope3[i]; }
+    p.pre[0] = pre1; p.pre[1] = pre2; p.pre[2] = pre3; p.cap = fix_cap;
+    const int grid = 2 * NUM_SMS;
+    p.list = fix_lists; p.count = fix_count;
+    tc::gate_fix_kernel<0><<<grid, 256, 0, (cudaStream_t)stream>>>(p);
+    p.list = fix_lists + fix_cap; p.count = fix_count + 1;
+    tc::gate_fix_kernel<1><<<grid, 256, 0, (cudaStream_t)stream>>>(p);
+    p.list = fix_lists + 2 * (size_t)fix_cap; p.count = fix_count + 2;
+    tc::gate_fix_kernel<2><<<grid, 256, 0, (cudaStream_t)stream>>>(p);
+    return check_launch("gate_fix_preacts");
+}
+
 // forward of the training step: s_ij plus the three pre-activations the backward differentiates through
 extern "C" int swe_edge_gate_tc_train_fwd(const float* xs, const float* xd_src, const float* xd_dst, const float* a,
                                           const int32_t* src, const int32_t* dst, int64_t n_edges, const void* image,
                                           int32_t k1, const int32_t* act3, const float* const* slope3, int32_t normalize,
-                                          float* pre1, float* pre2, float* pre3, float* s_out, void* stream) {
+                                          float* pre1, float* pre2, float* pre3, float* s_out,
+                                          unsigned long long* fix_lists, int32_t* fix_count, int32_t fix_cap, float fix_tau,
+                                          void* stream) {
     SWE_REQUIRE(xs && xd_src && src && dst && s_out && image && act3 && slope3 && pre1 && pre2 && pre3 && n_edges >= 0,
                 SWE_E_INVAL, "edge_gate_tc_train: bad arguments");
+    SWE_REQUIRE(!fix_count || (fix_lists && fix_cap > 0 && fix_tau >= 0.f), SWE_E_INVAL, "edge_gate_tc_train: work list");
     SWE_REQUIRE(aligned16(xs) && aligned16(xd_src) && aligned16(s_out) && aligned16(image) && (!a || aligned16(a)) &&
                 (!xd_dst || aligned16(xd_dst)) && aligned16(pre1) && aligned16(pre2) && aligned16(pre3), SWE_E_ALIGN,
                 "edge_gate_tc_train: unaligned buffer");
@@ -730,6 +856,10 @@ extern "C" int swe_edge_gate_tc_train_fwd(const float* xs, const float* xd_src, 
     for (int i = 0; i < 3; ++i) { p.act[i] = act3[i]; p.slope[i] = slope3[i]; }
     p.normalize = normalize; p.s_out = s_out;
     p.pre_out[0] = pre1; p.pre_out[1] = pre2; p.pre_out[2] = pre3;
+    if (fix_count) {
+        for (int i = 0; i < 3; ++i) p.fix_list[i] = fix_lists + (size_t)i * fix_cap;
+        p.fix_count = fix_count; p.fix_cap = fix_cap; p.fix_tau = fix_tau;
+    }
     p.n_seg = 0;
     for (int sg = 0; sg < 5; ++sg)
         if (sg < 3 || (sg == 3 && xd_dst) || (sg == 4 && a)) p.segs[p.n_seg++] = sg;

@@ -103,7 +103,9 @@ SIGNATURES = {
     "swe_edge_gate_tc_stat_fwd": (C.c_int, [_p, _p, _p, _p, _p, _p, _i64, _p, _i32, C.POINTER(C.c_int32),
                                             C.POINTER(C.c_void_p), _i32, _p, _p]),
     "swe_edge_gate_tc_train_fwd": (C.c_int, [_p, _p, _p, _p, _p, _p, _i64, _p, _i32, C.POINTER(C.c_int32),
-                                             C.POINTER(C.c_void_p), _i32, _p, _p, _p, _p, _p]),
+                                             C.POINTER(C.c_void_p), _i32, _p, _p, _p, _p, _p, _p, _i32, C.c_float, _p]),
+    "swe_gate_fix_preacts": (C.c_int, [_p] * 12 + [_i32, C.POINTER(C.c_int32), C.POINTER(C.c_void_p), _p, _p, _p, _p, _p,
+                                       _i32, _p]),
     "swe_mlp_layer_bwd_dx_tc": (C.c_int, [_p, _i64, _i32, _p, _i32, _i32, _i32, _i32, _p, _i32, _p, _i32, _i32, _p]),
     "swe_mlp_layer_bwd_dw_tc": (C.c_int, [_p, _i64, _i32, _rows, _p, _pi32, _p]),
     "swe_mlp_layer_bwd_dw_tc_grid": (C.c_int, [_i64]),
@@ -258,13 +260,26 @@ def edge_gate_tc_stat_fwd(p_edge, xs, xd_src, xd_dst, src, dst, n_edges, image, 
 
 
 def edge_gate_tc_train_fwd(xs, xd_src, xd_dst, a, src, dst, n_edges, image, k1, acts, slopes, normalize, pre1, pre2, pre3,
-                           s_out):
+                           s_out, fix_lists=None, fix_count=None, fix_cap=0, fix_tau=0.0):
     act3 = (C.c_int32 * 3)(*acts)
     slope3 = (C.c_void_p * 3)(*[None if s is None else ptr(s) for s in slopes])
     _check(load().swe_edge_gate_tc_train_fwd(_addr(xs), _addr(xd_src), _addr(xd_dst), _addr(a), ptr(src, torch.int32),
                                              ptr(dst, torch.int32), n_edges, image.data_ptr(), k1, act3, slope3,
-                                             int(normalize), ptr(pre1), ptr(pre2), ptr(pre3), ptr(s_out), _stream()),
+                                             int(normalize), ptr(pre1), ptr(pre2), ptr(pre3), ptr(s_out),
+                                             None if fix_lists is None else fix_lists.data_ptr(),
+                                             None if fix_count is None else fix_count.data_ptr(), int(fix_cap),
+                                             float(fix_tau), _stream()),
            "swe_edge_gate_tc_train_fwd")
+
+
+def gate_fix_preacts(xs, xd_src, xd_dst, a, src, dst, w1, b1, w2, b2, w3, b3, k1, acts, slopes, pre1, pre2, pre3, fix_lists,
+                     fix_count, fix_cap):
+    act3 = (C.c_int32 * 3)(*acts)
+    slope3 = (C.c_void_p * 3)(*[None if s is None else ptr(s) for s in slopes])
+    _check(load().swe_gate_fix_preacts(_addr(xs), _addr(xd_src), _addr(xd_dst), _addr(a), ptr(src, torch.int32),
+                                       ptr(dst, torch.int32), ptr(w1), ptr(b1), ptr(w2), ptr(b2), ptr(w3), ptr(b3), k1, act3,
+                                       slope3, ptr(pre1), ptr(pre2), ptr(pre3), fix_lists.data_ptr(), fix_count.data_ptr(),
+                                       int(fix_cap), _stream()), "swe_gate_fix_preacts")
 
 
 def node_linear_fwd(x, row_lo, n_rows, wt, out, F):

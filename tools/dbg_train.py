@@ -22,7 +22,7 @@ def run(parts):
     T._check_grads = orig
     return errs
 
-res = {p: run(p) for p in ["none", "fwd", "dx", "dw", "fwd,dx,dw"]}
+res = {p: run(p) for p in ["none", "fwd", "dx,dw", "fwd,dx,dw"]}
 keys = sorted(res["none"], key=lambda k: -res["fwd,dx,dw"][k][0])[:14]
 print("%-46s" % "key", *["%10s" % p for p in res], "      yard")
 for k in keys:
