@@ -349,7 +349,7 @@ int swe_gate_fix_preacts(const float* xs, const float* xd_src, const float* xd_d
  *          (split == ko: dx1 unused; otherwise split == 64, ko == 128: two 64-wide blocks in one pass).
  *   dw_tc: part[cta][seg_col0 * n + n_i * w_seg + k] = Σ_{rows of this CTA} delta[r, n_i] · X_seg[r, k] for every
  *          segment of the provider X (widths multiples of 32, none/relu/leakyrelu/prelu on load); n in {64, 128},
- *          provider up to 256 columns wide.  Reduce each segment with
+ *          provider 64, 128 or 256 columns wide.  Reduce each segment with
  *          swe_reduce_partials(part, grid, n * width(X), seg_col0 * n, n_out * w_seg, w_seg, ...). */
 int swe_mlp_layer_bwd_dx_tc(const float* delta, int64_t n_rows, int32_t n, const float* w, int32_t w_ld,
                             int32_t k_off, int32_t k_valid, int32_t ko, float* dx0, int32_t accumulate0, float* dx1,

@@ -46,6 +46,14 @@ def train_gemm_backend() -> str:
     return os.environ.get("MSWE_TRAIN_GEMM", "tc")
 
 
+def _min_rows() -> int:
+    """Row count below which the training GEMMs stay on CUDA cores (the tensor-core kernels' fixed cost — a weight
+    image per CTA, one CTA per 128 rows — is not paid back on the small coarse levels); MSWE_TC_MIN_ROWS overrides."""
+    import os
+    return int(os.environ.get("MSWE_TC_MIN_ROWS", "16384"))
+
+
+
 def _tc_part(name: str) -> bool:
     """MSWE_TRAIN_TC_PARTS selects which training GEMMs of the wide edge MLP use the tensor cores (3xTF32).
 
@@ -228,8 +236,8 @@ class TrainMLP:
                 ko = self.n_pad[li - 1]
                 dx = torch.empty(max(n_rows, 1), ko, dtype=torch.float32, device=dev)
                 prev_act = self.act_code(li - 1)
-                tc = tc_dx_on and n in (64, 128) and ko in (64, 128)
-                tc_dw = tc_dw_on and prev_act in _TC_ACTS and (n == 128 or (n == 64 and ko == 128))
+                tc = tc_dx_on and n in (64, 128) and ko in (64, 128) and n_rows >= _min_rows()
+                tc_dw = tc_dw_on and prev_act in _TC_ACTS and n in (64, 128) and ko in (64, 128) and n_rows >= _min_rows()
                 if tc:
                     # delta (in place) + bias / slope partials on CUDA cores (element-wise), the GEMM on tensor cores
                     lib.mlp_layer_bwd_dx(dh, pres[li], act, slope, n_rows, n, self.w_rm[li], self.w_rm[li].shape[1], 0, 16, 16,
@@ -246,7 +254,8 @@ class TrainMLP:
                 results = None
             else:
                 nb = len(self.blocks)
-                wide = n == 128 and all(bp == wd and wd in (64, 128) for (_, wd), bp in zip(self.blocks, self.block_pad))
+                wide = n in (64, 128) and n_rows >= _min_rows() and all(
+                    bp == wd and wd in (64, 128) for (_, wd), bp in zip(self.blocks, self.block_pad))
                 tc, tc_dw = tc_dx_on and wide, tc_dw_on and wide
                 results = [None] * nb
                 outs, accs = [None] * nb, [False] * nb
@@ -296,6 +305,8 @@ class TrainMLP:
                         grp, wsum = [], 0
                         while j < nb and wsum + self.block_pad[j] <= 256:
                             grp.append(j); wsum += self.block_pad[j]; j += 1
+                        while wsum not in (64, 128, 256):            # the kernel takes 64, 128 or 256 columns
+                            j -= 1; wsum -= self.block_pad[grp.pop()]
                         rows = lib.make_rows([(first_segs[q][0], first_segs[q][1], first_segs[q][2], first_segs[q][3], 0, None)
                                               for q in grp])
                         items, c = [], 0
@@ -316,6 +327,14 @@ class TrainMLP:
             if li > 0:
                 dh = dx
         return results
+
+    @staticmethod
+    def _dw_square(delta, n_rows, F, rows, gw, dev):
+        """dW of a bias-free F x F Linear over node rows (hop filters): tensor cores for F = 64 on large levels."""
+        if F == 64 and n_rows >= _min_rows() and _tc_part("dw"):
+            TrainMLP._dw_tc(delta, n_rows, F, rows, [(0, F, 0, F)], F, gw, F, F, dev)
+        else:
+            TrainMLP._dw(delta, n_rows, F, rows, F, gw, F, F, 0, F, dev)
 
     @staticmethod
     def _dw_tc(delta, n_rows, n, rows, items, width, gw, n_out, k_in, dev):
@@ -353,6 +372,14 @@ def _transposed(es):
                                             es.dst_lo + es.n_dst, by_row=True)
             es.t_rowptr, es.t_pos = rp, order.contiguous()       # "original edge id" of this build = CSR position
     return es.t_rowptr, es.t_pos
+
+
+def _node_linear_bwd(g: Arr, lo: int, n: int, W: torch.Tensor, out: Arr, F: int):
+    """out[lo:lo+n] = g[lo:lo+n] · W (input gradient of a bias-free Linear over node rows)."""
+    if F == 64 and n >= _min_rows() and _tc_part("dx"):
+        lib.mlp_layer_bwd_dx_tc(g.row0, n, F, W.detach().contiguous(), F, 0, F, F, out.addr + lo * F * 4, False)
+    else:
+        lib.node_linear_fwd(g.addr, lo, n, W.detach().contiguous(), out.addr, F)
 
 
 class SweCall:
@@ -461,9 +488,9 @@ def swegnn_backward(c: SweCall, g_out: Arr, d_xs: Arr, d_xd_src: Arr, d_xd_src_a
             if mod.with_filter_matrix:
                 Wk = mod.filter_matrix[k + 1].weight
                 rows = lib.make_rows([(c.agg[k].row0, None, F, F, 0, None)])
-                TrainMLP._dw(g.row0, n, F, rows, F, sink.of(Wk), F, F, 0, F, dev)
+                TrainMLP._dw_square(g.row0, n, F, rows, sink.of(Wk), dev)
                 da = Arr.empty(n, F, lo, dev)
-                lib.node_linear_fwd(g.addr, lo, n, Wk.detach().contiguous(), da.addr, F)
+                _node_linear_bwd(g, lo, n, Wk, da, F)
             else:
                 da = g
             flags = torch.empty(lo + n, dtype=torch.uint8, device=dev)
@@ -496,13 +523,13 @@ def swegnn_backward(c: SweCall, g_out: Arr, d_xs: Arr, d_xd_src: Arr, d_xd_src_a
         if mod.with_filter_matrix:
             W0 = mod.filter_matrix[0].weight
             rows = lib.make_rows([(c.xd_dst.addr + lo * F * 4, None, F, F, 0, None)])
-            TrainMLP._dw(g.row0, n, F, rows, F, sink.of(W0), F, F, 0, F, dev)
+            TrainMLP._dw_square(g.row0, n, F, rows, sink.of(W0), dev)
             if d_xd_src_accumulate:
                 tmp = Arr.empty(n, F, lo, dev)
-                lib.node_linear_fwd(g.addr, lo, n, W0.detach().contiguous(), tmp.addr, F)
+                _node_linear_bwd(g, lo, n, W0, tmp, F)
                 _add_rows(d_xd_src, tmp, lo, n, F)
             else:
-                lib.node_linear_fwd(g.addr, lo, n, W0.detach().contiguous(), d_xd_src.addr, F)
+                _node_linear_bwd(g, lo, n, W0, d_xd_src, F)
         else:
             if d_xd_src_accumulate:
                 _add_rows(d_xd_src, g, lo, n, F)

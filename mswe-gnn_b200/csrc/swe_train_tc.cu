@@ -154,20 +154,45 @@ __global__ void __launch_bounds__(DW_THREADS, 1) mlp_dw_tc_kernel(const __grid_c
         const int nq = qw / 64;                                  // Q chunks of 16 B per thread and stage
         const int qpr = qw / 4;                                  // 16-B chunks per Q row
         const int npc = pw / 64, ppr = pw / 4;                   // the same for P
+        // everything about a thread's chunks that does not depend on the stage, once: source segment (pointer to its
+        // column, row index map, row pitch, slope), row inside the stage, byte offset in the stage
+        // 512 threads cover a stage in passes of 512 chunks; the row pitch in chunks (16, 32 or 64) divides 512, so a
+        // thread keeps its column — hence its source segment — over the passes and only its row advances.  Everything
+        // that does not depend on the stage is computed once: segment column pointer, row map, pitch, slope, first
+        // row and its byte offset in the stage.
+        const int prow = t / ppr, pch = t % ppr, pstep = DW_ROW_THREADS / ppr;      // rows per pass
+        const int qrow = t / qpr, qch = t % qpr, qstep = DW_ROW_THREADS / qpr;
+        const SegS& sgp = prP->seg[prP->seg_of_panel[(pch * 4) >> 5]];
+        const SegS& sgq = prQ->seg[prQ->seg_of_panel[(qch * 4) >> 5]];
+        const float* const pb = sgp.base + (pch * 4 - sgp.col0);
+        const float* const qb = sgq.base + (qch * 4 - sgq.col0);
+        const int32_t* const pi = sgp.idx; const int32_t* const qi = sgq.idx;
+        const int pld = sgp.ld, qld = sgq.ld;
+        const float psl = sgp.slope, qsl = sgq.slope;
+        const uint32_t poff = (uint32_t)((pch >> 3) * DW_PANEL) + mn32b_offset(prow, pch & 7);
+        const uint32_t qoff = (uint32_t)(2 * DW_P_BYTES + (qch >> 3) * DW_PANEL) + mn32b_offset(qrow, qch & 7);
+        // (a row step that is a multiple of 4 keeps the swizzle phase: the offset advances by 128 B per row)
+#define SWE_CHUNK_ADDR(base_, idx_, ld_, row_, row0_, out_) do {                             \
+            long long g_ = (row0_) + (row_);                                                  \
+            if (g_ >= p.n_rows) g_ = p.n_rows - 1;             /* clamped; zeroed when stored */ \
+            long long r_ = g_;                                                                \
+            if (idx_) r_ = (long long)__ldg((idx_) + g_);                                     \
+            out_ = (base_) + r_ * (ld_);                                                      \
+        } while (0)
+#define SWE_CHUNK_FINISH(slope_, row_, v_, row0_) do {                                        \
+            const bool in_ = (row0_) + (row_) < p.n_rows;                                     \
+            const float keep_ = in_ ? 1.f : 0.f, sl_ = in_ ? (slope_) : 0.f;                  \
+            v_.x = keep_ * fmaxf(v_.x, 0.f) + sl_ * fminf(v_.x, 0.f); v_.y = keep_ * fmaxf(v_.y, 0.f) + sl_ * fminf(v_.y, 0.f); \
+            v_.z = keep_ * fmaxf(v_.z, 0.f) + sl_ * fminf(v_.z, 0.f); v_.w = keep_ * fmaxf(v_.w, 0.f) + sl_ * fminf(v_.w, 0.f); \
+        } while (0)
         float4 cp[2], cq[4], np[2], nq4[4];
         auto issue = [&](int i, float4 (&vp)[2], float4 (&vq)[4]) {
             const long long row0 = ((long long)blockIdx.x + (long long)i * gridDim.x) * DW_RS;
             const float* ap[2]; const float* aq[4];
 #pragma unroll
-            for (int j = 0; j < 2; ++j) {
-                const int q = t + DW_ROW_THREADS * (j < npc ? j : 0);
-                ap[j] = provider_addr(prP, row0 + q / ppr, p.n_rows, (q % ppr) * 4);
-            }
+            for (int j = 0; j < 2; ++j) SWE_CHUNK_ADDR(pb, pi, pld, prow + (j < npc ? j : 0) * pstep, row0, ap[j]);
 #pragma unroll
-            for (int j = 0; j < 4; ++j) {
-                const int q = t + DW_ROW_THREADS * (j < nq ? j : 0);
-                aq[j] = provider_addr(prQ, row0 + q / qpr, p.n_rows, (q % qpr) * 4);
-            }
+            for (int j = 0; j < 4; ++j) SWE_CHUNK_ADDR(qb, qi, qld, qrow + (j < nq ? j : 0) * qstep, row0, aq[j]);
 #pragma unroll
             for (int j = 0; j < 2; ++j)
                 if (j < npc) vp[j] = ldg4(ap[j]);
@@ -187,23 +212,21 @@ __global__ void __launch_bounds__(DW_THREADS, 1) mlp_dw_tc_kernel(const __grid_c
             unsigned char* st = ring + (size_t)slot * DW_STAGE_BYTES;
             const long long row0 = ((long long)blockIdx.x + (long long)i * gridDim.x) * DW_RS;
 #pragma unroll
-            for (int j = 0; j < 2; ++j) {
+            for (int j = 0; j < 2; ++j)
                 if (j < npc) {
-                    const int q = t + DW_ROW_THREADS * j;
-                    const int row = q / ppr, ch = q % ppr;
-                    unsigned char* d = st + (ch >> 3) * DW_PANEL + mn32b_offset(row, ch & 7);
-                    split_store4(d, d + DW_P_BYTES, provider_finish(prP, vp[j], row0 + row, p.n_rows, ch * 4));
+                    float4 v = vp[j];
+                    SWE_CHUNK_FINISH(psl, prow + j * pstep, v, row0);
+                    unsigned char* d = st + poff + j * pstep * 128;
+                    split_store4(d, d + DW_P_BYTES, v);
                 }
-            }
 #pragma unroll
-            for (int j = 0; j < 4; ++j) {
+            for (int j = 0; j < 4; ++j)
                 if (j < nq) {
-                    const int q = t + DW_ROW_THREADS * j;
-                    const int row = q / qpr, ch = q % qpr;
-                    unsigned char* d = st + 2 * DW_P_BYTES + (ch >> 3) * DW_PANEL + mn32b_offset(row, ch & 7);
-                    split_store4(d, d + DW_Q_BYTES, provider_finish(prQ, vq[j], row0 + row, p.n_rows, ch * 4));
+                    float4 v = vq[j];
+                    SWE_CHUNK_FINISH(qsl, qrow + j * qstep, v, row0);
+                    unsigned char* d = st + qoff + j * qstep * 128;
+                    split_store4(d, d + DW_Q_BYTES, v);
                 }
-            }
             fence_proxy_async_smem();
             mbar_arrive(&bar->full[slot]);
         };
@@ -222,6 +245,8 @@ __global__ void __launch_bounds__(DW_THREADS, 1) mlp_dw_tc_kernel(const __grid_c
             }
         }
         // ---- epilogue: TMEM lane m = feature of P, columns = features of Q -> per-CTA partial of dW
+#undef SWE_CHUNK_ADDR
+#undef SWE_CHUNK_FINISH
         if (n_my > 0) {
             mbar_wait(&bar->d_full, 0);
             tc_fence_after_sync();
@@ -466,7 +491,7 @@ extern "C" int swe_mlp_layer_bwd_dw_tc(const float* delta, int64_t n_rows, int32
     SWE_REQUIRE(aligned16(delta) && aligned16(part), SWE_E_ALIGN, "mlp_layer_bwd_dw_tc: unaligned buffer");
     const int xw = provider_width_tc(X);
     SWE_REQUIRE(xw > 0, SWE_E_UNSUPP, "mlp_layer_bwd_dw_tc: provider segments must be 32-column multiples with a leaky-family activation");
-    SWE_REQUIRE((n == 128 || n == 64) && xw <= 256 && xw % 64 == 0, SWE_E_UNSUPP,
+    SWE_REQUIRE((n == 128 || n == 64) && (xw == 64 || xw == 128 || xw == 256), SWE_E_UNSUPP,
                 "mlp_layer_bwd_dw_tc: unsupported shape n=%d, provider width %d", n, xw);
     if (grid_out) *grid_out = 0;
     if (n_rows == 0) return 0;

@@ -237,6 +237,20 @@ def test_training_step_is_bit_reproducible():
         assert torch.equal(grads[0][k], grads[1][k]), k
 
 
+def test_training_step_all_levels_on_tensor_cores(monkeypatch):
+    """MSWE_TC_MIN_ROWS=1: also the small levels and the 64 x 64 node-level GEMMs (hop filters, encoders) take the
+    tensor-core kernels (by default only levels with >= 16384 rows do)."""
+    monkeypatch.setenv("MSWE_TC_MIN_ROWS", "1")
+    ctor = dict(num_node_features=8, num_edge_features=1, num_scales=4, previous_t=3, **REF_CONFIG_MODELS)
+    data = make_tri_mesh(16, 16, 4, rollout_steps=1, seed=5)
+    _train_compare("MSGNN", ctor, data, 1)
+    ctor = dict(num_node_features=8, num_edge_features=1, previous_t=3, hid_features=64, K=3, n_GNN_layers=2,
+                mlp_layers=3, seed=7, learned_residuals="all", mlp_activation="prelu", gnn_activation="prelu",
+                with_WL=True)
+    data = make_single_scale_mesh(18, 14, rollout_steps=2, seed=6)
+    _train_compare("GNN", ctor, data, 2)
+
+
 def test_training_step_exact_fp32_path(monkeypatch):
     """MSWE_TRAIN_GEMM=ffma: every training GEMM on the exact-fp32 CUDA-core kernels."""
     monkeypatch.setenv("MSWE_TRAIN_GEMM", "ffma")

@@ -100,7 +100,7 @@ def test_dw_tc_gathered_segments(n_rows):
 
 
 @pytest.mark.parametrize("n,act,xw", [(128, "prelu", 128), (64, "prelu", 128), (64, "relu", 128), (128, "none", 128),
-                                      (64, "prelu", 64), (64, "none", 192)])
+                                      (64, "prelu", 64), (64, "none", 256)])
 def test_dw_tc_activation_on_load(n, act, xw):
     """X = act(pre) (layers 1 and 2 of the edge MLP; n = 64 against 128 columns runs with the operand roles
     swapped, n = 64 otherwise as a zero-padded 128-row operand)."""

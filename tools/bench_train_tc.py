@@ -66,3 +66,15 @@ gf = lib.mlp_layer_bwd_dw_grid(E)
 partf = torch.empty(gf * 128 * 128, device=DEV)
 t = timeit(lambda: lib.mlp_layer_bwd_dw(delta, E, 128, rows1, 128, partf))
 print(f"dw_ffma n=128 X=act(pre)128 {t:.3f} ms  {2*E*128*128/t/1e9:.1f} TFLOP/s")
+rows64p = lib.make_rows([(pre[:, :64].contiguous(), None, 64, 64, 1, None)])
+t = timeit(lambda: lib.mlp_layer_bwd_dw_tc(delta64, E, 64, rows64p, part))
+print(f"dw_tc  n=64  X=act(pre)64  {t:.3f} ms  {2*E*64*64/t/1e9:.1f} TFLOP/s")
+partf64 = torch.empty(gf * 64 * 64, device=DEV)
+t = timeit(lambda: lib.mlp_layer_bwd_dw(delta64, E, 64, rows64p, 64, partf64))
+print(f"dw_ffma n=64 X=act(pre)64  {t:.3f} ms  {2*E*64*64/t/1e9:.1f} TFLOP/s")
+w64 = torch.randn(64, 64, device=DEV) * 0.1
+dx64 = torch.empty(E, 64, device=DEV)
+t = timeit(lambda: lib.mlp_layer_bwd_dx_tc(delta64, E, 64, w64, 64, 0, 64, 64, dx64, False))
+print(f"dx_tc  n=64  ko=64         {t:.3f} ms  {2*E*64*64/t/1e9:.1f} TFLOP/s")
+t = timeit(lambda: lib.mlp_layer_bwd_dx(delta64, None, 0, None, E, 64, w64, 64, 0, 64, 64, dx64, False, False, None))
+print(f"dx_ffma n=64 ko=64         {t:.3f} ms  {2*E*64*64/t/1e9:.1f} TFLOP/s")
