@@ -522,7 +522,7 @@ def profile_train_kernels(step_fn):
     from mswe_gnn_b200 import lib
     records, orig = [], {}
     names = [n[4:] for n in lib.SIGNATURES if n.startswith("swe_") and hasattr(lib, n[4:]) and callable(getattr(lib, n[4:]))
-             and n[4:] not in ("mlp_layer_bwd_dx_grid", "mlp_layer_bwd_dw_grid", "mlp_layer_bwd_dw_tc_grid", "gate_tc_image_bytes", "hop_tc_image_bytes", "csr_build")]
+             and n[4:] not in ("mlp_layer_bwd_dx_grid", "mlp_layer_bwd_dw_grid", "mlp_layer_bwd_dw_tc_grid", "mlp_layer_bwd_dx_tc_grid", "gate_tc_image_bytes", "hop_tc_image_bytes", "csr_build")]
 
     def wrap(name):
         fn = getattr(lib, name)
@@ -540,6 +540,8 @@ def profile_train_kernels(step_fn):
                 fl = 2.0 * a[1] * a[2] * a[4]
             elif name == "mlp_layer_fwd":
                 fl = 2.0 * a[1] * a[4] * sum(a[0].seg[j].width for j in range(a[0].n_seg))
+            elif name == "mlp_layer_bwd_dx_tc_fused":
+                fl = 2.0 * a[4] * a[5] * a[10]
             elif name == "mlp_layer_bwd_dx_tc":
                 fl = 2.0 * a[1] * a[2] * a[7]
             elif name == "mlp_layer_bwd_dw_tc":

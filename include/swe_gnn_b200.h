@@ -354,6 +354,14 @@ int swe_gate_fix_preacts(const float* xs, const float* xd_src, const float* xd_d
 int swe_mlp_layer_bwd_dx_tc(const float* delta, int64_t n_rows, int32_t n, const float* w, int32_t w_ld,
                             int32_t k_off, int32_t k_valid, int32_t ko, float* dx0, int32_t accumulate0, float* dx1,
                             int32_t accumulate1, int32_t split, void* stream);
+/* dx_tc that forms delta = dh ⊙ act'(pre) itself while staging the rows (act in none/relu/leakyrelu/prelu): dh is
+ * overwritten with delta (the input of dw_tc), part receives [grid][n + 1] per-CTA partial sums of delta (bias
+ * gradient) and, last slot, of dh·pre over pre <= 0 (PReLU slope gradient) — what swe_mlp_layer_bwd_dx returns. */
+int swe_mlp_layer_bwd_dx_tc_fused(float* dh, const float* pre, int32_t act, const float* slope, int64_t n_rows,
+                                  int32_t n, const float* w, int32_t w_ld, int32_t k_off, int32_t k_valid, int32_t ko,
+                                  float* dx0, int32_t accumulate0, float* dx1, int32_t accumulate1, int32_t split,
+                                  float* part, int32_t* grid_out, void* stream);
+int swe_mlp_layer_bwd_dx_tc_grid(int64_t n_rows);
 int swe_mlp_layer_bwd_dw_tc(const float* delta, int64_t n_rows, int32_t n, const swe_rows_t* X, float* part,
                             int32_t* grid_out, void* stream);
 int swe_mlp_layer_bwd_dw_tc_grid(int64_t n_rows);

@@ -46,6 +46,12 @@ def train_gemm_backend() -> str:
     return os.environ.get("MSWE_TRAIN_GEMM", "tc")
 
 
+def _fuse_delta() -> bool:
+    """MSWE_TRAIN_FUSE_DELTA=0: form delta = dh ⊙ act'(pre) in a separate element-wise pass instead of inside dx_tc."""
+    import os
+    return os.environ.get("MSWE_TRAIN_FUSE_DELTA", "1") != "0"
+
+
 def _min_rows() -> int:
     """Row count below which the training GEMMs stay on CUDA cores (the tensor-core kernels' fixed cost — a weight
     image per CTA, one CTA per 128 rows — is not paid back on the small coarse levels); MSWE_TC_MIN_ROWS overrides."""
@@ -238,7 +244,13 @@ class TrainMLP:
                 prev_act = self.act_code(li - 1)
                 tc = tc_dx_on and n in (64, 128) and ko in (64, 128) and n_rows >= _min_rows()
                 tc_dw = tc_dw_on and prev_act in _TC_ACTS and n in (64, 128) and ko in (64, 128) and n_rows >= _min_rows()
-                if tc:
+                if tc and act in _TC_ACTS and _fuse_delta():
+                    # delta (in place), bias / slope partials and the GEMM in one pass over the rows
+                    grid = lib.mlp_layer_bwd_dx_tc_grid(n_rows)
+                    part = torch.empty(max(grid, 1) * (n + 1), dtype=torch.float32, device=dev)
+                    lib.mlp_layer_bwd_dx_tc_fused(dh, pres[li], act, slope, n_rows, n, self.w_rm[li], self.w_rm[li].shape[1], 0,
+                                                  ko, ko, dx, False, None, False, None, part)
+                elif tc:
                     # delta (in place) + bias / slope partials on CUDA cores (element-wise), the GEMM on tensor cores
                     lib.mlp_layer_bwd_dx(dh, pres[li], act, slope, n_rows, n, self.w_rm[li], self.w_rm[li].shape[1], 0, 16, 16,
                                          None, False, True, part)
@@ -271,24 +283,29 @@ class TrainMLP:
                 for j in range(1, nb):
                     col0[j] = col0[j - 1] + self.block_pad[j - 1]
                 ld0 = self.w_rm[0].shape[1]
-                if tc or tc_dw:
+                fuse = tc and act in _TC_ACTS and _fuse_delta() and any(o is not None for o in outs)
+                if (tc or tc_dw) and not fuse:
                     lib.mlp_layer_bwd_dx(dh, pres[0], act, slope, n_rows, n, self.w_rm[0], ld0, 0, 16, 16, None, False, True,
                                          part)
                 if tc:
-                    # input gradients: two 64-wide neighbours per pass where possible
+                    # input gradients: two 64-wide neighbours per pass where possible; the first pass also forms delta
                     j = 0
                     while j < nb:
                         if outs[j] is None:
                             j += 1
                             continue
                         wj = self.block_pad[j]
-                        if wj == 64 and j + 1 < nb and outs[j + 1] is not None and self.block_pad[j + 1] == 64:
-                            lib.mlp_layer_bwd_dx_tc(dh, n_rows, n, self.w_rm[0], ld0, col0[j], 128, 128, outs[j], accs[j],
-                                                    outs[j + 1], accs[j + 1], 64)
-                            j += 2
+                        pair = wj == 64 and j + 1 < nb and outs[j + 1] is not None and self.block_pad[j + 1] == 64
+                        args = (n_rows, n, self.w_rm[0], ld0, col0[j], 128 if pair else wj, 128 if pair else wj, outs[j], accs[j],
+                                outs[j + 1] if pair else None, accs[j + 1] if pair else False, 64 if pair else None)
+                        if fuse:
+                            grid = lib.mlp_layer_bwd_dx_tc_grid(n_rows)
+                            part = torch.empty(max(grid, 1) * (n + 1), dtype=torch.float32, device=dev)
+                            lib.mlp_layer_bwd_dx_tc_fused(dh, pres[0], act, slope, *args, part)
+                            fuse = False
                         else:
-                            lib.mlp_layer_bwd_dx_tc(dh, n_rows, n, self.w_rm[0], ld0, col0[j], wj, wj, outs[j], accs[j])
-                            j += 1
+                            lib.mlp_layer_bwd_dx_tc(dh, *args)
+                        j += 2 if pair else 1
                 else:
                     first = not tc_dw                       # (delta already finished when the dW side runs on tensor cores)
                     for j in range(nb):

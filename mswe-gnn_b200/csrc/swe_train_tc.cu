@@ -320,8 +320,12 @@ struct DxTcParams {
     const float* delta; long long n_rows; int n;
     const float* w; int w_ld, k_off, k_valid, ko;
     float* out0; float* out1; int split, acc0, acc1;      // columns [0, split) -> out0 [*, split], the rest -> out1
+    // FUSED: delta = dh ⊙ act'(pre) is formed while the rows are staged (written back over dh for the dW kernel) and
+    // the per-CTA partial sums of the bias / PReLU-slope gradients are produced on the way: part[cta][n + 1]
+    float* dh; const float* pre; const float* slope_p; int act; float* part;
 };
 
+template <bool FUSED>
 __global__ void __launch_bounds__(TR_THREADS, 1) mlp_dx_tc_kernel(const __grid_constant__ DxTcParams p) {
     extern __shared__ unsigned char smem_raw[];
     unsigned char* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
@@ -363,29 +367,59 @@ __global__ void __launch_bounds__(TR_THREADS, 1) mlp_dx_tc_kernel(const __grid_c
         const int piece = threadIdx.x & 7, r0 = threadIdx.x >> 3;
         const uint32_t g_off0 = sw128_offset(r0, piece * 4);
         uint32_t a_cnt = 0;
+        const float fslope = FUSED ? leaky_slope_of(p.act, p.slope_p) : 1.f;
+        const bool prelu = FUSED && p.act == SWE_ACT_PRELU;
+        float bacc[4][4];                                          // FUSED: Σ_rows delta of this thread's 4 columns per chunk
+        float sacc = 0.f;                                          //        Σ dh · pre over pre <= 0 (PReLU slope gradient)
+#pragma unroll
+        for (int c = 0; c < 4; ++c) { bacc[c][0] = bacc[c][1] = bacc[c][2] = bacc[c][3] = 0.f; }
         auto stage = [&](int i) {
             const long long row0 = ((long long)blockIdx.x + (long long)i * gridDim.x) * 128;
-            auto issue = [&](int c, float4 (&v)[4]) {
+            auto issue = [&](int c, float4 (&v)[4], float4 (&pv)[4]) {
 #pragma unroll
                 for (int j = 0; j < 4; ++j) {
                     const long long g = row0 + r0 + 32 * j;
-                    v[j] = g < p.n_rows ? ldg4_stream(p.delta + g * n + c * 32 + piece * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
+                    const long long at = g * n + c * 32 + piece * 4;
+                    if (FUSED) {
+                        v[j] = g < p.n_rows ? *reinterpret_cast<const float4*>(p.dh + at) : make_float4(0.f, 0.f, 0.f, 0.f);
+                        pv[j] = g < p.n_rows ? ldg4_stream(p.pre + at) : make_float4(1.f, 1.f, 1.f, 1.f);
+                    } else {
+                        v[j] = g < p.n_rows ? ldg4_stream(p.delta + at) : make_float4(0.f, 0.f, 0.f, 0.f);
+                    }
                 }
             };
-            float4 cur[4], nxt[4];
-            issue(0, cur);
-#pragma unroll 1
-            for (int c = 0; c < n_chunks; ++c, ++a_cnt) {
-                if (c + 1 < n_chunks) issue(c + 1, nxt);
-                const uint32_t slot = a_cnt % DX_A_STAGES;
-                mbar_wait(&bar->a_empty[slot], ((a_cnt / DX_A_STAGES) & 1) ^ 1);
-                unsigned char* hi_t = a_ring + (size_t)slot * DX_SLOT + g_off0;
+            float4 cur[4], nxt[4], pnx[4];
+            issue(0, nxt, pnx);
 #pragma unroll
-                for (int j = 0; j < 4; ++j) split_store4(hi_t + j * 4096, hi_t + DX_SLOT / 2 + j * 4096, cur[j]);
-                fence_proxy_async_smem();
-                mbar_arrive(&bar->a_full[slot]);
+            for (int c = 0; c < 4; ++c) {
+                if (c < n_chunks) {
+                    // raw loads of chunk c -> delta (+ partial sums, + write-back)
 #pragma unroll
-                for (int j = 0; j < 4; ++j) cur[j] = nxt[j];
+                    for (int j = 0; j < 4; ++j) {
+                        float4 d = nxt[j];
+                        if (FUSED) {
+                            const float4 q = pnx[j];
+                            if (prelu)
+                                sacc += (q.x > 0.f ? 0.f : d.x * q.x) + (q.y > 0.f ? 0.f : d.y * q.y) +
+                                        (q.z > 0.f ? 0.f : d.z * q.z) + (q.w > 0.f ? 0.f : d.w * q.w);
+                            d.x *= q.x > 0.f ? 1.f : fslope; d.y *= q.y > 0.f ? 1.f : fslope;
+                            d.z *= q.z > 0.f ? 1.f : fslope; d.w *= q.w > 0.f ? 1.f : fslope;
+                            bacc[c][0] += d.x; bacc[c][1] += d.y; bacc[c][2] += d.z; bacc[c][3] += d.w;
+                            const long long g = row0 + r0 + 32 * j;
+                            if (g < p.n_rows) stg4(p.dh + g * n + c * 32 + piece * 4, d);
+                        }
+                        cur[j] = d;
+                    }
+                    if (c + 1 < n_chunks) issue(c + 1, nxt, pnx);
+                    const uint32_t slot = a_cnt % DX_A_STAGES;
+                    mbar_wait(&bar->a_empty[slot], ((a_cnt / DX_A_STAGES) & 1) ^ 1);
+                    unsigned char* hi_t = a_ring + (size_t)slot * DX_SLOT + g_off0;
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) split_store4(hi_t + j * 4096, hi_t + DX_SLOT / 2 + j * 4096, cur[j]);
+                    fence_proxy_async_smem();
+                    mbar_arrive(&bar->a_full[slot]);
+                    ++a_cnt;
+                }
             }
         };
         const int qd = warp & 3, hf = warp >> 2;
@@ -422,6 +456,29 @@ __global__ void __launch_bounds__(TR_THREADS, 1) mlp_dx_tc_kernel(const __grid_c
         for (int i = 0; i < n_my; ++i) {
             if (i + 1 < n_my) stage(i + 1);
             epilogue(i);
+        }
+        if (FUSED && p.part) {
+            // every MMA has completed (the last epilogue waited for it): the operand ring is free and serves as the
+            // scratch of a fixed-order reduction over the 32 threads that share a column
+            float* red = reinterpret_cast<float*>(a_ring);
+            asm volatile("bar.sync 1, 256;" ::: "memory");
+#pragma unroll
+            for (int c = 0; c < 4; ++c)
+#pragma unroll
+                for (int u = 0; u < 4; ++u) red[r0 * 128 + c * 32 + piece * 4 + u] = bacc[c][u];
+            red[32 * 128 + threadIdx.x] = sacc;
+            asm volatile("bar.sync 1, 256;" ::: "memory");
+            float* my = p.part + (long long)blockIdx.x * (n + 1);
+            if ((int)threadIdx.x < n) {
+                float t = 0.f;
+                for (int r = 0; r < 32; ++r) t += red[r * 128 + threadIdx.x];
+                my[threadIdx.x] = t;
+            }
+            if (threadIdx.x == 0) {
+                float t = 0.f;
+                for (int r = 0; r < TR_ROW_THREADS; ++r) t += red[32 * 128 + r];
+                my[n] = t;
+            }
         }
     } else if (lane == 0) {
         const uint32_t idesc = make_idesc_tf32(128, ko);
@@ -515,6 +572,17 @@ extern "C" int swe_mlp_layer_bwd_dw_tc(const float* delta, int64_t n_rows, int32
     return check_launch("mlp_layer_bwd_dw_tc");
 }
 
+static int dx_tc_launch(tc::DxTcParams& p, bool fused, void* stream, const char* what) {
+    void (*kern)(const tc::DxTcParams) = fused ? tc::mlp_dx_tc_kernel<true> : tc::mlp_dx_tc_kernel<false>;
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc::DX_TC_SMEM);
+    if (e != cudaSuccess) { set_error("%s smem opt-in (%zu B): %s", what, tc::DX_TC_SMEM, cudaGetErrorString(e)); return (int)e; }
+    const long long n_tiles = (p.n_rows + 127) / 128;
+    kern<<<grid_for(n_tiles, 1), tc::TR_THREADS, tc::DX_TC_SMEM, (cudaStream_t)stream>>>(p);
+    return check_launch(what);
+}
+
+extern "C" int swe_mlp_layer_bwd_dx_tc_grid(int64_t n_rows) { return grid_for((n_rows + 127) / 128, 1); }
+
 extern "C" int swe_mlp_layer_bwd_dx_tc(const float* delta, int64_t n_rows, int32_t n, const float* w, int32_t w_ld,
                                        int32_t k_off, int32_t k_valid, int32_t ko, float* dx0, int32_t accumulate0,
                                        float* dx1, int32_t accumulate1, int32_t split, void* stream) {
@@ -528,9 +596,27 @@ extern "C" int swe_mlp_layer_bwd_dx_tc(const float* delta, int64_t n_rows, int32
     memset(&p, 0, sizeof(p));
     p.delta = delta; p.n_rows = n_rows; p.n = n; p.w = w; p.w_ld = w_ld; p.k_off = k_off; p.k_valid = k_valid; p.ko = ko;
     p.out0 = dx0; p.out1 = dx1; p.split = split; p.acc0 = accumulate0; p.acc1 = accumulate1;
-    cudaError_t e = cudaFuncSetAttribute(tc::mlp_dx_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc::DX_TC_SMEM);
-    if (e != cudaSuccess) { set_error("mlp_layer_bwd_dx_tc smem opt-in (%zu B): %s", tc::DX_TC_SMEM, cudaGetErrorString(e)); return (int)e; }
-    const long long n_tiles = (n_rows + 127) / 128;
-    tc::mlp_dx_tc_kernel<<<grid_for(n_tiles, 1), tc::TR_THREADS, tc::DX_TC_SMEM, (cudaStream_t)stream>>>(p);
-    return check_launch("mlp_layer_bwd_dx_tc");
+    return dx_tc_launch(p, false, stream, "mlp_layer_bwd_dx_tc");
+}
+
+extern "C" int swe_mlp_layer_bwd_dx_tc_fused(float* dh, const float* pre, int32_t act, const float* slope, int64_t n_rows,
+                                             int32_t n, const float* w, int32_t w_ld, int32_t k_off, int32_t k_valid,
+                                             int32_t ko, float* dx0, int32_t accumulate0, float* dx1, int32_t accumulate1,
+                                             int32_t split, float* part, int32_t* grid_out, void* stream) {
+    SWE_REQUIRE(dh && pre && w && dx0 && n_rows >= 0, SWE_E_INVAL, "mlp_layer_bwd_dx_tc_fused: bad arguments");
+    SWE_REQUIRE((n == 64 || n == 128) && (ko == 64 || ko == 128), SWE_E_UNSUPP, "mlp_layer_bwd_dx_tc_fused: n=%d ko=%d", n, ko);
+    SWE_REQUIRE(leaky_family(act), SWE_E_UNSUPP, "mlp_layer_bwd_dx_tc_fused: activation %d", act);
+    SWE_REQUIRE(split == ko || (split == 64 && ko == 128 && dx1), SWE_E_INVAL, "mlp_layer_bwd_dx_tc_fused: split=%d ko=%d", split, ko);
+    SWE_REQUIRE(k_valid >= 0 && k_valid <= ko && k_off >= 0 && k_off + k_valid <= w_ld, SWE_E_INVAL, "mlp_layer_bwd_dx_tc_fused: column range");
+    SWE_REQUIRE(aligned16(dh) && aligned16(pre) && aligned16(dx0) && (!dx1 || aligned16(dx1)), SWE_E_ALIGN,
+                "mlp_layer_bwd_dx_tc_fused: unaligned buffer");
+    if (grid_out) *grid_out = 0;
+    if (n_rows == 0) return 0;
+    tc::DxTcParams p;
+    memset(&p, 0, sizeof(p));
+    p.delta = dh; p.n_rows = n_rows; p.n = n; p.w = w; p.w_ld = w_ld; p.k_off = k_off; p.k_valid = k_valid; p.ko = ko;
+    p.out0 = dx0; p.out1 = dx1; p.split = split; p.acc0 = accumulate0; p.acc1 = accumulate1;
+    p.dh = dh; p.pre = pre; p.slope_p = slope; p.act = act; p.part = part;
+    if (grid_out) *grid_out = swe_mlp_layer_bwd_dx_tc_grid(n_rows);
+    return dx_tc_launch(p, true, stream, "mlp_layer_bwd_dx_tc_fused");
 }

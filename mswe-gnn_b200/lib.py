@@ -107,6 +107,9 @@ SIGNATURES = {
     "swe_gate_fix_preacts": (C.c_int, [_p] * 12 + [_i32, C.POINTER(C.c_int32), C.POINTER(C.c_void_p), _p, _p, _p, _p, _p,
                                        _i32, _p]),
     "swe_mlp_layer_bwd_dx_tc": (C.c_int, [_p, _i64, _i32, _p, _i32, _i32, _i32, _i32, _p, _i32, _p, _i32, _i32, _p]),
+    "swe_mlp_layer_bwd_dx_tc_fused": (C.c_int, [_p, _p, _i32, _p, _i64, _i32, _p, _i32, _i32, _i32, _i32, _p, _i32, _p, _i32,
+                                                _i32, _p, _pi32, _p]),
+    "swe_mlp_layer_bwd_dx_tc_grid": (C.c_int, [_i64]),
     "swe_mlp_layer_bwd_dw_tc": (C.c_int, [_p, _i64, _i32, _rows, _p, _pi32, _p]),
     "swe_mlp_layer_bwd_dw_tc_grid": (C.c_int, [_i64]),
     "swe_reduce_partials": (C.c_int, [_p, _i32, _i64, _i32, _i32, _i32, _i32, _p, _i32, _i32, _p]),
@@ -419,6 +422,19 @@ def mlp_layer_bwd_dx_tc(delta, n_rows, n, w, w_ld, k_off, k_valid, ko, dx0, acc0
     _check(load().swe_mlp_layer_bwd_dx_tc(_addr(delta), n_rows, n, _addr(w), w_ld, k_off, k_valid, ko, _addr(dx0), int(acc0),
                                           _addr(dx1), int(acc1), ko if split is None else split, _stream()),
            "swe_mlp_layer_bwd_dx_tc")
+
+
+def mlp_layer_bwd_dx_tc_fused(dh, pre, act, slope, n_rows, n, w, w_ld, k_off, k_valid, ko, dx0, acc0, dx1, acc1, split, part):
+    g = C.c_int32(0)
+    _check(load().swe_mlp_layer_bwd_dx_tc_fused(_addr(dh), _addr(pre), act, ptr(slope), n_rows, n, _addr(w), w_ld, k_off,
+                                                k_valid, ko, _addr(dx0), int(acc0), _addr(dx1), int(acc1),
+                                                ko if split is None else split, _addr(part), C.byref(g), _stream()),
+           "swe_mlp_layer_bwd_dx_tc_fused")
+    return g.value
+
+
+def mlp_layer_bwd_dx_tc_grid(n_rows) -> int:
+    return int(load().swe_mlp_layer_bwd_dx_tc_grid(n_rows))
 
 
 def mlp_layer_bwd_dw_tc(delta, n_rows, n, rows: SweRows, part):

@@ -149,3 +149,44 @@ def test_tc_rejects_unsupported_shapes():
         lib.mlp_layer_bwd_dw_tc(delta, 10, 96, rows, part)
     with pytest.raises(RuntimeError):
         lib.mlp_layer_bwd_dx_tc(delta, 10, 96, delta, 96, 0, 64, 64, part, False)
+
+
+@pytest.mark.parametrize("act", ["prelu", "relu", "none"])
+@pytest.mark.parametrize("n_rows,n,ko,split", [(1, 128, 128, 128), (5000, 64, 64, 64), (70_001, 128, 128, 64), (33_333, 64, 128, 128)])
+def test_dx_tc_fused_delta_matches_separate_pass(n_rows, n, ko, split, act):
+    """dx_tc forming delta = dh ⊙ act'(pre) itself: delta bit-identical to the element-wise CUDA-core pass, dx equal to
+    the unfused tensor-core result, bias / slope partial sums within fp32 summation-order noise."""
+    g = torch.Generator(device="cpu").manual_seed(n_rows + n)
+    dh0 = torch.randn(n_rows, n, generator=g).to(DEV)
+    pre = torch.randn(n_rows, n, generator=g).to(DEV)
+    w = (torch.randn(n, 256, generator=g) * 0.1).to(DEV)
+    slope = torch.tensor([0.2], device=DEV)
+    code = _act_code(act)
+    sl = slope if act == "prelu" else None
+    # reference: separate delta pass + unfused dx_tc
+    dh_a = dh0.clone()
+    grid_a = lib.mlp_layer_bwd_dx_grid(n_rows)
+    part_a = torch.zeros(grid_a * (n + 1), device=DEV)
+    lib.mlp_layer_bwd_dx(dh_a, pre, code, sl, n_rows, n, w, 256, 0, 16, 16, None, False, True, part_a)
+    outs_a = [torch.zeros(n_rows, split, device=DEV), torch.ones(n_rows, ko - split, device=DEV) if split != ko else None]
+    lib.mlp_layer_bwd_dx_tc(dh_a, n_rows, n, w, 256, 32, ko, ko, outs_a[0], False, outs_a[1], True, split)
+    # fused
+    dh_b = dh0.clone()
+    grid_b = lib.mlp_layer_bwd_dx_tc_grid(n_rows)
+    part_b = torch.full((grid_b * (n + 1),), float("nan"), device=DEV)
+    outs_b = [torch.zeros(n_rows, split, device=DEV), torch.ones(n_rows, ko - split, device=DEV) if split != ko else None]
+    assert lib.mlp_layer_bwd_dx_tc_fused(dh_b, pre, code, sl, n_rows, n, w, 256, 32, ko, ko, outs_b[0], False, outs_b[1], True,
+                                         split, part_b) == grid_b
+    torch.cuda.synchronize()
+    assert torch.equal(dh_a, dh_b)
+    assert torch.equal(outs_a[0], outs_b[0])
+    if outs_a[1] is not None:
+        assert torch.equal(outs_a[1], outs_b[1])
+    sa = part_a.view(grid_a, n + 1).double().sum(0)
+    sb = part_b.view(grid_b, n + 1).double().sum(0)
+    ref = dh_a.double().sum(0)
+    assert float((sb[:n] - ref).abs().max()) <= 1e-5 * float(dh_a.double().abs().sum(0).max()) + 1e-12
+    assert float((sa[:n] - sb[:n]).abs().max()) <= 1e-5 * float(dh_a.double().abs().sum(0).max()) + 1e-12
+    if act == "prelu":
+        ref_s = (dh0.double() * pre.double())[pre <= 0].sum()
+        assert abs(float(sb[n] - ref_s)) <= 1e-5 * float((dh0.double() * pre.double()).abs().sum()) + 1e-12
