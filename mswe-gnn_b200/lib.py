@@ -167,7 +167,15 @@ def _check(status: int, what: str):
         raise RuntimeError(f"{what} failed (status {status}): {msg}")
 
 
+_raw_stream = getattr(torch._C, "_cuda_getCurrentRawStream", None)
+
+
 def _stream() -> int:
+    """cudaStream_t of torch's current stream on the current device (also the capturing stream inside
+    ``torch.cuda.graph``).  The raw query is ~20x cheaper than building a ``torch.cuda.Stream`` object, which matters
+    with ~700 launches per training step."""
+    if _raw_stream is not None:
+        return _raw_stream(torch.cuda.current_device())
     return torch.cuda.current_stream().cuda_stream
 
 

@@ -27,9 +27,25 @@ def get_loss_variable_scaler(velocity_scaler=1):
     return loss_scaler
 
 
+def _masked_mean_error(diff, keep, type_loss):
+    """``get_mean_error(diff[keep])`` without the data-dependent shape (boolean indexing makes the host wait for the
+    device): Σ over kept rows / number of kept rows.  Same value up to fp32 summation order."""
+    w = keep.to(diff.dtype).unsqueeze(1)
+    cnt = w.sum()
+    if type_loss == 'RMSE':
+        return torch.sqrt((diff * diff * w).sum(0) / cnt)
+    if type_loss == 'MAE':
+        return (diff.abs() * w).sum(0) / cnt
+    raise ValueError("loss_type must be either 'RMSE' or 'MAE'")
+
+
 def get_multiscale_loss(diff, data, only_where_water=True, type_loss='RMSE', nodes_dim=0):
     """Finest-scale rows only (reference ``loss.py:49-74``)."""
     node_ptr = data.node_ptr
+    finest = getattr(data, "_finest_rows", None)           # cached by training.train._adapt_cached: no host reads
+    if finest is not None and finest.device == diff.device and nodes_dim == 0:
+        keep = finest & mask_on_water(diff) if only_where_water else finest
+        return _masked_mean_error(diff, keep, type_loss)
     where_water = mask_on_water(diff) if only_where_water else torch.ones(diff.shape[0], dtype=torch.bool, device=diff.device)
     if node_ptr.dim() == 2:
         ptr = node_ptr.tolist()
@@ -45,6 +61,8 @@ def loss_function(preds, real, data, BC=None, type_loss='RMSE', only_where_water
     diff = preds - real
     if 'node_ptr' in data.keys():
         loss = get_multiscale_loss(diff, data, only_where_water, type_loss, nodes_dim=0)
+    elif only_where_water and getattr(data, "_finest_rows", None) is not None:
+        loss = _masked_mean_error(diff, mask_on_water(diff), type_loss)
     else:
         if only_where_water:
             diff = diff[mask_on_water(diff)]

@@ -161,6 +161,43 @@ def rollout_test(model, batch, use_cuda_graph: Optional[bool] = None):
     return preds.permute(1, 2, 0)
 
 
+_ADAPT_CACHE = {}        # topology identity of a collated batch -> (tensors kept alive, adapted batch)
+
+
+def _adapt_cached(batch):
+    """``adapt_batch_training`` is pure index bookkeeping on the topology of the batch (Python slicing per graph and
+    scale, host reads): done once per collated batch and reused while its topology tensors are the same objects with the
+    same version counters; x / y / BC (the values that change from sample to sample) are taken from the current batch.
+    Reusing the adapted edge tensors also keeps the model's plan cache (CSR, transposed CSR) hot across steps."""
+    names = [n for n in ("edge_index", "edge_attr", "node_BC", "ptr", "node_ptr", "edge_ptr", "intra_mesh_edge_index",
+                         "intra_edge_ptr") if torch.is_tensor(getattr(batch, n, None))]
+    tensors = [getattr(batch, n) for n in names]
+    key = tuple((n, t.data_ptr(), t._version, tuple(t.shape)) for n, t in zip(names, tensors)) + (int(batch.num_graphs),)
+    hit = _ADAPT_CACHE.get(key)
+    if hit is None:
+        if len(_ADAPT_CACHE) >= 4:
+            _ADAPT_CACHE.pop(next(iter(_ADAPT_CACHE)))
+        adapted = adapt_batch_training(batch)
+        # rows of the finest scale of every graph (what the loss is taken over), as a device mask: read once here
+        dev = adapted.x.device
+        finest = torch.zeros(adapted.x.shape[0], dtype=torch.bool, device=dev)
+        if "node_ptr" in adapted.keys():
+            for p0, p1 in [(r[0], r[1]) for r in adapted.node_ptr.reshape(-1, adapted.node_ptr.shape[-1]).tolist()]:
+                finest[p0:p1] = True
+        else:
+            finest[:] = True
+        adapted._finest_rows = finest
+        hit = (tensors, adapted)
+        _ADAPT_CACHE[key] = hit
+    src = hit[1]
+    temp = src.__class__.__new__(src.__class__)
+    temp.__dict__.update(src.__dict__)
+    for n in ("x", "y", "BC"):
+        if hasattr(batch, n):
+            setattr(temp, n, getattr(batch, n))
+    return temp
+
+
 def training_step(model, batch, rollout_steps: int = 1, type_loss: str = "RMSE", only_where_water: bool = True,
                   velocity_scaler: float = 7.0, group=None):
     """One training step of the reference's ``LightningTrainer.training_step`` (``training/train.py:125-145``):
@@ -168,7 +205,7 @@ def training_step(model, batch, rollout_steps: int = 1, type_loss: str = "RMSE",
     process group the flat gradient is all-reduced (data parallel over simulations).  Returns the detached loss.
     The optimizer step stays with the caller (``torch.optim.AdamW`` in the reference, ``train.py:147-155``)."""
     from .loss import loss_function
-    temp = adapt_batch_training(batch) if _is_batch(batch) else batch.clone()
+    temp = _adapt_cached(batch) if _is_batch(batch) else batch.clone()
     dyn = model.previous_t * NUM_WATER_VARS
     roll = []
     x = temp.x
