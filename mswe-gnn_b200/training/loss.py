@@ -7,6 +7,7 @@ from __future__ import annotations
 import torch
 
 NUM_WATER_VARS = 2
+_SCALER_CACHE = {}
 
 
 def get_mean_error(diff_rollout, type_loss, nodes_dim=0):
@@ -67,5 +68,9 @@ def loss_function(preds, real, data, BC=None, type_loss='RMSE', only_where_water
         if only_where_water:
             diff = diff[mask_on_water(diff)]
         loss = get_mean_error(diff, type_loss, nodes_dim=0)
-    loss_scaler = get_loss_variable_scaler(velocity_scaler=velocity_scaler).to(diff.device)
+    key = (str(diff.device), float(velocity_scaler))
+    loss_scaler = _SCALER_CACHE.get(key)
+    if loss_scaler is None:       # a host -> device copy from pageable memory makes the host wait for the stream: once only
+        loss_scaler = get_loss_variable_scaler(velocity_scaler=velocity_scaler).to(diff.device)
+        _SCALER_CACHE[key] = loss_scaler
     return torch.dot(loss, loss_scaler) / loss_scaler.sum()

@@ -45,3 +45,7 @@ print(s.getvalue()[:6000])
 s = io.StringIO()
 pstats.Stats(pr, stream=s).sort_stats("tottime").print_stats(18)
 print(s.getvalue()[:5000])
+
+s = io.StringIO()
+pstats.Stats(pr, stream=s).print_callers("method 'to' of")
+print(s.getvalue()[:4000])
