@@ -220,11 +220,11 @@ __global__ void __launch_bounds__(R_THREADS, 1) row_mlp_tc_kernel(const __grid_c
             }
             mbar_arrive(&bar->st_empty);
         };
-#pragma unroll 1
-        for (int i = 0; i < n_my; ++i) {
+        // the rows of tile i + 1 are requested as soon as tile i has been handed to the tensor core, so that their
+        // latency (and the first encoder layer) overlaps with writing out tile i - 1
+        float4 x[4];
+        auto load_tile = [&](int i) {
             const long long r0 = (tile0 + i) * R_TILE;
-            if (warp == 0) R_STAMP(0, i, 0);
-            float4 x[4];
 #pragma unroll
             for (int k = 0; k < 4; ++k) {
                 const long long row = r0 + g + 32 * k;
@@ -259,6 +259,11 @@ __global__ void __launch_bounds__(R_THREADS, 1) row_mlp_tc_kernel(const __grid_c
                     }
                 }
             }
+        };
+        if (n_my > 0) load_tile(0);
+#pragma unroll 1
+        for (int i = 0; i < n_my; ++i) {
+            if (warp == 0) R_STAMP(0, i, 0);
             if (warp == 0) R_STAMP(0, i, 1);
             mbar_wait(&bar->a_empty, ((uint32_t)i & 1) ^ 1);               // layer-0 MMAs of the previous tile are done
             if (warp == 0) R_STAMP(0, i, 2);
@@ -273,6 +278,7 @@ __global__ void __launch_bounds__(R_THREADS, 1) row_mlp_tc_kernel(const __grid_c
             fence_proxy_async_smem();
             mbar_arrive(&bar->a_full);
             if (warp == 0) R_STAMP(0, i, 3);
+            if (i + 1 < n_my) load_tile(i + 1);
             if (i > 0) finish_tile(i - 1);
             if (warp == 0) R_STAMP(0, i, 4);
         }
