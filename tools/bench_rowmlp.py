@@ -37,6 +37,20 @@ if os.environ.get("ONLY_W0"):
         for r, nm in enumerate(["row", "epi", "mma"]):
             print(tile, nm, " ".join(f"{ev[r][e]}={int(tt[r, tile, e]) - t0}" for e in range(len(ev[r]))))
     sys.exit(0)
+if os.environ.get("ONLY_DEC") or os.environ.get("ONLY_ENC"):
+    import ctypes as C
+    l = lib.load(); l.swe_row_mlp_tc_set_trace.argtypes = [C.c_void_p]
+    fn = (lambda: m._decode(h, "tanh", m.gnn_activation, x, plan, pred, None, 0, xn)) if os.environ.get("ONLY_DEC") else \
+         (lambda: m._tc_static.encode(x, 0, 2, True, (1, 6), None, 0, N, xs))
+    print("time: %.3f ms" % t(fn))
+    tr = torch.zeros(3 * 128, dtype=torch.int64, device=DEV)
+    l.swe_row_mlp_tc_set_trace(tr.data_ptr())
+    fn(); torch.cuda.synchronize()
+    tt = tr.cpu().view(3, 16, 8); t0 = int(tt[0, 3, 0])
+    for tile in range(3, 7):
+        for r, nm in enumerate(["row", "epi", "mma"]):
+            print(tile, nm, " ".join(str(int(tt[r, tile, e]) - t0) for e in range(6)))
+    sys.exit(0)
 for be in ("tc", "ffma"):
     os.environ["MSWE_ROWMLP"] = be
     print(be, "encode (static N + dynamic N): %.3f ms" % t(lambda: m._encode_nodes(x, plan, N, xs, xd)))
