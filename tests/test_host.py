@@ -110,3 +110,52 @@ def test_batch_collation_and_permutation():
     s0 = graphs[0].node_ptr[1].item()
     assert perm[:s0].tolist() == list(range(s0)) and perm[s0] == n[0]        # scale-major, graph-minor
     assert t.node_BC.tolist() == [s0 - 1, n[0] + s0 - 1, n[0] + n[1] + s0 - 1]
+
+
+def test_adapted_batch_is_cached_per_topology_and_follows_the_values():
+    """training_step adapts a collated batch once per topology (the reference re-adapts every step); x / y / BC of the
+    current batch are used, and another collated batch gets its own adaptation."""
+    from mswe_gnn_b200.training.train import _adapt_cached, adapt_batch_training
+    graphs = [make_tri_mesh(8, 8, 3, rollout_steps=2, seed=s) for s in range(3)]
+    b = Batch.from_data_list(graphs)
+    t1 = _adapt_cached(b)
+    b.x = b.x + 1.0                                                   # new values, same topology tensors
+    t2 = _adapt_cached(b)
+    assert t2.edge_index is t1.edge_index and t2.node_ptr is t1.node_ptr          # adapted topology reused
+    assert t2.x is b.x and t1.x is not b.x                                          # values follow the batch
+    ref = adapt_batch_training(b)
+    for name in ("edge_index", "edge_attr", "node_ptr", "edge_ptr", "intra_mesh_edge_index", "intra_edge_ptr", "node_BC"):
+        assert torch.equal(getattr(t2, name), getattr(ref, name)), name
+    fin = t2._finest_rows
+    rows = torch.zeros_like(fin)
+    for r in ref.node_ptr.tolist():
+        rows[r[0]:r[1]] = True
+    assert torch.equal(fin, rows)
+    b2 = Batch.from_data_list([make_tri_mesh(8, 8, 3, rollout_steps=2, seed=7), make_tri_mesh(8, 8, 3, rollout_steps=2, seed=8)])
+    t3 = _adapt_cached(b2)
+    assert t3.edge_index is not t1.edge_index and int(t3.node_ptr.shape[0]) == 2
+
+
+@pytest.mark.parametrize("type_loss", ["RMSE", "MAE"])
+def test_sync_free_loss_equals_boolean_indexed_loss(type_loss):
+    """The mask-weighted form of the loss (no data-dependent shapes, no host reads) against the reference's boolean
+    indexing (training/loss.py:49-118), multiscale batch and single graph, values and gradients."""
+    from mswe_gnn_b200.training.loss import loss_function
+    from mswe_gnn_b200.training.train import _adapt_cached
+    torch.manual_seed(0)
+    b = Batch.from_data_list([make_tri_mesh(8, 8, 3, rollout_steps=1, seed=s) for s in range(3)])
+    t = _adapt_cached(b)
+    n = t.x.shape[0]
+    real = torch.rand(n, 2) * (torch.rand(n, 1) < 0.6)
+    out = {}
+    for cached in (True, False):
+        preds = (real + torch.randn(n, 2, generator=torch.Generator().manual_seed(1)) * (torch.rand(n, 1, generator=torch.Generator().manual_seed(2)) < 0.7)).requires_grad_(True)
+        data = t
+        if not cached:
+            data = t.__class__.__new__(t.__class__)
+            data.__dict__.update({k: v for k, v in t.__dict__.items() if k != "_finest_rows"})
+        loss = loss_function(preds, real, data, None, type_loss=type_loss, only_where_water=True, velocity_scaler=7.0)
+        loss.backward()
+        out[cached] = (loss.detach(), preds.grad.clone())
+    assert torch.allclose(out[True][0], out[False][0], rtol=1e-6, atol=1e-8)
+    assert torch.allclose(out[True][1], out[False][1], rtol=1e-5, atol=1e-9)
