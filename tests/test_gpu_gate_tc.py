@@ -221,3 +221,39 @@ def test_rollout_with_hoisted_static_share_matches_full_gate(monkeypatch, with_W
     assert e > 1e-4, e                                               # the two rollouts really differ
     depth = out["full"][0][:, :, 0]
     assert float((depth[-1] - depth[0]).abs().max()) > 1e-2          # and the water level really moves
+
+
+@pytest.mark.parametrize("nx,ny", [(5, 3), (60, 40), (129, 77)])
+def test_gate_training_forward_and_static_table_stay_inside_their_buffers(nx, ny):
+    """Guard bands around every output of the training forward (s, three pre-activations, work lists) and of the static
+    table producer (padded to whole tiles by contract): nothing is written outside (no compute-sanitizer on this pool)."""
+    n, E, src, dst, xs, xd, a, mlp, k1 = _setup(64, seed=5, nx=nx, ny=ny)
+    tc = PackedGateTC(mlp)
+    codes, slopes = tc.acts_and_slopes()
+    pad = 4096
+
+    def guarded(n_elems, dtype=torch.float32):
+        buf = torch.full((n_elems + 2 * pad,), 7, device=DEV, dtype=dtype)
+        return buf, buf[pad:pad + n_elems]
+
+    bufs = {}
+    for name, ne in (("s", E * 64), ("p1", E * 128), ("p2", E * 128), ("p3", E * 64)):
+        bufs[name] = guarded(ne)
+    cap = 1 << 12
+    lists = guarded(3 * cap, torch.int64)
+    count = torch.zeros(4, dtype=torch.int32, device=DEV)
+    lib.edge_gate_tc_train_fwd(xs, xd, xd, a, src, dst, E, tc.image(), k1, codes, slopes, True, bufs["p1"][1].view(E, 128),
+                               bufs["p2"][1].view(E, 128), bufs["p3"][1].view(E, 64), bufs["s"][1].view(E, 64), lists[1], count,
+                               cap, 1e-2)                       # a wide threshold: the lists overflow their capacity
+    n_tiles = (E + 127) // 128
+    tab = guarded(n_tiles * 128 * 128)
+    lib.gate_static_partials_tc(xs, a, src, dst, E, tc.image(), k1, tab[1])
+    torch.cuda.synchronize()
+    for buf, view in list(bufs.values()) + [lists, tab]:
+        assert bool((buf[:pad] == 7).all()) and bool((buf[pad + view.numel():] == 7).all())
+    assert int(count[:3].max()) > 0
+    # the listed entries are in range even when the lists overflow
+    for layer, width in ((0, 128), (1, 128), (2, 64)):
+        k = min(int(count[layer]), cap)
+        ent = lists[1][layer * cap: layer * cap + k]
+        assert bool(((ent >> 8) < E).all()) and bool(((ent & 255) < width).all())

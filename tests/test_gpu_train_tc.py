@@ -190,3 +190,48 @@ def test_dx_tc_fused_delta_matches_separate_pass(n_rows, n, ko, split, act):
     if act == "prelu":
         ref_s = (dh0.double() * pre.double())[pre <= 0].sum()
         assert abs(float(sb[n] - ref_s)) <= 1e-5 * float((dh0.double() * pre.double()).abs().sum()) + 1e-12
+
+
+def _guarded(n_elems, fill=float("nan")):
+    """A tensor of n_elems floats embedded between two guard bands; returns (view, check) — check() asserts that the
+    guards are untouched (the pool has no compute-sanitizer: out-of-range writes are caught this way)."""
+    pad = 4096
+    buf = torch.full((n_elems + 2 * pad,), 12345.0, device=DEV)
+    view = buf[pad:pad + n_elems]
+    view.fill_(fill)
+
+    def check():
+        torch.cuda.synchronize()
+        assert bool((buf[:pad] == 12345.0).all()) and bool((buf[pad + n_elems:] == 12345.0).all()), "guard band overwritten"
+    return view, check
+
+
+@pytest.mark.parametrize("n_rows", [1, 127, 129, 4097, 33_001])
+def test_tensor_core_training_kernels_stay_inside_their_buffers(n_rows):
+    g = torch.Generator(device="cpu").manual_seed(n_rows)
+    n = 128
+    dh = torch.randn(n_rows, n, generator=g).to(DEV)
+    pre = torch.randn(n_rows, n, generator=g).to(DEV)
+    w = (torch.randn(n, 320, generator=g) * 0.1).to(DEV)
+    slope = torch.tensor([0.2], device=DEV)
+    checks = []
+    # dx (two 64-wide blocks) with the fused delta pass
+    dx0, c = _guarded(n_rows * 64); checks.append(c)
+    dx1, c = _guarded(n_rows * 64); checks.append(c)
+    grid = lib.mlp_layer_bwd_dx_tc_grid(n_rows)
+    part, c = _guarded(grid * (n + 1)); checks.append(c)
+    delta, c = _guarded(n_rows * n); checks.append(c)
+    delta.copy_(dh.flatten())
+    lib.mlp_layer_bwd_dx_tc_fused(delta, pre, lib.ACT_CODES["prelu"], slope, n_rows, n, w, 320, 64, 128, 128, dx0, False, dx1,
+                                  False, 64, part)
+    # dW with gathered segments
+    n_nodes = max(n_rows // 3, 2)
+    xs = torch.randn(n_nodes, 64, generator=g).to(DEV)
+    src = torch.randint(0, n_nodes, (n_rows,), generator=g).to(torch.int32).to(DEV)
+    rows = lib.make_rows([(xs, src, 64, 64, 0, None), (xs, src, 64, 64, 0, None), (pre, None, 128, 128, 1, slope)])
+    gdw = lib.mlp_layer_bwd_dw_tc_grid(n_rows)
+    pdw, c = _guarded(gdw * n * 256); checks.append(c)
+    assert lib.mlp_layer_bwd_dw_tc(delta, n_rows, n, rows, pdw) == gdw
+    for c in checks:
+        c()
+    assert bool(torch.isfinite(dx0).all()) and bool(torch.isfinite(dx1).all()) and bool(torch.isfinite(pdw).all())
