@@ -506,7 +506,7 @@ def run_train(args):
                     "what": "training_step(model, batch.to(device)) from pinned host memory every step, loss.item() back"},
             "gpu_launches": launches,
             "roofline": {"bound": "tensor", "kernel": dom["name"], "achieved": dom["tflops"], "peak": pk["bf16"], "unit": "TFLOP/s",
-                         "frac": dom["tflops"] / pk["bf16"], "traffic": None,
+                         "frac": dom["tflops"] / pk["bf16"], "traffic": _traffic_of(dom["name"]),
                          "peak_source": pk["hbm_src"] + " (sustained bf16)",
                          "note": "algorithmic FLOPs / time of the entry point with the largest share of the step; the wide edge-MLP "
                                  "GEMMs run as 3xTF32 on tcgen05 (fp32-accurate), the narrow ones in exact fp32 on CUDA cores"},
@@ -515,6 +515,16 @@ def run_train(args):
     print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
+
+
+def _traffic_of(name):
+    """Measured DRAM bytes of one launch of `name` from the committed ncu --set full captures (or None)."""
+    try:
+        tr = json.load(open(os.path.join(ROOT, "profiles", "traffic_r01.json"))).get(name)
+        return {"dram_bytes_per_launch": tr["dram_bytes_per_launch"],
+                "algorithmic_bytes_per_launch": tr["algorithmic_bytes_per_launch"], "capture": tr["capture"]} if tr else None
+    except Exception:
+        return None
 
 
 def profile_train_kernels(step_fn):
