@@ -91,7 +91,7 @@ __global__ void __launch_bounds__(R_THREADS, 1) row_mlp_tc_kernel(const __grid_c
     unsigned char* a_slot = smem;
     unsigned char* w_tile = smem + R_A_SLOT;                           // layer l at + l * 32 KB
     float* stage = reinterpret_cast<float*>(w_tile + 2 * R_W_IMAGE);
-    float* s_wf = stage + R_TILE * R_STAGE_LD;                          // [64][8] first-layer weights (padded with 0)
+    float* s_wf = stage + R_TILE * R_STAGE_LD;                          // [8][64] first-layer weights (k-major, padded with 0)
     float* s_bf = s_wf + 64 * 8;                                        // [64]
     float* s_bias = s_bf + 64;                                          // [2][64]
     float* s_wh = s_bias + 128;                                         // [2][64] head weights
@@ -110,8 +110,8 @@ __global__ void __launch_bounds__(R_THREADS, 1) row_mlp_tc_kernel(const __grid_c
         for (int i = threadIdx.x * 16; i < (int)R_W_IMAGE; i += R_THREADS * 16)
             *reinterpret_cast<float4*>(w_tile + l * R_W_IMAGE + i) = *reinterpret_cast<const float4*>(p.img[l] + i);
     for (int i = threadIdx.x; i < 64 * 8; i += R_THREADS) {
-        const int n = i >> 3, k = i & 7;
-        s_wf[i] = (p.w_first && k < p.raw_k) ? p.w_first[n * p.raw_k + k] : 0.f;
+        const int n = i >> 3, k = i & 7;                                 // stored [k][64]: a lane reads its 4 columns as one float4
+        s_wf[k * 64 + n] = (p.w_first && k < p.raw_k) ? p.w_first[n * p.raw_k + k] : 0.f;
     }
     for (int i = threadIdx.x; i < 64; i += R_THREADS) {
         s_bf[i] = p.b_first ? p.b_first[i] : 0.f;
@@ -144,14 +144,10 @@ __global__ void __launch_bounds__(R_THREADS, 1) row_mlp_tc_kernel(const __grid_c
         const ActSel a_in = act_select(p.act_in, p.slope_in), a_f = act_select(p.act_first, p.slope_first),
                      a_h = act_select(p.act_head, p.slope_head);
         // this lane's 4 output columns of the CUDA-core first layer
-        float wf[4][8], bf[4];
+        float bf[4];
         if (p.raw) {
 #pragma unroll
-            for (int c = 0; c < 4; ++c) {
-                bf[c] = s_bf[q4 + c];
-#pragma unroll
-                for (int k = 0; k < 8; ++k) wf[c][k] = s_wf[(q4 + c) * 8 + k];
-            }
+            for (int c = 0; c < 4; ++c) bf[c] = s_bf[q4 + c];
         }
         const int n_static_raw = p.n_cols - 2 * p.previous_t;
         auto finish_tile = [&](int j) {
@@ -225,38 +221,58 @@ __global__ void __launch_bounds__(R_THREADS, 1) row_mlp_tc_kernel(const __grid_c
         float4 x[4];
         auto load_tile = [&](int i) {
             const long long r0 = (tile0 + i) * R_TILE;
+            if (p.x_rows) {
 #pragma unroll
-            for (int k = 0; k < 4; ++k) {
-                const long long row = r0 + g + 32 * k;
-                x[k] = make_float4(0.f, 0.f, 0.f, 0.f);
-                if (row < p.n_rows) {
-                    if (p.x_rows) {
+                for (int k = 0; k < 4; ++k) {
+                    const long long row = r0 + g + 32 * k;
+                    x[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+                    if (row < p.n_rows) {
                         x[k] = ldg4(p.x_rows + ((long long)p.row_lo + row) * RF + q4);
                         if (p.act_in != SWE_ACT_NONE) {
                             x[k].x = act_do(a_in, x[k].x); x[k].y = act_do(a_in, x[k].y);
                             x[k].z = act_do(a_in, x[k].z); x[k].w = act_do(a_in, x[k].w);
                         }
-                    } else {
+                    }
+                }
+            } else {
+                // first encoder layer on CUDA cores: the 8 raw inputs of this thread's 4 rows, then one pass over k with
+                // the weights of its 4 columns read once per k (a float4 from shared memory) and used for all 4 rows
+                float in[4][8];
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    const long long row = r0 + g + 32 * k;
+#pragma unroll
+                    for (int c = 0; c < 8; ++c) in[k][c] = 0.f;
+                    if (row < p.n_rows) {
                         const long long node = (long long)p.row_lo + row;
                         const float* xr = p.raw + (long long)(p.perm ? p.perm[node] : node) * p.raw_ld;
-                        float in[8];
 #pragma unroll
-                        for (int c = 0; c < 8; ++c) in[c] = c < p.raw_cols ? __ldg(xr + p.raw_col0 + c) : 0.f;
+                        for (int c = 0; c < 8; ++c) in[k][c] = c < p.raw_cols ? __ldg(xr + p.raw_col0 + c) : 0.f;
                         if (p.with_wl) {
                             const float wl = __ldg(xr + p.wl_col_a) + __ldg(xr + p.wl_col_b);
 #pragma unroll
-                            for (int c = 0; c < 8; ++c) if (c == p.raw_cols) in[c] = wl;
+                            for (int c = 0; c < 8; ++c) if (c == p.raw_cols) in[k][c] = wl;
                         }
-                        float o[4];
-#pragma unroll
-                        for (int c = 0; c < 4; ++c) {
-                            float acc = 0.f;
-#pragma unroll
-                            for (int kk = 0; kk < 8; ++kk) acc = fmaf(in[kk], wf[c][kk], acc);
-                            o[c] = act_do(a_f, acc + bf[c]);
-                        }
-                        x[k] = make_float4(o[0], o[1], o[2], o[3]);
                     }
+                }
+                float acc[4][4];
+#pragma unroll
+                for (int k = 0; k < 4; ++k) { acc[k][0] = acc[k][1] = acc[k][2] = acc[k][3] = 0.f; }
+#pragma unroll
+                for (int kk = 0; kk < 8; ++kk) {
+                    const float4 w = *reinterpret_cast<const float4*>(s_wf + kk * 64 + q4);
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) {
+                        acc[k][0] = fmaf(in[k][kk], w.x, acc[k][0]); acc[k][1] = fmaf(in[k][kk], w.y, acc[k][1]);
+                        acc[k][2] = fmaf(in[k][kk], w.z, acc[k][2]); acc[k][3] = fmaf(in[k][kk], w.w, acc[k][3]);
+                    }
+                }
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    const long long row = r0 + g + 32 * k;
+                    x[k] = row < p.n_rows ? make_float4(act_do(a_f, acc[k][0] + bf[0]), act_do(a_f, acc[k][1] + bf[1]),
+                                                        act_do(a_f, acc[k][2] + bf[2]), act_do(a_f, acc[k][3] + bf[3]))
+                                          : make_float4(0.f, 0.f, 0.f, 0.f);
                 }
             }
         };
