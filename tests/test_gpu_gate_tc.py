@@ -257,3 +257,18 @@ def test_gate_training_forward_and_static_table_stay_inside_their_buffers(nx, ny
         k = min(int(count[layer]), cap)
         ent = lists[1][layer * cap: layer * cap + k]
         assert bool(((ent >> 8) < E).all()) and bool(((ent & 255) < width).all())
+
+
+def test_gate_static_and_training_entry_points_accept_zero_edges():
+    n, E, src, dst, xs, xd, a, mlp, k1 = _setup(64, seed=1, nx=5, ny=3)
+    tc = PackedGateTC(mlp)
+    codes, slopes = tc.acts_and_slopes()
+    s = torch.full((4, 64), 2.0, device=DEV)
+    tab = torch.full((128, 128), 2.0, device=DEV)
+    p1, p2, p3 = (torch.full((4, w), 2.0, device=DEV) for w in (128, 128, 64))
+    lib.gate_static_partials_tc(xs, a, src, dst, 0, tc.image(), k1, tab)
+    lib.edge_gate_tc_stat_fwd(tab, None, xd, xd, src, dst, 0, tc.image(), k1, codes, slopes, True, s)
+    lib.edge_gate_tc_train_fwd(xs, xd, xd, a, src, dst, 0, tc.image(), k1, codes, slopes, True, p1, p2, p3, s)
+    torch.cuda.synchronize()
+    for t in (s, tab, p1, p2, p3):
+        assert bool((t == 2.0).all())

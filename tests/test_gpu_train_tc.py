@@ -235,3 +235,17 @@ def test_tensor_core_training_kernels_stay_inside_their_buffers(n_rows):
     for c in checks:
         c()
     assert bool(torch.isfinite(dx0).all()) and bool(torch.isfinite(dx1).all()) and bool(torch.isfinite(pdw).all())
+
+
+def test_empty_inputs_are_no_ops():
+    """Zero rows / zero edges: every tensor-core training entry point returns without touching its outputs."""
+    z = torch.zeros(1, 128, device=DEV)
+    w = torch.zeros(128, 128, device=DEV)
+    out = torch.full((4, 128), 3.0, device=DEV)
+    part = torch.full((1024,), 3.0, device=DEV)
+    lib.mlp_layer_bwd_dx_tc(z, 0, 128, w, 128, 0, 128, 128, out, False)
+    assert lib.mlp_layer_bwd_dx_tc_fused(z, z, 0, None, 0, 128, w, 128, 0, 128, 128, out, False, None, False, None, part) == 0
+    rows = lib.make_rows([(z, None, 128, 128, 0, None)])
+    assert lib.mlp_layer_bwd_dw_tc(z, 0, 128, rows, part) == 0
+    torch.cuda.synchronize()
+    assert bool((out == 3.0).all()) and bool((part == 3.0).all())
