@@ -35,7 +35,9 @@ constexpr int R_ROW_WARPS = 16, R_ROW_THREADS = 512, R_EPI_WARPS = 4;
 constexpr int R_THREADS = R_ROW_THREADS + R_EPI_WARPS * 32 + 32;    // 672
 constexpr int R_STAGE_LD = RF + 4;
 constexpr size_t R_STAGE_BYTES = (size_t)R_TILE * R_STAGE_LD * 4;
-constexpr uint32_t RC_D0 = 0, RC_D1 = 64, RC_AHI = 128, RC_ALO = 192;      // TMEM columns (256 allocated)
+// TMEM columns (512 allocated): everything between the two tensor-core layers is double-buffered by tile parity, so
+// that the epilogue warps turn D0 of tile i + 1 into its layer-1 operand while layer 1 of tile i is still running
+constexpr uint32_t RC_D0 = 0, RC_D1 = 128, RC_AHI = 256, RC_ALO = 384;      // + 64 * (tile & 1)
 
 // Activations inside the per-element loops: the "leaky family" (none / relu / leakyrelu / prelu) is two FP32
 // instructions; everything else goes through ONE out-of-line function.  Inlining the 8-way act_apply switch at the
@@ -57,13 +59,13 @@ __device__ __forceinline__ float act_do(const ActSel& a, float v) {
 
 struct __align__(8) RowBarriers {
     uint64_t a_full, a_empty;          // A operand written (512) / consumed by layer-0 MMAs (commit)
-    uint64_t d0_full, d1_full;         // layer-0 / layer-1 accumulators complete (commit)
-    uint64_t x1_ready;                 // layer-1 operand written to TMEM (128)
-    uint64_t d0_free;                  // layer-0 accumulator read by the epilogue (128): the next tile's layer 0 may start
-    uint64_t st_full, st_empty;        // stage holds a tile (128) / consumed (512)
+    uint64_t d0_full[2], d1_full[2];   // layer-0 / layer-1 accumulators complete (commit), per buffer
+    uint64_t x1_ready[2];              // layer-1 operand written to TMEM (128), per buffer
+    uint64_t d0_free[2], d1_free[2];   // accumulators read by the epilogue (128): the buffer may be overwritten
+    uint64_t st_full[2], st_empty[2];  // stage buffer (tile parity) holds a tile (128) / consumed (512)
 };
 
-constexpr size_t ROWMLP_SMEM = 1024 + (size_t)R_A_SLOT + 2 * R_W_IMAGE + R_STAGE_BYTES + 64 * 8 * 4 + 64 * 4 +
+constexpr size_t ROWMLP_SMEM = 1024 + (size_t)R_A_SLOT + 2 * R_W_IMAGE + 2 * R_STAGE_BYTES + 64 * 8 * 4 + 64 * 4 +
                                2 * 64 * 4 + 2 * 64 * 4 + sizeof(RowBarriers) + 16;
 
 struct RowMlpParams {
@@ -91,7 +93,9 @@ __global__ void __launch_bounds__(R_THREADS, 1) row_mlp_tc_kernel(const __grid_c
     unsigned char* a_slot = smem;
     unsigned char* w_tile = smem + R_A_SLOT;                           // layer l at + l * 32 KB
     float* stage = reinterpret_cast<float*>(w_tile + 2 * R_W_IMAGE);
-    float* s_wf = stage + R_TILE * R_STAGE_LD;                          // [8][64] first-layer weights (k-major, padded with 0)
+    // two stage buffers (tile parity): the epilogue warps fill one while the row warps write the other one out — with a
+    // single buffer the two took turns and their hand-over latencies added up to the whole tile time
+    float* s_wf = stage + 2 * R_TILE * R_STAGE_LD;                      // [8][64] first-layer weights (k-major, padded with 0)
     float* s_bf = s_wf + 64 * 8;                                        // [64]
     float* s_bias = s_bf + 64;                                          // [2][64]
     float* s_wh = s_bias + 128;                                         // [2][64] head weights
@@ -101,17 +105,47 @@ __global__ void __launch_bounds__(R_THREADS, 1) row_mlp_tc_kernel(const __grid_c
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     if (threadIdx.x == 0) {
         mbar_init(&bar->a_full, R_ROW_THREADS); mbar_init(&bar->a_empty, 1);
-        mbar_init(&bar->d0_full, 1); mbar_init(&bar->d1_full, 1);
-        mbar_init(&bar->x1_ready, R_EPI_WARPS * 32); mbar_init(&bar->d0_free, R_EPI_WARPS * 32);
-        mbar_init(&bar->st_full, R_EPI_WARPS * 32); mbar_init(&bar->st_empty, R_ROW_THREADS);
+        for (int b = 0; b < 2; ++b) {
+            mbar_init(&bar->d0_full[b], 1); mbar_init(&bar->d1_full[b], 1);
+            mbar_init(&bar->x1_ready[b], R_EPI_WARPS * 32);
+            mbar_init(&bar->d0_free[b], R_EPI_WARPS * 32); mbar_init(&bar->d1_free[b], R_EPI_WARPS * 32);
+        }
+        for (int b = 0; b < 2; ++b) { mbar_init(&bar->st_full[b], R_EPI_WARPS * 32); mbar_init(&bar->st_empty[b], R_ROW_THREADS); }
         fence_barrier_init();
     }
     for (int l = 0; l < p.n_tc; ++l)
         for (int i = threadIdx.x * 16; i < (int)R_W_IMAGE; i += R_THREADS * 16)
             *reinterpret_cast<float4*>(w_tile + l * R_W_IMAGE + i) = *reinterpret_cast<const float4*>(p.img[l] + i);
-    for (int i = threadIdx.x; i < 64 * 8; i += R_THREADS) {
-        const int n = i >> 3, k = i & 7;                                 // stored [k][64]: a lane reads its 4 columns as one float4
-        s_wf[k * 64 + n] = (p.w_first && k < p.raw_k) ? p.w_first[n * p.raw_k + k] : 0.f;
+    // First encoder layer, stored [k][64] (a lane reads its 4 columns as one float4).  When a node's raw row is exactly
+    // 8 floats (the default models) the weights are re-indexed by ABSOLUTE raw column, and the water-level input
+    // WL = x[a] + x[b] is folded in by adding its weight to columns a and b: the row workers then load the row as two
+    // float4 and run a plain 8 -> 64 layer (before: 10 predicated scalar loads per row, 7 k cycles per 128 rows).
+    const bool row8 = p.raw != nullptr && p.raw_ld == 8 && p.raw_col0 + p.raw_cols <= 8 &&
+                      (!p.with_wl || (p.wl_col_a < 8 && p.wl_col_b < 8)) && ((reinterpret_cast<uintptr_t>(p.raw) & 15u) == 0);
+    if (row8) {
+        if (threadIdx.x < 64) {
+            const int n = threadIdx.x;
+            float w8[8];
+#pragma unroll
+            for (int c = 0; c < 8; ++c) w8[c] = 0.f;
+            for (int j = 0; j < p.raw_cols; ++j) {
+                const float w = p.w_first ? p.w_first[n * p.raw_k + j] : 0.f;
+#pragma unroll
+                for (int c = 0; c < 8; ++c) if (c == p.raw_col0 + j) w8[c] += w;
+            }
+            if (p.with_wl) {
+                const float w = p.w_first ? p.w_first[n * p.raw_k + p.raw_cols] : 0.f;
+#pragma unroll
+                for (int c = 0; c < 8; ++c) if (c == p.wl_col_a || c == p.wl_col_b) w8[c] += w;
+            }
+#pragma unroll
+            for (int c = 0; c < 8; ++c) s_wf[c * 64 + n] = w8[c];
+        }
+    } else {
+        for (int i = threadIdx.x; i < 64 * 8; i += R_THREADS) {
+            const int n = i >> 3, k = i & 7;
+            s_wf[k * 64 + n] = (p.w_first && k < p.raw_k) ? p.w_first[n * p.raw_k + k] : 0.f;
+        }
     }
     for (int i = threadIdx.x; i < 64; i += R_THREADS) {
         s_bf[i] = p.b_first ? p.b_first[i] : 0.f;
@@ -121,7 +155,7 @@ __global__ void __launch_bounds__(R_THREADS, 1) row_mlp_tc_kernel(const __grid_c
         s_wh[64 + i] = p.head ? p.w_head[64 + i] : 0.f;
     }
     fence_proxy_async_smem();
-    if (warp == R_ROW_WARPS + R_EPI_WARPS) tmem_alloc(tmem_holder, 256);
+    if (warp == R_ROW_WARPS + R_EPI_WARPS) tmem_alloc(tmem_holder, 512);
     tc_fence_before_sync();
     __syncthreads();
     tc_fence_after_sync();
@@ -168,12 +202,14 @@ __global__ void __launch_bounds__(R_THREADS, 1) row_mlp_tc_kernel(const __grid_c
                     }
                 }
             }
-            mbar_wait(&bar->st_full, (uint32_t)j & 1);
+            const float* stg = stage + (j & 1) * (R_TILE * R_STAGE_LD);
+            mbar_wait(&bar->st_full[j & 1], ((uint32_t)j >> 1) & 1);
+            if (warp == 0) R_STAMP(0, j + 2, 6);
 #pragma unroll
             for (int k = 0; k < 4; ++k) {
                 const int r = g + 32 * k;
                 const long long row = r0 + r;
-                const float4 d = *reinterpret_cast<const float4*>(stage + r * R_STAGE_LD + q4);
+                const float4 d = *reinterpret_cast<const float4*>(stg + r * R_STAGE_LD + q4);
                 if (!p.head) {
                     if (row < p.n_rows) stg4(p.out_rows + ((long long)p.row_lo + row) * RF + q4, d);
                 } else {
@@ -214,7 +250,7 @@ __global__ void __launch_bounds__(R_THREADS, 1) row_mlp_tc_kernel(const __grid_c
                     }
                 }
             }
-            mbar_arrive(&bar->st_empty);
+            mbar_arrive(&bar->st_empty[j & 1]);
         };
         // the rows of tile i + 1 are requested as soon as tile i has been handed to the tensor core, so that their
         // latency (and the first encoder layer) overlaps with writing out tile i - 1
@@ -237,71 +273,93 @@ __global__ void __launch_bounds__(R_THREADS, 1) row_mlp_tc_kernel(const __grid_c
             } else {
                 // first encoder layer on CUDA cores: the 8 raw inputs of this thread's 4 rows, then one pass over k with
                 // the weights of its 4 columns read once per k (a float4 from shared memory) and used for all 4 rows
-                float in[4][8];
+                // (two rows at a time: with all four in flight the 32 inputs + 16 accumulators + the prefetched tile
+                //  did not fit the 80-register budget and the inner loop ran out of local memory)
+#pragma unroll 1
+                for (int kp = 0; kp < 4; kp += 2) {
+                    // the 8 inputs of a row live in two float4 NAMED per row (an indexed float[2][8] was placed in
+                    // local memory: its STL/LDL were a quarter of all stall samples of the kernel)
+                    float4 lo0 = make_float4(0.f, 0.f, 0.f, 0.f), hi0 = lo0, lo1 = lo0, hi1 = lo0;
 #pragma unroll
-                for (int k = 0; k < 4; ++k) {
-                    const long long row = r0 + g + 32 * k;
+                    for (int u = 0; u < 2; ++u) {
+                        const long long row = r0 + g + 32 * (kp + u);
+                        if (row < p.n_rows) {
+                            const long long node = (long long)p.row_lo + row;
+                            const float* xr = p.raw + (long long)(p.perm ? p.perm[node] : node) * p.raw_ld;
+                            float4 l4, h4;
+                            if (row8) {
+                                l4 = ldg4(xr); h4 = ldg4(xr + 4);
+                            } else {
+                                float t[8];
 #pragma unroll
-                    for (int c = 0; c < 8; ++c) in[k][c] = 0.f;
-                    if (row < p.n_rows) {
-                        const long long node = (long long)p.row_lo + row;
-                        const float* xr = p.raw + (long long)(p.perm ? p.perm[node] : node) * p.raw_ld;
+                                for (int c = 0; c < 8; ++c) t[c] = c < p.raw_cols ? __ldg(xr + p.raw_col0 + c) : 0.f;
+                                if (p.with_wl) {
+                                    const float wl = __ldg(xr + p.wl_col_a) + __ldg(xr + p.wl_col_b);
 #pragma unroll
-                        for (int c = 0; c < 8; ++c) in[k][c] = c < p.raw_cols ? __ldg(xr + p.raw_col0 + c) : 0.f;
-                        if (p.with_wl) {
-                            const float wl = __ldg(xr + p.wl_col_a) + __ldg(xr + p.wl_col_b);
-#pragma unroll
-                            for (int c = 0; c < 8; ++c) if (c == p.raw_cols) in[k][c] = wl;
+                                    for (int c = 0; c < 8; ++c) t[c] = (c == p.raw_cols) ? wl : t[c];
+                                }
+                                l4 = make_float4(t[0], t[1], t[2], t[3]); h4 = make_float4(t[4], t[5], t[6], t[7]);
+                            }
+                            if (u == 0) { lo0 = l4; hi0 = h4; } else { lo1 = l4; hi1 = h4; }
                         }
                     }
-                }
-                float acc[4][4];
+                    float acc[2][4];
 #pragma unroll
-                for (int k = 0; k < 4; ++k) { acc[k][0] = acc[k][1] = acc[k][2] = acc[k][3] = 0.f; }
+                    for (int u = 0; u < 2; ++u) { acc[u][0] = acc[u][1] = acc[u][2] = acc[u][3] = 0.f; }
+#define SWE_IN8(l_, h_, kk_) ((kk_) == 0 ? l_.x : (kk_) == 1 ? l_.y : (kk_) == 2 ? l_.z : (kk_) == 3 ? l_.w : \
+                              (kk_) == 4 ? h_.x : (kk_) == 5 ? h_.y : (kk_) == 6 ? h_.z : h_.w)
 #pragma unroll
-                for (int kk = 0; kk < 8; ++kk) {
-                    const float4 w = *reinterpret_cast<const float4*>(s_wf + kk * 64 + q4);
-#pragma unroll
-                    for (int k = 0; k < 4; ++k) {
-                        acc[k][0] = fmaf(in[k][kk], w.x, acc[k][0]); acc[k][1] = fmaf(in[k][kk], w.y, acc[k][1]);
-                        acc[k][2] = fmaf(in[k][kk], w.z, acc[k][2]); acc[k][3] = fmaf(in[k][kk], w.w, acc[k][3]);
+                    for (int kk = 0; kk < 8; ++kk) {
+                        const float4 w = *reinterpret_cast<const float4*>(s_wf + kk * 64 + q4);
+                        const float i0 = SWE_IN8(lo0, hi0, kk), i1 = SWE_IN8(lo1, hi1, kk);
+                        acc[0][0] = fmaf(i0, w.x, acc[0][0]); acc[0][1] = fmaf(i0, w.y, acc[0][1]);
+                        acc[0][2] = fmaf(i0, w.z, acc[0][2]); acc[0][3] = fmaf(i0, w.w, acc[0][3]);
+                        acc[1][0] = fmaf(i1, w.x, acc[1][0]); acc[1][1] = fmaf(i1, w.y, acc[1][1]);
+                        acc[1][2] = fmaf(i1, w.z, acc[1][2]); acc[1][3] = fmaf(i1, w.w, acc[1][3]);
                     }
-                }
+#undef SWE_IN8
 #pragma unroll
-                for (int k = 0; k < 4; ++k) {
-                    const long long row = r0 + g + 32 * k;
-                    x[k] = row < p.n_rows ? make_float4(act_do(a_f, acc[k][0] + bf[0]), act_do(a_f, acc[k][1] + bf[1]),
-                                                        act_do(a_f, acc[k][2] + bf[2]), act_do(a_f, acc[k][3] + bf[3]))
-                                          : make_float4(0.f, 0.f, 0.f, 0.f);
+                    for (int u = 0; u < 2; ++u) {
+                        const long long row = r0 + g + 32 * (kp + u);
+                        const float4 y = row < p.n_rows ? make_float4(act_do(a_f, acc[u][0] + bf[0]), act_do(a_f, acc[u][1] + bf[1]),
+                                                                      act_do(a_f, acc[u][2] + bf[2]), act_do(a_f, acc[u][3] + bf[3]))
+                                                        : make_float4(0.f, 0.f, 0.f, 0.f);
+                        if (kp == 0) { if (u == 0) x[0] = y; else x[1] = y; } else { if (u == 0) x[2] = y; else x[3] = y; }
+                    }
                 }
             }
         };
-        if (n_my > 0) load_tile(0);
+        // one loop with ONE call site per phase (the phases are big inlined lambdas; with a prologue and two epilogue
+        // copies the kernel was 10.9 k SASS instructions): iteration i stores tile i, requests tile i + 1 and writes
+        // out tile i - 2.  The output lags two tiles behind the input: waiting for tile i - 1 (whose layer 1 is only
+        // issued after layer 0 of tile i) would hold back the store of tile i + 1 and serialise the whole chain.
 #pragma unroll 1
-        for (int i = 0; i < n_my; ++i) {
-            if (warp == 0) R_STAMP(0, i, 0);
-            if (warp == 0) R_STAMP(0, i, 1);
-            mbar_wait(&bar->a_empty, ((uint32_t)i & 1) ^ 1);               // layer-0 MMAs of the previous tile are done
-            if (warp == 0) R_STAMP(0, i, 2);
-            unsigned char* base = a_slot + (size_t)chunk * 2 * R_A_TILE;
+        for (int i = -1; i < n_my + 2; ++i) {
+            if (i >= 0 && i < n_my) {
+                if (warp == 0) R_STAMP(0, i, 0);
+                mbar_wait(&bar->a_empty, ((uint32_t)i & 1) ^ 1);           // layer-0 MMAs of the previous tile are done
+                if (warp == 0) R_STAMP(0, i, 2);
+                unsigned char* base = a_slot + (size_t)chunk * 2 * R_A_TILE;
 #pragma unroll
-            for (int k = 0; k < 4; ++k) {
-                float4 hh, ll;
-                split_tf32(x[k].x, hh.x, ll.x); split_tf32(x[k].y, hh.y, ll.y); split_tf32(x[k].z, hh.z, ll.z); split_tf32(x[k].w, hh.w, ll.w);
-                *reinterpret_cast<float4*>(base + a_off[k]) = hh;
-                *reinterpret_cast<float4*>(base + R_A_TILE + a_off[k]) = ll;
+                for (int k = 0; k < 4; ++k) {
+                    float4 hh, ll;
+                    split_tf32(x[k].x, hh.x, ll.x); split_tf32(x[k].y, hh.y, ll.y); split_tf32(x[k].z, hh.z, ll.z); split_tf32(x[k].w, hh.w, ll.w);
+                    *reinterpret_cast<float4*>(base + a_off[k]) = hh;
+                    *reinterpret_cast<float4*>(base + R_A_TILE + a_off[k]) = ll;
+                }
+                fence_proxy_async_smem();
+                mbar_arrive(&bar->a_full);
+                if (warp == 0) R_STAMP(0, i, 3);
             }
-            fence_proxy_async_smem();
-            mbar_arrive(&bar->a_full);
-            if (warp == 0) R_STAMP(0, i, 3);
             if (i + 1 < n_my) load_tile(i + 1);
-            if (i > 0) finish_tile(i - 1);
-            if (warp == 0) R_STAMP(0, i, 4);
+            if (warp == 0 && i >= 0) R_STAMP(0, i, 5);
+            if (i >= 2 && i - 2 < n_my) finish_tile(i - 2);
+            if (warp == 0 && i >= 0) R_STAMP(0, i, 4);
         }
-        if (n_my > 0) finish_tile(n_my - 1);
     } else if (warp < R_ROW_WARPS + R_EPI_WARPS) {
         // =====================================================================================
-        // epilogue warps
+        // epilogue warps.  Two-layer stacks:  E0(0) ; for i: { E0(i + 1) ; E1(i) }  — the operand of layer 1 of the next
+        // tile is produced before this tile's layer-1 result is awaited, so the tensor pipe always has work queued.
         // =====================================================================================
         const int lq = warp & 3;
         const uint32_t lane_addr = tmem_base + ((uint32_t)(lq * 32) << 16);
@@ -311,45 +369,48 @@ __global__ void __launch_bounds__(R_THREADS, 1) row_mlp_tc_kernel(const __grid_c
         const bool two = p.n_tc > 1;
         const ActSel a_l = two ? a1 : a0;
         const float* bias_l = s_bias + (two ? 64 : 0);
-        const uint32_t dcol_l = two ? RC_D1 : RC_D0;
-        float* my_row = stage + (lq * 32 + lane) * R_STAGE_LD;
-#pragma unroll 1
-        for (int i = 0; i < n_my; ++i) {
-            const uint32_t ph = (uint32_t)i & 1;
-            if (lq == 0) R_STAMP(1, i, 0);
-            mbar_wait(&bar->d0_full, ph);
+        float* my_row0 = stage + (lq * 32 + lane) * R_STAGE_LD;
+        // X1 = act(D0 + b0) -> TF32 hi/lo -> TMEM operand of layer 1 (buffer = tile parity)
+        auto e0 = [&](int i) {
+            const uint32_t b = (uint32_t)i & 1, bph = ((uint32_t)i >> 1) & 1, bo = b * 64;
+            mbar_wait(&bar->d0_full[b], bph);
             tc_fence_after_sync();
-            if (lq == 0) R_STAMP(1, i, 1);
-            if (two) {
-                // X1 = act(D0 + b0) -> TF32 hi/lo -> TMEM operand of layer 1
 #pragma unroll 1
-                for (int hf = 0; hf < 2; ++hf) {
-                    uint32_t v[32], lo[32];
-                    tmem_ld32(lane_addr + RC_D0 + hf * 32, v);
-                    tmem_wait_ld();
+            for (int hf = 0; hf < 2; ++hf) {
+                uint32_t v[32], lo[32];
+                tmem_ld32(lane_addr + RC_D0 + bo + hf * 32, v);
+                tmem_wait_ld();
 #pragma unroll
-                    for (int j = 0; j < 32; ++j) {
-                        const float y = act_do(a0, __uint_as_float(v[j]) + s_bias[hf * 32 + j]);
-                        const float hh = round_tf32(y);
-                        v[j] = __float_as_uint(hh);
-                        lo[j] = __float_as_uint(y - hh);
-                    }
-                    tmem_st32(lane_addr + RC_AHI + hf * 32, v);
-                    tmem_st32(lane_addr + RC_ALO + hf * 32, lo);
+                for (int j = 0; j < 32; ++j) {
+                    const float y = act_do(a0, __uint_as_float(v[j]) + s_bias[hf * 32 + j]);
+                    const float hh = round_tf32(y);
+                    v[j] = __float_as_uint(hh);
+                    lo[j] = __float_as_uint(y - hh);
                 }
-                tmem_wait_st();
-                tc_fence_before_sync();
-                mbar_arrive(&bar->d0_free);
-                mbar_arrive(&bar->x1_ready);
-                mbar_wait(&bar->d1_full, ph);
-                tc_fence_after_sync();
+                tmem_st32(lane_addr + RC_AHI + bo + hf * 32, v);
+                tmem_st32(lane_addr + RC_ALO + bo + hf * 32, lo);
             }
-            mbar_wait(&bar->st_empty, ph ^ 1);                            // stage consumed (tile i-1)
+            tmem_wait_st();
+            tc_fence_before_sync();
+            mbar_arrive(&bar->d0_free[b]);
+            mbar_arrive(&bar->x1_ready[b]);
+        };
+#pragma unroll 1
+        for (int i = -1; i < n_my; ++i) {
+            if (two && i + 1 < n_my) e0(i + 1);
+            if (i < 0) continue;
+            const uint32_t b = (uint32_t)i & 1, bph = ((uint32_t)i >> 1) & 1, bo = b * 64;
+            if (lq == 0) R_STAMP(1, i, 1);
+            if (two) mbar_wait(&bar->d1_full[b], bph); else mbar_wait(&bar->d0_full[b], bph);
+            tc_fence_after_sync();
+            mbar_wait(&bar->st_empty[b], bph ^ 1);                        // this stage buffer consumed (tile i-2)
+            float* my_row = my_row0 + b * (R_TILE * R_STAGE_LD);
             if (lq == 0) R_STAMP(1, i, 2);
+            const uint32_t dcol = (two ? RC_D1 : RC_D0) + bo;
 #pragma unroll 1
             for (int hf = 0; hf < 2; ++hf) {
                 uint32_t v[32];
-                tmem_ld32(lane_addr + dcol_l + hf * 32, v);
+                tmem_ld32(lane_addr + dcol + hf * 32, v);
                 tmem_wait_ld();
 #pragma unroll
                 for (int j = 0; j < 32; j += 4) {
@@ -362,25 +423,27 @@ __global__ void __launch_bounds__(R_THREADS, 1) row_mlp_tc_kernel(const __grid_c
                 }
             }
             tc_fence_before_sync();
-            if (!two) mbar_arrive(&bar->d0_free);
-            mbar_arrive(&bar->st_full);
+            if (two) mbar_arrive(&bar->d1_free[b]); else mbar_arrive(&bar->d0_free[b]);
+            mbar_arrive(&bar->st_full[b]);
             if (lq == 0) R_STAMP(1, i, 3);
         }
     } else {
         // =====================================================================================
-        // MMA issuer
+        // MMA issuer.  L0(0) ; for i: { L0(i + 1) ; L1(i) }
         // =====================================================================================
         if (lane == 0) {
             const uint32_t idesc = make_idesc_tf32(R_TILE, RF);
             const uint32_t a_u32 = smem_u32(a_slot), w_u32 = smem_u32(w_tile);
-            for (int i = 0; i < n_my; ++i) {
+            auto l0 = [&](int i) {
                 const uint32_t ph = (uint32_t)i & 1;
+                const uint32_t b = (uint32_t)i & 1, bph = ((uint32_t)i >> 1) & 1;
                 R_STAMP(2, i, 0);
-                mbar_wait(&bar->d0_free, ph ^ 1);                         // D0 of tile i-1 has been read
+                mbar_wait(&bar->d0_free[b], bph ^ 1);                     // D0[b] of tile i-2 has been read
                 R_STAMP(2, i, 1);
                 mbar_wait(&bar->a_full, ph);
                 tc_fence_after_sync();
                 R_STAMP(2, i, 2);
+                const uint32_t d0 = tmem_base + RC_D0 + b * 64;
 #pragma unroll
                 for (int c = 0; c < 2; ++c) {
                     const uint32_t a_hi = a_u32 + c * 2 * R_A_TILE, a_lo = a_hi + R_A_TILE;
@@ -389,17 +452,24 @@ __global__ void __launch_bounds__(R_THREADS, 1) row_mlp_tc_kernel(const __grid_c
                     for (int ks = 0; ks < R_KC / 8; ++ks) {
                         const uint64_t dah = make_desc_sw128(a_hi + ks * 32), dal = make_desc_sw128(a_lo + ks * 32);
                         const uint64_t dwh = make_desc_sw128(w_hi + ks * 32), dwl = make_desc_sw128(w_lo + ks * 32);
-                        mma_tf32_ss(tmem_base + RC_D0, dal, dwh, idesc, (c | ks) ? 1u : 0u);
-                        mma_tf32_ss(tmem_base + RC_D0, dah, dwl, idesc, 1u);
-                        mma_tf32_ss(tmem_base + RC_D0, dah, dwh, idesc, 1u);
+                        mma_tf32_ss(d0, dal, dwh, idesc, (c | ks) ? 1u : 0u);
+                        mma_tf32_ss(d0, dah, dwl, idesc, 1u);
+                        mma_tf32_ss(d0, dah, dwh, idesc, 1u);
                     }
                 }
                 mma_commit(&bar->a_empty);
-                mma_commit(&bar->d0_full);
+                mma_commit(&bar->d0_full[b]);
                 R_STAMP(2, i, 3);
+            };
+            for (int i = -1; i < n_my; ++i) {
+                if (i + 1 < n_my) l0(i + 1);
+                if (i < 0) continue;
+                const uint32_t b = (uint32_t)i & 1, bph = ((uint32_t)i >> 1) & 1;
                 if (p.n_tc > 1) {
-                    mbar_wait(&bar->x1_ready, ph);
+                    mbar_wait(&bar->x1_ready[b], bph);
+                    mbar_wait(&bar->d1_free[b], bph ^ 1);                 // D1[b] of tile i-2 has been staged
                     tc_fence_after_sync();
+                    const uint32_t d1 = tmem_base + RC_D1 + b * 64, xh = tmem_base + RC_AHI + b * 64, xl = tmem_base + RC_ALO + b * 64;
 #pragma unroll
                     for (int c = 0; c < 2; ++c) {
                         const uint32_t w_hi = w_u32 + (uint32_t)R_W_IMAGE + c * 2 * R_W_TILE, w_lo = w_hi + R_W_TILE;
@@ -407,19 +477,19 @@ __global__ void __launch_bounds__(R_THREADS, 1) row_mlp_tc_kernel(const __grid_c
                         for (int ks = 0; ks < R_KC / 8; ++ks) {
                             const uint32_t kcol = c * R_KC + ks * 8;
                             const uint64_t dwh = make_desc_sw128(w_hi + ks * 32), dwl = make_desc_sw128(w_lo + ks * 32);
-                            mma_tf32_ts(tmem_base + RC_D1, tmem_base + RC_ALO + kcol, dwh, idesc, (c | ks) ? 1u : 0u);
-                            mma_tf32_ts(tmem_base + RC_D1, tmem_base + RC_AHI + kcol, dwl, idesc, 1u);
-                            mma_tf32_ts(tmem_base + RC_D1, tmem_base + RC_AHI + kcol, dwh, idesc, 1u);
+                            mma_tf32_ts(d1, xl + kcol, dwh, idesc, (c | ks) ? 1u : 0u);
+                            mma_tf32_ts(d1, xh + kcol, dwl, idesc, 1u);
+                            mma_tf32_ts(d1, xh + kcol, dwh, idesc, 1u);
                         }
                     }
-                    mma_commit(&bar->d1_full);
+                    mma_commit(&bar->d1_full[b]);
                 }
             }
         }
     }
     tc_fence_before_sync();
     __syncthreads();
-    if (warp == R_ROW_WARPS + R_EPI_WARPS) tmem_dealloc(tmem_base, 256);
+    if (warp == R_ROW_WARPS + R_EPI_WARPS) tmem_dealloc(tmem_base, 512);
 }
 
 }  // namespace tc

@@ -49,7 +49,7 @@ if os.environ.get("ONLY_DEC") or os.environ.get("ONLY_ENC"):
     tt = tr.cpu().view(3, 16, 8); t0 = int(tt[0, 3, 0])
     for tile in range(3, 7):
         for r, nm in enumerate(["row", "epi", "mma"]):
-            print(tile, nm, " ".join(str(int(tt[r, tile, e]) - t0) for e in range(6)))
+            print(tile, nm, " ".join(str(int(tt[r, tile, e]) - t0) for e in range(7)))
     sys.exit(0)
 for be in ("tc", "ffma"):
     os.environ["MSWE_ROWMLP"] = be
