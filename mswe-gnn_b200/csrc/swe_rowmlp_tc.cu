@@ -273,9 +273,9 @@ __global__ void __launch_bounds__(R_THREADS, 1) row_mlp_tc_kernel(const __grid_c
             } else {
                 // first encoder layer on CUDA cores: the 8 raw inputs of this thread's 4 rows, then one pass over k with
                 // the weights of its 4 columns read once per k (a float4 from shared memory) and used for all 4 rows
-                // (two rows at a time: with all four in flight the 32 inputs + 16 accumulators + the prefetched tile
-                //  did not fit the 80-register budget and the inner loop ran out of local memory)
-#pragma unroll 1
+                // (two rows per pass keeps the live set — inputs, accumulators, the weights of one k — inside the kernel's
+                //  80-register budget)
+#pragma unroll
                 for (int kp = 0; kp < 4; kp += 2) {
                     // the 8 inputs of a row live in two float4 NAMED per row (an indexed float[2][8] was placed in
                     // local memory: its STL/LDL were a quarter of all stall samples of the kernel)
