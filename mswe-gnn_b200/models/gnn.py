@@ -160,6 +160,11 @@ class _EncodeDecodeMixin:
         if not x.is_cuda:
             raise RuntimeError("mswe_gnn_b200 models run on CUDA tensors only (no CPU fallback); "
                                f"graph.x is on {x.device}")
+        if x.device.index is not None and x.device.index != torch.cuda.current_device():
+            # every launch goes to the raw stream of the CURRENT device (lib._stream); pointers of another device
+            # there end in an illegal address
+            raise RuntimeError(f"graph.x is on {x.device} but the current CUDA device is {torch.cuda.current_device()}; "
+                               f"wrap the call in `with torch.cuda.device({x.device.index}):`")
         if x.dtype != torch.float32:
             raise TypeError("graph.x must be float32")
         if x.shape[1] != self.num_node_features:

@@ -302,6 +302,7 @@ class PartitionedRollout:
         self.bc = self.graph.BC.to(device, torch.float32).contiguous()
         self.n_static_raw = self.x.shape[1] - model.previous_t * NUM_WATER_VARS
         self.launches_per_step = 0
+        self.done = 0                             # host mirror of the device step counter (bounds check in run())
         self._token = new_static_token()
 
     def _one_step(self):
@@ -321,10 +322,15 @@ class PartitionedRollout:
     def reset(self):
         self.x.copy_(self.graph.x)
         self.step.zero_()
+        self.done = 0
 
     def run(self, n_steps: Optional[int] = None):
-        for _ in range(self.T if n_steps is None else n_steps):
+        n = self.T - self.done if n_steps is None else int(n_steps)
+        if n < 0 or self.done + n > self.T:
+            raise ValueError(f"rollout of {self.T} steps: {self.done} done, {n} more requested (call reset() first)")
+        for _ in range(n):
             self._one_step()
+        self.done += n
         return self.preds
 
     def owned_predictions(self):
@@ -338,17 +344,22 @@ class PartitionedRollout:
 def allreduce_gradients(params: Sequence[torch.Tensor], group=None, average: bool = True):
     """One all-reduce of the flat fp32 gradient (811,309 floats = 3.25 MB for the default model)."""
     import torch.distributed as dist
-    ps = [p for p in params if p.grad is not None]
+    # the list must not depend on the data: a rank whose batch never touched a parameter (grad is None) still takes
+    # part with zeros, otherwise the flat buffers differ in length between ranks and the collective hangs or mixes
+    ps = [p for p in params if p.requires_grad]
     if not ps:
         return 0
-    flat = torch.cat([p.grad.reshape(-1) for p in ps])
+    flat = torch.cat([(p.grad if p.grad is not None else torch.zeros_like(p)).reshape(-1) for p in ps])
     dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=group)
     if average:
         flat /= dist.get_world_size(group)
     off = 0
     for p in ps:
-        n = p.grad.numel()
-        p.grad.copy_(flat[off:off + n].view_as(p.grad))
+        n = p.numel()
+        if p.grad is None:
+            p.grad = flat[off:off + n].view_as(p).clone()
+        else:
+            p.grad.copy_(flat[off:off + n].view_as(p.grad))
         off += n
     return flat.numel() * 4
 

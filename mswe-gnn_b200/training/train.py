@@ -97,7 +97,9 @@ class RolloutRunner:
             use_cuda_graph = os.environ.get("MSWE_CUDA_GRAPH", "1") != "0"
         self.use_cuda_graph = use_cuda_graph and self.T > 2
         self._graph = None
+        self._graph_stamp = None
         self.launches_per_step = 0
+        self.done = 0                        # host mirror of the device step counter (bounds check in run())
         self._token = new_static_token()     # renewed whenever x (and with it, possibly, the static columns) is replaced
 
     def _one_step(self):
@@ -114,9 +116,17 @@ class RolloutRunner:
                       pred_stride=self.preds.shape[1] * NUM_WATER_VARS, x_next=self.x)
         lib.step_advance(self.step)
 
+    def _replay_stamp(self):
+        """What a captured step silently depends on besides its own buffers: the weights (packed images are rebuilt
+        in eager steps only) and who last encoded the shared static workspace of this (model, plan)."""
+        ws = self.model._ws.get((self.plan.key, self.plan.n_nodes))
+        return (tuple((p.data_ptr(), p._version) for p in self.model.parameters()),
+                None if ws is None else ws.get("_static_owner"))
+
     def reset(self, x: Optional[torch.Tensor] = None):
         self.x.copy_(self.graph.x if x is None else x)
         self.step.zero_()
+        self.done = 0
         if x is not None:
             self._token = new_static_token() # other static columns: the hoisted tables are recomputed (and the
             self._graph = None               # captured step, which does not contain their producer, is re-captured)
@@ -124,21 +134,37 @@ class RolloutRunner:
     def run(self, n_steps: Optional[int] = None):
         """Advance `n_steps` (default: all remaining) steps; returns the prediction buffer
         ``[T, N, 2]`` (slot t holds step t)."""
-        n = self.T if n_steps is None else n_steps
+        n = self.T - self.done if n_steps is None else int(n_steps)
+        if n < 0 or self.done + n > self.T:
+            # the decode kernel writes slot `step` of preds and apply_bc reads BC[..., step]: going past T would run
+            # off the end of both buffers on the device
+            raise ValueError(f"rollout of {self.T} steps: {self.done} done, {n} more requested (call reset() first)")
+        ws = self.model._ws.get((self.plan.key, self.plan.n_nodes))
+        if self._graph is not None and self._replay_stamp() != self._graph_stamp:
+            self._graph = None                   # weights changed in place, or another runner re-encoded the shared
+                                                 # static workspace: the captured step would read stale features
         done = 0
         if self.use_cuda_graph and self._graph is None and n > 1:
+            if ws is not None:
+                ws["_static_owner"] = None       # forces the eager step below to re-encode the static features
+                self.model._xs_stamp = None
             self._one_step()                     # eager: lazy packing / allocation happen here
             done = 1
+            ws = self.model._ws.get((self.plan.key, self.plan.n_nodes))
+            if ws is not None:
+                ws["_static_owner"] = self._token
             g = torch.cuda.CUDAGraph()
             torch.cuda.synchronize()
             with torch.cuda.graph(g):
                 self._one_step()
             self._graph = g
+            self._graph_stamp = self._replay_stamp()
         for _ in range(done, n):
             if self._graph is not None:
                 self._graph.replay()
             else:
                 self._one_step()
+        self.done += n
         return self.preds
 
 

@@ -1,0 +1,155 @@
+"""GPU parity at the sizes BASELINE.json's configs name: the CUDA path against the
+oracle on the full cfg3 mesh, cfg2-train gradients on a full tri(160,160) graph, and per-stage fp64 checks
+of the tensor-core hop / row-MLP kernels.  The oracle runs on the box's host cores (cfg3: about half a
+minute per step), so these are the slow tests of the suite.
+
+Tolerances as in test_gpu_parity.py: forward rel-L2 <= 2e-5 and |Δ| <= 2e-5 + 1e-4·|ref| outside wet/dry
+flips; the second rollout step within 4x that (drift); gradients within max(2e-4, 20x the
+fp32-oracle-vs-fp64-oracle distance) per tensor."""
+import numpy as np
+import pytest
+import torch
+
+from helpers import REF_CONFIG_MODELS, assert_close_masked, build_model, rel_l2, spec_of
+from mswe_gnn_b200 import lib
+from mswe_gnn_b200.utils.synthetic import make_single_scale_mesh, make_tri_mesh
+from oracle import swe_oracle as O
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+FWD_RTOL, FWD_ATOL, FWD_L2 = 1e-4, 2e-5, 2e-5
+
+
+def test_cfg3_forward_and_rollout_vs_oracle():
+    """BASELINE.json configs[2]: default config.yaml mSWE-GNN on tri(712,712) = 1,346,574 nodes; forward and a
+    2-step rollout against oracle.swe_oracle.rollout (reference op order: per-hop masks, K x edge MLP,
+    scatter_add_; /root/reference/models/gnn.py:267-445, training/train.py:67-95)."""
+    from mswe_gnn_b200.training.train import rollout_test
+    ctor = dict(num_node_features=8, num_edge_features=1, num_scales=4, previous_t=3, **REF_CONFIG_MODELS)
+    meta = dict(model="MSGNN", ctor=ctor)
+    m = build_model(meta, device=DEV)
+    d = make_tri_mesh(712, 712, 4, seed=0, rollout_steps=2)
+    assert d.x.shape[0] == 1346574
+    sd = {k: v.cpu() for k, v in m.state_dict().items()}
+    ours = rollout_test(m, d.to(DEV)).cpu()                        # [N, 2, 2]
+    ref = O.rollout(sd, spec_of(meta), d, steps=2)
+    assert ours.shape == ref.shape
+    e0, e1 = rel_l2(ours[..., 0], ref[..., 0]), rel_l2(ours[..., 1], ref[..., 1])
+    assert e0 < FWD_L2, e0
+    assert e1 < 4 * FWD_L2, e1
+    assert_close_masked(ours[..., 0], ref[..., 0], FWD_RTOL, FWD_ATOL, "cfg3 step 0")
+    assert_close_masked(ours[..., 1], ref[..., 1], 4 * FWD_RTOL, 4 * FWD_ATOL, "cfg3 step 1")
+    # integer artefacts at this size: the dry mask is exact on both sides
+    assert bool(((ours[:, 0] == 0) | (ours[:, 0].abs() > 1e-4)).all())
+
+
+def test_cfg2_train_gradients_full_size_graph():
+    """BASELINE.json configs[1]: single-scale SWE-GNN training step; one full tri(160,160) graph (51,201 nodes,
+    the size of each of the 8 graphs of the batch), gradients against torch.autograd on the fp64 oracle
+    (/root/reference/training/train.py:125-145)."""
+    from test_gpu_backward import _train_compare
+    gc = {k: v for k, v in REF_CONFIG_MODELS.items() if k not in ("learned_pooling", "skip_connections")}
+    ctor = dict(num_node_features=8, num_edge_features=1, previous_t=3, n_GNN_layers=2, **gc)
+    data = make_single_scale_mesh(160, 160, rollout_steps=1, seed=5)
+    assert data.x.shape[0] == 51201
+    worst = _train_compare("GNN", ctor, data, 1)
+    print("cfg2-train worst parameter:", worst)
+
+
+# ------------------------------------------------------------------------------------------------
+# per-stage fp64 checks of the tensor-core hop and row-MLP kernels (direct, not via the FFMA kernels)
+# ------------------------------------------------------------------------------------------------
+def _csr_of(d):
+    n = d.x.shape[0]
+    ei = d.edge_index.to(DEV)
+    rowptr, src, dst, eid = lib.csr_build(ei[0], ei[1], None, 0, n, 0, n)
+    return n, rowptr, src, dst, eid
+
+
+@pytest.mark.parametrize("act,addend", [(0, False), ("tanh", True), ("prelu", False)])
+def test_hop_tc_stage_vs_fp64(act, addend):
+    """out[c] = act(o[c] + (sum_p s_p * (o[c] - o[src_p])) W^T + addend[c]) (models/gnn.py:428-443) in fp64 from the
+    same fp32 inputs; the aggregation is exact fp32 in edge order, the filter 3xTF32: rel-L2 <= 1e-5 (north_star)."""
+    from mswe_gnn_b200.lib import ACT_CODES
+    torch.manual_seed(11)
+    d = make_single_scale_mesh(40, 36, seed=3)
+    n, rowptr, src, dst, eid = _csr_of(d)
+    E = int(src.numel())
+    o = torch.randn(n, 64, device=DEV)
+    o[torch.rand(n, device=DEV) < 0.3] = 0.0
+    s = torch.randn(E, 64, device=DEV)
+    s = s / s.norm(dim=1, keepdim=True)
+    W = torch.randn(64, 64, device=DEV) / 8.0
+    add = torch.randn(n, 64, device=DEV) if addend else None
+    slope = torch.tensor([0.25], device=DEV) if act == "prelu" else None
+    img = torch.empty(lib.hop_tc_image_bytes(), dtype=torch.uint8, device=DEV)
+    lib.hop_tc_pack(W.contiguous(), img)
+    out = torch.empty(n, 64, device=DEV)
+    code = ACT_CODES[act] if isinstance(act, str) else 0
+    lib.propagate_hop_tc_fwd(o, o, s, rowptr, src, 0, n, img, True, False, add, code, slope, None, out)
+    # fp64 restatement
+    o64, s64, W64 = o.double().cpu(), s.double().cpu(), W.double().cpu()
+    srcl, dstl = src.long().cpu(), dst.long().cpu()
+    agg = torch.zeros(n, 64, dtype=torch.float64).index_add_(0, dstl, s64 * (o64[dstl] - o64[srcl]))
+    ref = o64 + agg @ W64.T
+    if addend:
+        ref = ref + add.double().cpu()
+    if act == "tanh":
+        ref = torch.tanh(ref)
+    elif act == "prelu":
+        ref = torch.where(ref > 0, ref, 0.25 * ref)
+    e = rel_l2(out.cpu(), ref)
+    assert e < 1e-5, e
+    assert float((out.cpu().double() - ref).abs().max()) < 1e-4
+
+
+def _make_mlp_weights(shapes, bias):
+    ws, bs = [], []
+    for (n_out, k) in shapes:
+        ws.append((torch.rand(n_out, k, device=DEV) * 2 - 1) / k ** 0.5)
+        bs.append((torch.rand(n_out, device=DEV) * 2 - 1) / k ** 0.5 if bias else None)
+    return ws, bs
+
+
+def _prelu64(x, a):
+    return torch.where(x > 0, x, a * x)
+
+
+@pytest.mark.parametrize("n_rows", [1, 127, 128, 129, 40000])
+def test_row_mlp_tc_encoder_stage_vs_fp64(n_rows):
+    """Encoder stack (Linear(8 -> 64) + PReLU on CUDA cores, two 64 -> 64 tcgen05 layers + PReLU; reference
+    models/models.py:121-146, gnn.py:284-294) against fp64 from the same fp32 inputs: rel-L2 <= 1e-5 per stack."""
+    import torch.nn as nn
+    from mswe_gnn_b200.engine import RowMlpTC
+    torch.manual_seed(5)
+    seq = nn.Sequential(nn.Linear(8, 64), nn.PReLU(), nn.Linear(64, 64), nn.PReLU(), nn.Linear(64, 64), nn.PReLU()).to(DEV)
+    with torch.no_grad():
+        seq[1].weight.fill_(0.2); seq[3].weight.fill_(0.3); seq[5].weight.fill_(0.1)
+    rm = RowMlpTC.for_encoder(seq, 64)
+    assert rm is not None
+    raw = torch.randn(n_rows, 8, device=DEV)
+    out = torch.full((n_rows, 64), float("nan"), device=DEV)
+    rm.encode(raw, 0, 8, False, (0, 0), None, 0, n_rows, out)
+    x = raw.double().cpu()
+    with torch.no_grad():
+        for i in (0, 2, 4):
+            x = x @ seq[i].weight.double().cpu().T + seq[i].bias.double().cpu()
+            x = _prelu64(x, float(seq[i + 1].weight))
+    e = rel_l2(out.cpu(), x)
+    assert e < 1e-5, e
+
+
+@pytest.mark.parametrize("n_rows", [1, 128, 129, 40000])
+def test_row_mlp_tc_linear_stage_vs_fp64(n_rows):
+    """o_0 = x_d W_0^T (models/gnn.py:401-402) on tcgen05 (3xTF32) against fp64: rel-L2 <= 1e-5."""
+    import torch.nn as nn
+    from mswe_gnn_b200.engine import RowMlpTC
+    torch.manual_seed(6)
+    lin = nn.Linear(64, 64, bias=False).to(DEV)
+    rm = RowMlpTC([lin], [None], "linear")
+    x = torch.randn(n_rows + 7, 64, device=DEV)
+    out = torch.full((n_rows + 7, 64), float("nan"), device=DEV)
+    rm.linear(x, 3, n_rows, out)
+    ref = x[3:3 + n_rows].double().cpu() @ lin.weight.detach().double().cpu().T
+    assert rel_l2(out[3:3 + n_rows].cpu(), ref) < 1e-5
+    assert bool(torch.isnan(out[:3]).all()) and bool(torch.isnan(out[3 + n_rows:]).all())      # guard rows untouched
