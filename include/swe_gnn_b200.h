@@ -150,6 +150,32 @@ int swe_edge_gate_tc_fwd(const float* xs, const float* xd_src, const float* xd_d
                          int32_t k1, const int32_t* act3, const float* const* slope3, int32_t normalize,
                          float* s_out, float* dbg, void* stream);
 
+/* swe_edge_gate_tc_fwd restricted to the 128-edge tiles tile_list[1 .. tile_list[0]] (device memory; tile t = edges
+ * [128 t, 128 t + 128)).  A fixed launch whatever the list holds: used as the range-guard fallback of
+ * swe_edge_gate_tc16_fwd inside captured graphs. */
+int swe_edge_gate_tc_fwd_listed(const float* xs, const float* xd_src, const float* xd_dst, const float* a,
+                                const int32_t* src, const int32_t* dst, int64_t n_edges, const void* image,
+                                int32_t k1, const int32_t* act3, const float* const* slope3, int32_t normalize,
+                                float* s_out, const int32_t* tile_list, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Edge gate on tcgen05 with fp16 hi/lo splits (kind::f16, K = 16 per instruction: half the tensor-core
+ * instructions of the 3xTF32 kernel, same three products, same fp32 accumulation).  Same contract and
+ * reference span as swe_edge_gate_fwd (models/gnn.py:414-426).  Operands are scaled by powers of two into fp16's
+ * exponent window: per matrix for the weights (wmax3 = HOST array of max |w| of the three layers, read when the
+ * image is packed), per row for the hidden activations, a fixed factor for the gathered layer-0 inputs — whose
+ * rows are range-checked while they are converted: tiles with a row maximum outside [2^-9, 2^11] are listed in
+ * flag_ws ((number of tiles + 1) int32 of scratch) and re-evaluated by swe_edge_gate_tc_fwd_listed from image_tf32
+ * (the swe_gate_tc_pack image of the same weights).  flag_ws == NULL skips the guard (tests).
+ * ------------------------------------------------------------------------------------------- */
+size_t swe_gate_tc16_image_bytes(int32_t k1);
+int swe_gate_tc16_pack(const float* w1, int32_t k1, const float* b1, const float* w2, const float* b2,
+                       const float* w3, const float* b3, const float* wmax3, void* image, void* stream);
+int swe_edge_gate_tc16_fwd(const float* xs, const float* xd_src, const float* xd_dst, const float* a,
+                           const int32_t* src, const int32_t* dst, int64_t n_edges, const void* image16,
+                           const void* image_tf32, int32_t k1, const int32_t* act3, const float* const* slope3,
+                           int32_t normalize, float* s_out, float* dbg, int32_t* flag_ws, void* stream);
+
 /* Decomposed first layer of the edge MLP: W1·[x_s[r]|x_s[c]|x_d[r]|x_d[c]|a] = P_src[r] + P_dst[c] + E·a with
  *   P_src[n] = A·x_s[n] + C·x_d[n]   (role 0),   P_dst[n] = B·x_s[n] + D·x_d[n]   (role 1; xd NULL drops D·x_d),
  * evaluated once per NODE (2·128² MAC) instead of once per edge.  swe_gate_partials_tc writes one table

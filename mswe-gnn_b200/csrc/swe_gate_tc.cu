@@ -102,7 +102,15 @@ struct GateTcParams {
     // TRAIN: work lists of the pre-activations that lie within the 3xTF32 error of the activation's kink (|pre| < tau):
     // entry = edge << 8 | column; swe_gate_fix_preacts re-evaluates exactly those in exact fp32 (see there)
     unsigned long long* fix_list[3]; int* fix_count; int fix_cap; float fix_tau;
+    // list mode (MODE 0): only the tiles tile_list[1 .. tile_list[0]] are evaluated — the tiles the fp16 kernel
+    // (swe_gate_tc16.cu) found outside its input window
+    const int32_t* tile_list;
 };
+
+__device__ __forceinline__ long long gate_tile_of(const GateTcParams& p, int i) {
+    const long long t = (long long)blockIdx.x + (long long)i * gridDim.x;
+    return p.tile_list ? (long long)p.tile_list[1 + t] : t;
+}
 
 __device__ __forceinline__ int l1_chunk_segment(const GateTcParams& p, int i) {
     // i-th ACTIVE chunk of layer 0 -> input segment (two 32-column chunks per 64-wide segment)
@@ -160,7 +168,11 @@ __global__ void __launch_bounds__(N_THREADS, 1) edge_gate_tc_kernel(const __grid
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int n_l1 = 2 * p.n_seg;                                            // active layer-0 chunks
     const int h_l1 = n_l1 / 2;
-    const long long n_tiles_all = (p.n_edges + TILE_ROWS - 1) / TILE_ROWS;
+    long long n_tiles_all = (p.n_edges + TILE_ROWS - 1) / TILE_ROWS;
+    if (p.tile_list) {
+        n_tiles_all = min((long long)p.tile_list[0], n_tiles_all);
+        if (n_tiles_all <= (long long)blockIdx.x) return;                             // (uniform over the CTA; usually: no tile at all)
+    }
     const int n_my = (int)((n_tiles_all - blockIdx.x + gridDim.x - 1) / gridDim.x);   // tiles of this CTA
 
     if (threadIdx.x == 0) {
@@ -196,7 +208,7 @@ __global__ void __launch_bounds__(N_THREADS, 1) edge_gate_tc_kernel(const __grid
         const uint32_t g_off0 = sw128_offset(r0, piece * 4);          // + i * 4096 for row r0 + 32 i
 
         auto load_ids = [&](int i) {                                  // endpoints of tile t_i -> s_ids[i & 1]
-            const long long e0 = ((long long)blockIdx.x + (long long)i * gridDim.x) * TILE_ROWS;
+            const long long e0 = gate_tile_of(p, i) * TILE_ROWS;
             int32_t* ids = s_ids + (i & 1) * 2 * TILE_ROWS;
             if (threadIdx.x < TILE_ROWS) {
                 long long e = e0 + threadIdx.x;
@@ -210,7 +222,7 @@ __global__ void __launch_bounds__(N_THREADS, 1) edge_gate_tc_kernel(const __grid
             asm volatile("bar.sync 1, 256;" ::: "memory");
         };
         auto gather = [&](int i, int c_lo, int c_hi) {                // layer-0 input chunks [c_lo, c_hi) of tile t_i
-            const long long e0 = ((long long)blockIdx.x + (long long)i * gridDim.x) * TILE_ROWS;
+            const long long e0 = gate_tile_of(p, i) * TILE_ROWS;
             const int32_t* ids = s_ids + (i & 1) * 2 * TILE_ROWS;
             auto issue = [&](int c, float4 (&v)[4]) {                 // 4 independent 16-B loads per thread
                 const int sg = l1_chunk_segment(p, c);
@@ -260,7 +272,7 @@ __global__ void __launch_bounds__(N_THREADS, 1) edge_gate_tc_kernel(const __grid
             if (MODE == 3 && layer == 0) {
                 // per-edge table in tile-transposed order [tile][column half][16-B chunk][row]: the 32 rows of a warp
                 // read 512 contiguous bytes per chunk (the table is padded to whole tiles)
-                const long long tile = (long long)blockIdx.x + (long long)i * gridDim.x;
+                const long long tile = gate_tile_of(p, i);
                 const float* pe = p.p_src + tile * (TILE_ROWS * GH) + hf * (TILE_ROWS * 64) + row * 4;
 #pragma unroll
                 for (int j = 0; j < 16; ++j) padd[j] = ldg4_stream(pe + j * (TILE_ROWS * 4));
@@ -314,7 +326,7 @@ __global__ void __launch_bounds__(N_THREADS, 1) edge_gate_tc_kernel(const __grid
                     for (int j = 0; j < 32; ++j) d[j] = __uint_as_float(v[j]);
                 }
                 if (TRAIN) {
-                    const long long e = ((long long)blockIdx.x + (long long)i * gridDim.x) * TILE_ROWS + row;
+                    const long long e = gate_tile_of(p, i) * TILE_ROWS + row;
                     if (e < p.n_edges) {
                         float* d = p.pre_out[layer] + e * GH + hf * 64 + cb * 32;
                         float mn = 3.4e38f, mx = 0.f;
@@ -379,7 +391,7 @@ __global__ void __launch_bounds__(N_THREADS, 1) edge_gate_tc_kernel(const __grid
             }
             const float* bias = s_bias + 256;
             if (TRAIN) {
-                const long long e = ((long long)blockIdx.x + (long long)i * gridDim.x) * TILE_ROWS + row;
+                const long long e = gate_tile_of(p, i) * TILE_ROWS + row;
                 if (e < p.n_edges) {
                     float* d = p.pre_out[2] + e * GF;
                     float mn = 3.4e38f, mx = 0.f;
@@ -429,7 +441,7 @@ __global__ void __launch_bounds__(N_THREADS, 1) edge_gate_tc_kernel(const __grid
             }
             float inv = 1.f;
             if (p.normalize) inv = 1.f / sqrtf(ss);                   // ss == 0 -> inf -> 0*inf = NaN -> 0 below
-            const long long e = ((long long)blockIdx.x + (long long)i * gridDim.x) * TILE_ROWS + row;
+            const long long e = gate_tile_of(p, i) * TILE_ROWS + row;
             if (e < p.n_edges) {
                 float* o = p.s_out + e * GF;
 #pragma unroll
@@ -466,7 +478,7 @@ __global__ void __launch_bounds__(N_THREADS, 1) edge_gate_tc_kernel(const __grid
                 const int buf = i & 1;
                 mbar_wait(&bar->d_full[buf], (uint32_t)(i >> 1) & 1);
                 tc_fence_after_sync();
-                const long long tile = (long long)blockIdx.x + (long long)i * gridDim.x;
+                const long long tile = gate_tile_of(p, i);
                 const long long e = tile * TILE_ROWS + row;
                 // per-node table: row-major [node][128]; per-edge table (src/dst given): the tile-transposed order
                 // MODE 3 reads (see there), all rows of the (padded) last tile included
@@ -706,6 +718,31 @@ extern "C" int swe_edge_gate_tc_fwd_traced(const float* xs, const float* xd_src,
         if (sg < 3 || (sg == 3 && xd_dst) || (sg == 4 && a)) p.segs[p.n_seg++] = sg;
     if (int r = gate_tc_launch(p, 0, stream)) return r;
     return check_launch("edge_gate_tc_fwd");
+}
+
+// list mode: the tiles tile_list[1 .. tile_list[0]] only (fallback of swe_edge_gate_tc16_fwd's range guard; the list lives
+// in device memory, so the launch is a fixed node of a captured graph and costs a few microseconds when it is empty)
+extern "C" int swe_edge_gate_tc_fwd_listed(const float* xs, const float* xd_src, const float* xd_dst, const float* a,
+                                           const int32_t* src, const int32_t* dst, int64_t n_edges, const void* image,
+                                           int32_t k1, const int32_t* act3, const float* const* slope3, int32_t normalize,
+                                           float* s_out, const int32_t* tile_list, void* stream) {
+    SWE_REQUIRE(xs && xd_src && src && dst && s_out && image && act3 && slope3 && tile_list && n_edges >= 0, SWE_E_INVAL,
+                "edge_gate_tc_listed: bad arguments");
+    SWE_REQUIRE(aligned16(xs) && aligned16(xd_src) && aligned16(s_out) && aligned16(image) && (!a || aligned16(a)) &&
+                (!xd_dst || aligned16(xd_dst)), SWE_E_ALIGN, "edge_gate_tc_listed: unaligned buffer");
+    SWE_REQUIRE(k1 == (a ? 5 : 4) * tc::GF, SWE_E_UNSUPP, "edge_gate_tc_listed: k1=%d does not match the inputs", k1);
+    if (n_edges == 0) return 0;
+    tc::GateTcParams p;
+    memset(&p, 0, sizeof(p));
+    p.xs = xs; p.xd_src = xd_src; p.xd_dst = xd_dst; p.a = a; p.src = src; p.dst = dst; p.n_edges = n_edges;
+    p.img = (const unsigned char*)image; p.n_l1_img = k1 / tc::KC;
+    for (int i = 0; i < 3; ++i) { p.act[i] = act3[i]; p.slope[i] = slope3[i]; }
+    p.normalize = normalize; p.s_out = s_out; p.tile_list = tile_list;
+    p.n_seg = 0;
+    for (int sg = 0; sg < 5; ++sg)
+        if (sg < 3 || (sg == 3 && xd_dst) || (sg == 4 && a)) p.segs[p.n_seg++] = sg;
+    if (int r = gate_tc_launch(p, 0, stream)) return r;
+    return check_launch("edge_gate_tc_fwd_listed");
 }
 
 // ---------------------------------------------------------------------------------------------

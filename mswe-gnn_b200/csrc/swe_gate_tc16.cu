@@ -1,0 +1,553 @@
+// Edge gate on tcgen05, second edition: fp16 hi/lo splits on kind::f16 (K = 16 per instruction) instead of TF32
+// hi/lo splits on kind::tf32 (K = 8).  Same arithmetic contract as swe_gate_tc.cu (models/gnn.py:414-426, F = 64,
+// 3-layer edge MLP 5F|4F -> 2F -> 2F -> F, fp32 accumulation in TMEM, result within rel 1e-5 per layer of fp32),
+// half the tensor-core instructions: 108 instead of 216 per 128-edge tile — the instruction count is what bounds the
+// TF32 kernel (tools/microbench/mma_rate2.cu: one tcgen05.mma with M = 128, N <= 128 retires per ~105-111 cycles
+// whatever its kind, so K = 16 per instruction does twice the work of K = 8).
+//
+// Precision.  x' = 2^e x is split as hi = rn16(x'), lo = rn16(x' - hi); |x' - hi - lo| <= max(2^-24 |x'|, 2^-25).
+// A·W ≈ A_lo·W_hi + A_hi·W_lo + A_hi·W_hi (dropped A_lo·W_lo <= 2^-22 |A||W|): the same three products as 3xTF32.
+// fp16 has 5 exponent bits, so every operand is scaled by a power of two (exact) into the window where both halves are
+// normal numbers:
+//   * weights: one exponent per matrix (max |w'| in [2^13, 2^14)), chosen when the image is packed;
+//   * hidden activations (layers 1, 2): one exponent per ROW (max |y'| in [2^13, 2^14)), formed in the epilogue that
+//     produces the row (the thread owns it) and undone in the next epilogue — no range restriction at all;
+//   * layer-0 inputs (five gathered segments, converted by different threads before the row's maximum is known):
+//     the fixed factor 16, i.e. an absolute resolution of 2^-29 (<= 2^-20 of the row's maximum inside the
+//     guarded window) and a ceiling of 4094.  The kernel tracks max |x| per
+//     row while it converts; a tile with a row outside [2^-9, 2^11] (never seen with O(1) encoder outputs, but
+//     nothing forbids it) is appended to a work list and redone by the TF32 kernel (swe_gate_tc.cu in list mode),
+//     so the result never depends on the window.
+//
+// One CTA, 18 warps, persistent over 128-edge tiles, TWO tiles in flight (ping-pong):
+//   warps 0-7 / 8-15 : row-worker group 0 / 1 (tiles k = g, g + 2, ...): gather + convert the layer-0 input into the
+//                      group's shared-memory ring (UMMA K-major, 64-byte swizzle, 32 fp16 per row), then the three
+//                      epilogues of the tile (thread = TMEM lane = edge, half of the columns): tcgen05.ld ->
+//                      descale, bias, activation -> row scale -> fp16 hi/lo -> tcgen05.st (next layer's A operand
+//                      stays in TMEM) / L2-normalise + store s_ij
+//   warp 16          : weight loader: W2, W3 resident in shared memory (96 KB, loaded once), W1 streamed in 16 KB chunks
+//                      through a 3-slot ring (cp.async.bulk + mbarrier tx) in the order the MMA issuer consumes them
+//   warp 17          : MMA issuer (one thread): a static interleave of the two tiles' layers so that every epilogue
+//                      of one group runs under MMAs of the other group:
+//                        m-th round: P0(2m) Q1(2m-1) P1(2m) Q2(2m-1) Q1(2m) P0(2m+1) Q2(2m) P1(2m+1)
+//                      (P0/P1 = first / second half of layer 0's K-chunks, Q1/Q2 = layers 1 / 2)
+// TMEM (512 columns): group g owns [256 g, 256 g + 256): D (128 fp32 columns, reused by the three layers),
+// A_hi (64 columns = 128 fp16), A_lo (64 columns).
+#include "swe_tc.cuh"
+
+namespace swe {
+namespace tc16 {
+using namespace swe::tc;
+
+constexpr int GF = 64, GH = 128;
+constexpr int KC = 32;                          // K elements per chunk = one 64-byte swizzled row
+constexpr int TILE = 128;
+constexpr int A_TILE = TILE * 64;               // [128 x 32] fp16 = 8 KB
+constexpr int A_SLOT = 2 * A_TILE;              // hi | lo
+constexpr int W1_CHUNK = 2 * GH * 64;           // [128 x 32] fp16 hi | lo = 16 KB
+constexpr int W3_CHUNK = 2 * GF * 64;           // [64 x 32]  fp16 hi | lo = 8 KB
+constexpr int W_RES_BYTES = 4 * W1_CHUNK + 4 * W3_CHUNK;      // W2 + W3 = 96 KB
+constexpr int A_STAGES = 2, W_STAGES = 3;
+constexpr int GROUP_THREADS = 256;
+constexpr int N_THREADS = 2 * GROUP_THREADS + 64;             // + loader warp 16 + MMA warp 17
+constexpr float L0_SCALE = 16.f;
+constexpr int N_IMG_FLOATS = 324;               // bias[320] | descale[3] | pad
+
+struct __align__(8) Bar {
+    uint64_t a_full[2][A_STAGES], a_empty[2][A_STAGES];
+    uint64_t w_full[W_STAGES], w_empty[W_STAGES];
+    uint64_t w_res;                             // resident W2 / W3 have landed
+    uint64_t d_full[2];                         // group g: accumulator complete (commit; 3 per tile)
+    uint64_t a_ready[2];                        // group g: next layer's A operand is in TMEM (256 arrivals; 2 per tile)
+    uint64_t d_free[2];                         // group g: the final epilogue has read D (256 arrivals; 1 per tile)
+};
+
+constexpr size_t SMEM_BYTES = 1024 + (size_t)W_RES_BYTES + (size_t)W_STAGES * W1_CHUNK + 4 * (size_t)A_SLOT +
+                              sizeof(float) * N_IMG_FLOATS + sizeof(int32_t) * 512 + sizeof(float) * 512 +
+                              sizeof(uint32_t) * 256 + sizeof(int) * 4 + sizeof(Bar) + 16;
+
+// image layout (bytes): W1 chunks | W2 chunks | W3 chunks | floats
+__host__ __device__ constexpr size_t img_w1_off(int chunk) { return (size_t)chunk * W1_CHUNK; }
+__host__ __device__ constexpr size_t img_w2_off(int n_l1) { return (size_t)n_l1 * W1_CHUNK; }
+__host__ __device__ constexpr size_t img_w3_off(int n_l1) { return (size_t)(n_l1 + 4) * W1_CHUNK; }
+__host__ __device__ constexpr size_t img_float_off(int n_l1) { return (size_t)(n_l1 + 4) * W1_CHUNK + 4 * (size_t)W3_CHUNK; }
+__host__ __device__ constexpr size_t img_bytes(int n_l1) { return img_float_off(n_l1) + N_IMG_FLOATS * sizeof(float); }
+
+// ---------------------------------------------------------------------------------------------
+// weight packing: Linear weights [n_out, k_in] (row-major = K-major) -> swizzled fp16 hi|lo chunk images;
+// exp3[l] = power-of-two exponent applied to layer l's weights (chosen by the host from max |w|)
+// ---------------------------------------------------------------------------------------------
+__global__ void gate_tc16_pack_kernel(const float* __restrict__ w1, int k1, const float* __restrict__ b1,
+                                      const float* __restrict__ w2, const float* __restrict__ b2,
+                                      const float* __restrict__ w3, const float* __restrict__ b3,
+                                      int e1, int e2, int e3, unsigned char* __restrict__ img) {
+    const int n_l1 = k1 / KC;
+    const int total = GH * k1 + GH * GH + GF * GH;
+    for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += gridDim.x * blockDim.x) {
+        const float* w; int n, k, kin, rows, ex; size_t base, chunk_bytes;
+        if (idx < GH * k1) { w = w1; kin = k1; n = idx / k1; k = idx % k1; rows = GH; ex = e1; base = 0; chunk_bytes = W1_CHUNK; }
+        else if (idx < GH * k1 + GH * GH) { int j = idx - GH * k1; w = w2; kin = GH; n = j / GH; k = j % GH; rows = GH; ex = e2; base = img_w2_off(n_l1); chunk_bytes = W1_CHUNK; }
+        else { int j = idx - GH * k1 - GH * GH; w = w3; kin = GH; n = j / GH; k = j % GH; rows = GF; ex = e3; base = img_w3_off(n_l1); chunk_bytes = W3_CHUNK; }
+        const float v = ldexpf(w[(size_t)n * kin + k], ex);
+        const __half h = __float2half_rn(v);
+        const __half l = __float2half_rn(v - __half2float(h));
+        const int kk = k % KC;
+        const size_t off = base + (size_t)(k / KC) * chunk_bytes + sw64_piece_offset(n, kk >> 3) + (kk & 7) * 2;
+        *reinterpret_cast<__half*>(img + off) = h;
+        *reinterpret_cast<__half*>(img + off + (size_t)rows * 64) = l;
+    }
+    float* f = reinterpret_cast<float*>(img + img_float_off(n_l1));
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < N_IMG_FLOATS; i += gridDim.x * blockDim.x) {
+        float v = 0.f;
+        if (i < 128) v = b1 ? b1[i] : 0.f;
+        else if (i < 256) v = b2 ? b2[i - 128] : 0.f;
+        else if (i < 320) v = b3 ? b3[i - 256] : 0.f;
+        else if (i == 320) v = ldexpf(1.f / L0_SCALE, -e1);          // D0 -> pre-activation of layer 0
+        else if (i == 321) v = ldexpf(1.f, -e2);                     // x the row's own 2^-e
+        else if (i == 322) v = ldexpf(1.f, -e3);
+        f[i] = v;
+    }
+}
+
+struct Gate16Params {
+    const float* xs; const float* xd_src; const float* xd_dst; const float* a;
+    const int32_t* src; const int32_t* dst;
+    long long n_edges;
+    const unsigned char* img; int n_l1_img;
+    int act[3]; const float* slope[3];
+    int normalize;
+    float* s_out;
+    float* dbg;                                   // optional [128*128 + 128*128 + 128*64] pre-activations (no bias) of tile 0
+    int n_seg; int segs[5];                       // layer-0 input segments in order (0 x_s[r], 1 x_s[c], 2 x_d[r], 3 x_d[c], 4 a_e)
+    int* flag_ws;                                 // [0] = number of flagged tiles, [1 + i] = tile ids (capacity: all tiles)
+};
+
+__device__ __noinline__ float act_generic16(int act, float v, float slope) { return act_apply(act, v, slope); }
+struct ActSel { int act; float slope; bool leaky; };
+__device__ __forceinline__ ActSel act_select(int act, const float* slope_p) {
+    ActSel a;
+    a.act = act;
+    a.leaky = (act == SWE_ACT_NONE || act == SWE_ACT_PRELU || act == SWE_ACT_RELU || act == SWE_ACT_LEAKYRELU);
+    a.slope = act == SWE_ACT_NONE ? 1.f : act == SWE_ACT_RELU ? 0.f : act == SWE_ACT_LEAKYRELU ? 0.1f
+              : (act == SWE_ACT_PRELU && slope_p) ? __ldg(slope_p) : 0.f;
+    return a;
+}
+template <bool GENERIC>
+__device__ __forceinline__ float act_do(const ActSel& a, float v) {
+    if (GENERIC) { if (!a.leaky) return act_generic16(a.act, v, a.slope); }
+    return fmaxf(v, 0.f) + a.slope * fminf(v, 0.f);
+}
+
+__device__ __forceinline__ void group_sync(int g) { asm volatile("bar.sync %0, 256;" ::"r"(1 + g) : "memory"); }
+
+template <bool GENERIC>
+__global__ void __launch_bounds__(N_THREADS, 1) edge_gate_tc16_kernel(const __grid_constant__ Gate16Params p) {
+    extern __shared__ unsigned char smem_raw[];
+    unsigned char* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+    unsigned char* w_res = smem;                                           // W2 (4 x 16 KB) | W3 (4 x 8 KB)
+    unsigned char* w_ring = w_res + W_RES_BYTES;
+    unsigned char* a_ring = w_ring + (size_t)W_STAGES * W1_CHUNK;          // [group][slot]
+    float* s_f = reinterpret_cast<float*>(a_ring + 4 * (size_t)A_SLOT);   // bias[320] | descale[3]
+    int32_t* s_ids = reinterpret_cast<int32_t*>(s_f + N_IMG_FLOATS);       // [group][src 128 | dst 128]
+    float* s_xch = reinterpret_cast<float*>(s_ids + 512);                  // [group][half][128]
+    uint32_t* s_rowmax = reinterpret_cast<uint32_t*>(s_xch + 512);         // [group][128] max |x| of the layer-0 input row (bits)
+    int* s_flag = reinterpret_cast<int*>(s_rowmax + 256);                  // [group]
+    Bar* bar = reinterpret_cast<Bar*>(s_flag + 4);
+    uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(bar + 1);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int n_l1 = 2 * p.n_seg, h_l1 = p.n_seg;
+    const long long n_tiles_all = (p.n_edges + TILE - 1) / TILE;
+    const int n_my = (int)((n_tiles_all - blockIdx.x + gridDim.x - 1) / gridDim.x);
+
+    if (threadIdx.x == 0) {
+        for (int g = 0; g < 2; ++g) {
+            for (int i = 0; i < A_STAGES; ++i) { mbar_init(&bar->a_full[g][i], GROUP_THREADS); mbar_init(&bar->a_empty[g][i], 1); }
+            mbar_init(&bar->d_full[g], 1); mbar_init(&bar->a_ready[g], GROUP_THREADS); mbar_init(&bar->d_free[g], GROUP_THREADS);
+        }
+        for (int i = 0; i < W_STAGES; ++i) { mbar_init(&bar->w_full[i], 1); mbar_init(&bar->w_empty[i], 1); }
+        mbar_init(&bar->w_res, 1);
+        fence_barrier_init();
+    }
+    {
+        const float* gf = reinterpret_cast<const float*>(p.img + img_float_off(p.n_l1_img));
+        for (int i = threadIdx.x; i < N_IMG_FLOATS; i += N_THREADS) s_f[i] = gf[i];
+        for (int i = threadIdx.x; i < 256; i += N_THREADS) s_rowmax[i] = 0u;
+        if (threadIdx.x < 4) s_flag[threadIdx.x] = 0;
+    }
+    if (warp == 16) tmem_alloc(tmem_holder, 512);
+    tc_fence_before_sync();
+    __syncthreads();
+    tc_fence_after_sync();
+    const uint32_t tmem_base = *tmem_holder;
+
+    if (warp < 16) {
+        // =====================================================================================
+        // row-worker groups
+        // =====================================================================================
+        const int g = warp >> 3, gw = warp & 7, q = gw & 3, hf = gw >> 2;
+        const int tg = threadIdx.x & 255;
+        const int row = q * 32 + lane;                                   // TMEM lane / edge within the tile
+        const uint32_t lane_addr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)g * 256u;
+        const uint32_t COL_D = 0, COL_AHI = 128, COL_ALO = 192;
+        const ActSel a0 = act_select(p.act[0], p.slope[0]), a1 = act_select(p.act[1], p.slope[1]), a2 = act_select(p.act[2], p.slope[2]);
+        int32_t* ids = s_ids + g * 256;
+        float* xch = s_xch + g * 256;
+        uint32_t* rowmax = s_rowmax + g * 128;
+        unsigned char* my_ring = a_ring + (size_t)g * A_STAGES * A_SLOT;
+        const int piece = tg & 3, r0 = tg >> 2;                          // gather: rows r0, r0 + 64; 8 floats (32 B) each
+        const uint32_t g_off = sw64_piece_offset(r0, piece);             // row r0 + 64: + 4096
+        uint32_t a_cnt = 0;
+        const int n_g = (n_my - g + 1) / 2;
+
+#pragma unroll 1
+        for (int j = 0; j < n_g; ++j) {
+            const long long tile = (long long)blockIdx.x + (long long)(g + 2 * j) * gridDim.x;
+            const long long e0 = tile * TILE;
+            // ---------------------------------------------------------------- endpoints of the tile
+            {
+                long long e = e0 + (tg & 127);
+                if (e >= p.n_edges) e = p.n_edges - 1;
+                ids[tg] = tg < 128 ? __ldg(p.src + e) : __ldg(p.dst + e);
+                group_sync(g);
+            }
+            // ---------------------------------------------------------------- gather + convert layer-0 input chunks
+            {
+                float m0 = 0.f, m1 = 0.f;
+                auto issue = [&](int c, float4 (&v)[4]) {
+                    const int sg = p.segs[c >> 1];
+                    const int koff = (c & 1) * KC + piece * 8;
+                    if (sg == 4) {
+#pragma unroll
+                        for (int u = 0; u < 2; ++u) {
+                            long long e = e0 + r0 + 64 * u;
+                            if (e >= p.n_edges) e = p.n_edges - 1;
+                            const float* ptr = p.a + e * GF + koff;
+                            v[2 * u] = ldg4_stream(ptr); v[2 * u + 1] = ldg4_stream(ptr + 4);
+                        }
+                    } else {
+                        const float* base = sg < 2 ? p.xs : (sg == 2 ? p.xd_src : p.xd_dst);
+                        const int32_t* idp = ids + ((sg & 1) ? 128 : 0) + r0;
+#pragma unroll
+                        for (int u = 0; u < 2; ++u) {
+                            const float* ptr = base + (long long)idp[64 * u] * GF + koff;
+                            v[2 * u] = ldg4(ptr); v[2 * u + 1] = ldg4(ptr + 4);
+                        }
+                    }
+                };
+                // loads run two chunks ahead of the conversion (a chunk's MMAs take ~670 cycles, an L2 round trip more)
+                float4 cur[4], nxt[4], nx2[4];
+                issue(0, cur);
+                if (n_l1 > 1) issue(1, nxt);
+#pragma unroll 1
+                for (int c = 0; c < n_l1; ++c, ++a_cnt) {
+                    if (c + 2 < n_l1) issue(c + 2, nx2);
+                    const uint32_t slot = a_cnt % A_STAGES;
+                    mbar_wait(&bar->a_empty[g][slot], ((a_cnt / A_STAGES) & 1) ^ 1);
+                    unsigned char* hi_t = my_ring + (size_t)slot * A_SLOT + g_off;
+#pragma unroll
+                    for (int u = 0; u < 2; ++u) {
+                        const float4 x = cur[2 * u], y = cur[2 * u + 1];
+                        const float mm = fmaxf(fmaxf(fmaxf(fabsf(x.x), fabsf(x.y)), fmaxf(fabsf(x.z), fabsf(x.w))),
+                                               fmaxf(fmaxf(fabsf(y.x), fabsf(y.y)), fmaxf(fabsf(y.z), fabsf(y.w))));
+                        if (u == 0) m0 = fmaxf(m0, mm); else m1 = fmaxf(m1, mm);
+                        uint4 hh, ll;
+                        split_f16x2(x.x * L0_SCALE, x.y * L0_SCALE, hh.x, ll.x);
+                        split_f16x2(x.z * L0_SCALE, x.w * L0_SCALE, hh.y, ll.y);
+                        split_f16x2(y.x * L0_SCALE, y.y * L0_SCALE, hh.z, ll.z);
+                        split_f16x2(y.z * L0_SCALE, y.w * L0_SCALE, hh.w, ll.w);
+                        *reinterpret_cast<uint4*>(hi_t + u * 4096) = hh;
+                        *reinterpret_cast<uint4*>(hi_t + A_TILE + u * 4096) = ll;
+                    }
+                    fence_proxy_async_smem();
+                    mbar_arrive(&bar->a_full[g][slot]);
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) { cur[u] = nxt[u]; nxt[u] = nx2[u]; }
+                }
+                // row maxima of the layer-0 input (range guard); NaN / inf inputs compare as huge and flag the tile
+                atomicMax(rowmax + r0, __float_as_uint(m0) & 0x7fffffffu);
+                atomicMax(rowmax + r0 + 64, __float_as_uint(m1) & 0x7fffffffu);
+            }
+            const bool dump = p.dbg != nullptr && blockIdx.x == 0 && g == 0 && j == 0;
+            float inv_scale = 1.f;                                       // 2^-e of the row's current A operand
+            // ---------------------------------------------------------------- epilogues of layers 0 and 1
+#pragma unroll 1
+            for (int layer = 0; layer < 2; ++layer) {
+                const ActSel& al = layer == 0 ? a0 : a1;
+                const float* bias = s_f + layer * 128 + hf * 64;
+                const float dsc = layer == 0 ? s_f[320] : s_f[321] * inv_scale;
+                mbar_wait(&bar->d_full[g], (uint32_t)(3 * j + layer) & 1);
+                tc_fence_after_sync();
+                // pass 1: the row's largest |activation| (this thread's 64 columns), nothing kept in registers
+                float m = 0.f;
+#pragma unroll
+                for (int cb = 0; cb < 2; ++cb) {
+                    uint32_t v[32];
+                    tmem_ld32(lane_addr + COL_D + hf * 64 + cb * 32, v);
+                    tmem_wait_ld();
+                    if (dump) {
+                        float* d = p.dbg + (size_t)layer * 128 * 128 + (size_t)row * 128 + hf * 64 + cb * 32;
+#pragma unroll
+                        for (int i = 0; i < 32; ++i) d[i] = __uint_as_float(v[i]) * dsc;
+                    }
+#pragma unroll
+                    for (int i = 0; i < 32; ++i)
+                        m = fmaxf(m, fabsf(act_do<GENERIC>(al, fmaf(__uint_as_float(v[i]), dsc, bias[cb * 32 + i]))));
+                }
+                xch[hf * 128 + row] = m;
+                group_sync(g);
+                m = fmaxf(m, xch[(hf ^ 1) * 128 + row]);
+                if (layer == 0 && hf == 0) {
+                    // range guard of the layer-0 conversion: every row's max |x| inside [2^-9, 2^11] (or exactly 0)
+                    const uint32_t mb = rowmax[row];
+                    rowmax[row] = 0u;
+                    if (mb != 0u && (mb < 0x3B000000u || mb > 0x45000000u)) atomicOr(s_flag + g, 1);
+                }
+                // row scale: max |y'| in [2^13, 2^14)  (biased exponent E of m -> 2^(140 - E), clamped)
+                const uint32_t E = __float_as_uint(m) >> 23;
+                uint32_t sb = 267u - E;
+                sb = sb > 253u ? 253u : sb;
+                const float scale = __uint_as_float(sb << 23);
+                inv_scale = __uint_as_float((254u - sb) << 23);
+                // (no second barrier: a thread rewrites its xch slot only after the next d_full, which needs the a_ready
+                //  arrival every thread of the group makes after this read)
+                // pass 2: activations again (TMEM reads are cheap, 64 live values are not), scaled, split, stored as the
+                // next layer's A operand: 8 packed columns = 16 K-elements per store
+#pragma unroll 1
+                for (int cb = 0; cb < 4; ++cb) {
+                    uint32_t v[16], hi[8], lo[8];
+                    tmem_ld16(lane_addr + COL_D + hf * 64 + cb * 16, v);
+                    tmem_wait_ld();
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) {
+                        const float t0 = act_do<GENERIC>(al, fmaf(__uint_as_float(v[2 * i]), dsc, bias[cb * 16 + 2 * i]));
+                        const float t1 = act_do<GENERIC>(al, fmaf(__uint_as_float(v[2 * i + 1]), dsc, bias[cb * 16 + 2 * i + 1]));
+                        split_f16x2(t0 * scale, t1 * scale, hi[i], lo[i]);
+                    }
+                    tmem_st8(lane_addr + COL_AHI + hf * 32 + cb * 8, hi);
+                    tmem_st8(lane_addr + COL_ALO + hf * 32 + cb * 8, lo);
+                }
+                tmem_wait_st();
+                tc_fence_before_sync();
+                mbar_arrive(&bar->a_ready[g]);
+            }
+            // ---------------------------------------------------------------- final epilogue: 32 columns per thread
+            {
+                mbar_wait(&bar->d_full[g], (uint32_t)(3 * j + 2) & 1);
+                tc_fence_after_sync();
+                const float dsc = s_f[322] * inv_scale;
+                const float* bias = s_f + 256 + hf * 32;
+                uint32_t v[32];
+                tmem_ld32(lane_addr + COL_D + hf * 32, v);
+                tmem_wait_ld();
+                tc_fence_before_sync();
+                mbar_arrive(&bar->d_free[g]);                            // D may be overwritten by the group's next tile
+                if (dump) {
+                    float* d = p.dbg + (size_t)2 * 128 * 128 + (size_t)row * 64 + hf * 32;
+#pragma unroll
+                    for (int i = 0; i < 32; ++i) d[i] = __uint_as_float(v[i]) * dsc;
+                }
+                float ss = 0.f;
+#pragma unroll
+                for (int i = 0; i < 32; ++i) {
+                    const float t = act_do<GENERIC>(a2, fmaf(__uint_as_float(v[i]), dsc, bias[i]));
+                    ss = fmaf(t, t, ss);
+                    v[i] = __float_as_uint(t);
+                }
+                xch[hf * 128 + row] = ss;
+                group_sync(g);
+                ss += xch[(hf ^ 1) * 128 + row];
+                float inv = 1.f;
+                if (p.normalize) inv = 1.f / sqrtf(ss);                  // ss == 0 -> inf -> 0 * inf = NaN -> 0 below
+                const long long e = e0 + row;
+                if (e < p.n_edges) {
+                    float* o = p.s_out + e * GF + hf * 32;
+#pragma unroll
+                    for (int i = 0; i < 32; i += 4) {
+                        float4 r;
+                        r.x = __uint_as_float(v[i]) * inv; r.y = __uint_as_float(v[i + 1]) * inv;
+                        r.z = __uint_as_float(v[i + 2]) * inv; r.w = __uint_as_float(v[i + 3]) * inv;
+                        r.x = (r.x != r.x) ? 0.f : r.x; r.y = (r.y != r.y) ? 0.f : r.y;      // NaN -> 0 (gnn.py:426)
+                        r.z = (r.z != r.z) ? 0.f : r.z; r.w = (r.w != r.w) ? 0.f : r.w;
+                        stg4(o + i, r);
+                    }
+                }
+                if (tg == 0 && s_flag[g]) {                              // (set during epilogue 0, two group barriers ago)
+                    s_flag[g] = 0;
+                    if (p.flag_ws) { const int k = atomicAdd(p.flag_ws, 1); p.flag_ws[1 + k] = (int)tile; }
+                }
+                // (the group barrier after the next tile's endpoint load orders this read of xch before its next write)
+            }
+        }
+    } else if (warp == 16) {
+        // =====================================================================================
+        // weight loader: W2 | W3 once, W1 chunks in the MMA issuer's order
+        // =====================================================================================
+        if (lane == 0 && n_my > 0) {
+            mbar_arrive_expect_tx(&bar->w_res, (uint32_t)W_RES_BYTES);
+            const unsigned char* src = p.img + img_w2_off(p.n_l1_img);
+            for (int i = 0; i < W_RES_BYTES / W1_CHUNK; ++i)
+                bulk_g2s(w_res + (size_t)i * W1_CHUNK, src + (size_t)i * W1_CHUNK, W1_CHUNK, &bar->w_res);
+            uint32_t w_cnt = 0;
+            auto load_p = [&](int c_lo, int c_hi) {
+                for (int c = c_lo; c < c_hi; ++c, ++w_cnt) {
+                    const uint32_t slot = w_cnt % W_STAGES;
+                    mbar_wait(&bar->w_empty[slot], ((w_cnt / W_STAGES) & 1) ^ 1);
+                    mbar_arrive_expect_tx(&bar->w_full[slot], (uint32_t)W1_CHUNK);
+                    bulk_g2s(w_ring + (size_t)slot * W1_CHUNK, p.img + img_w1_off(2 * p.segs[c >> 1] + (c & 1)), W1_CHUNK,
+                             &bar->w_full[slot]);
+                }
+            };
+            for (int m = 0; 2 * m - 1 < n_my; ++m) {
+                const int k0 = 2 * m, k1 = 2 * m + 1;
+                if (k0 < n_my) { load_p(0, h_l1); load_p(h_l1, n_l1); }
+                if (k1 < n_my) { load_p(0, h_l1); load_p(h_l1, n_l1); }
+            }
+        }
+    } else {
+        // =====================================================================================
+        // MMA issuer
+        // =====================================================================================
+        if (lane == 0 && n_my > 0) {
+            const uint32_t idesc128 = make_idesc_f16(128, 128), idesc64 = make_idesc_f16(128, 64);
+            const uint32_t a_ring_u32 = smem_u32(a_ring), w_ring_u32 = smem_u32(w_ring), w_res_u32 = smem_u32(w_res);
+            uint32_t a_cnt[2] = {0u, 0u};
+            uint32_t w_cnt = 0;
+            // layer 0 (SS): D (+)= A_chunk · W_chunkᵀ for chunks [c_lo, c_hi) of local tile k
+            auto P = [&](int k, int c_lo, int c_hi) {
+                const int g = k & 1, j = k >> 1;
+                const uint32_t d = tmem_base + (uint32_t)g * 256u;
+                if (c_lo == 0 && j >= 1) {
+                    mbar_wait(&bar->d_free[g], (uint32_t)(j - 1) & 1);   // the group's previous tile has left D
+                    tc_fence_after_sync();
+                }
+                for (int c = c_lo; c < c_hi; ++c, ++w_cnt) {
+                    const uint32_t ac = a_cnt[g]++;
+                    const uint32_t sa = ac % A_STAGES, sw = w_cnt % W_STAGES;
+                    mbar_wait(&bar->a_full[g][sa], (ac / A_STAGES) & 1);
+                    mbar_wait(&bar->w_full[sw], (w_cnt / W_STAGES) & 1);
+                    tc_fence_after_sync();
+                    const uint32_t a_hi = a_ring_u32 + (uint32_t)(g * A_STAGES + sa) * A_SLOT, a_lo = a_hi + A_TILE;
+                    const uint32_t w_hi = w_ring_u32 + sw * W1_CHUNK, w_lo = w_hi + W1_CHUNK / 2;
+#pragma unroll
+                    for (int ks = 0; ks < KC / 16; ++ks) {
+                        const uint64_t dah = make_desc_sw64(a_hi + ks * 32), dal = make_desc_sw64(a_lo + ks * 32);
+                        const uint64_t dwh = make_desc_sw64(w_hi + ks * 32), dwl = make_desc_sw64(w_lo + ks * 32);
+                        mma_f16_ss(d, dal, dwh, idesc128, (c | ks) ? 1u : 0u);
+                        mma_f16_ss(d, dah, dwl, idesc128, 1u);
+                        mma_f16_ss(d, dah, dwh, idesc128, 1u);
+                    }
+                    mma_commit(&bar->a_empty[g][sa]);
+                    mma_commit(&bar->w_empty[sw]);
+                }
+                if (c_hi == n_l1) mma_commit(&bar->d_full[g]);
+            };
+            // layers 1 / 2 (TS): A from TMEM, weights resident
+            auto Q = [&](int k, int layer) {
+                const int g = k & 1, j = k >> 1;
+                mbar_wait(&bar->a_ready[g], (uint32_t)(2 * j + layer - 1) & 1);
+                tc_fence_after_sync();
+                const uint32_t d = tmem_base + (uint32_t)g * 256u, a_hi = d + 128u, a_lo = d + 192u;
+                const uint32_t idesc = layer == 1 ? idesc128 : idesc64;
+                const uint32_t wb = layer == 1 ? w_res_u32 : w_res_u32 + 4u * W1_CHUNK;
+                const uint32_t chunk = layer == 1 ? (uint32_t)W1_CHUNK : (uint32_t)W3_CHUNK;
+#pragma unroll
+                for (int ks = 0; ks < GH / 16; ++ks) {
+                    const uint32_t w_hi = wb + (uint32_t)(ks >> 1) * chunk + (uint32_t)(ks & 1) * 32u, w_lo = w_hi + chunk / 2;
+                    const uint64_t dwh = make_desc_sw64(w_hi), dwl = make_desc_sw64(w_lo);
+                    mma_f16_ts(d, a_lo + ks * 8, dwh, idesc, ks ? 1u : 0u);
+                    mma_f16_ts(d, a_hi + ks * 8, dwl, idesc, 1u);
+                    mma_f16_ts(d, a_hi + ks * 8, dwh, idesc, 1u);
+                }
+                mma_commit(&bar->d_full[g]);
+            };
+            mbar_wait(&bar->w_res, 0);
+            tc_fence_after_sync();
+            for (int m = 0; 2 * m - 1 < n_my; ++m) {
+                const int k0 = 2 * m, k1 = 2 * m + 1, kp = 2 * m - 1;
+                if (k0 < n_my) P(k0, 0, h_l1);
+                if (kp >= 0) Q(kp, 1);
+                if (k0 < n_my) P(k0, h_l1, n_l1);
+                if (kp >= 0) Q(kp, 2);
+                if (k0 < n_my) Q(k0, 1);
+                if (k1 < n_my) P(k1, 0, h_l1);
+                if (k0 < n_my) Q(k0, 2);
+                if (k1 < n_my) P(k1, h_l1, n_l1);
+            }
+        }
+    }
+    tc_fence_before_sync();
+    __syncthreads();
+    if (warp == 16) tmem_dealloc(tmem_base, 512);
+}
+
+}  // namespace tc16
+}  // namespace swe
+
+using namespace swe;
+
+extern "C" size_t swe_gate_tc16_image_bytes(int32_t k1) { return tc16::img_bytes(k1 / tc16::KC); }
+
+extern "C" int swe_gate_tc16_pack(const float* w1, int32_t k1, const float* b1, const float* w2, const float* b2,
+                                  const float* w3, const float* b3, const float* wmax3, void* image, void* stream) {
+    SWE_REQUIRE(w1 && w2 && w3 && image && wmax3, SWE_E_INVAL, "gate_tc16_pack: null pointer");
+    SWE_REQUIRE(k1 == 4 * tc16::GF || k1 == 5 * tc16::GF, SWE_E_UNSUPP, "gate_tc16_pack: k1=%d (expected 256 or 320)", k1);
+    SWE_REQUIRE(aligned16(image), SWE_E_ALIGN, "gate_tc16_pack: image unaligned");
+    int ex[3];
+    for (int l = 0; l < 3; ++l) {
+        // max |w'| in [2^13, 2^14): 2^ex with ex = 13 - floor(log2 max|w|); an all-zero (or non-finite) matrix keeps ex = 0
+        const float m = wmax3[l];
+        int e = 0;
+        if (m > 0.f && m < 3.0e38f) { (void)frexpf(m, &e); e = 14 - e; }       // m = f * 2^e', f in [0.5, 1): floor(log2 m) = e' - 1
+        ex[l] = e < -100 ? -100 : (e > 100 ? 100 : e);
+    }
+    tc16::gate_tc16_pack_kernel<<<148, 256, 0, (cudaStream_t)stream>>>(w1, k1, b1, w2, b2, w3, b3, ex[0], ex[1], ex[2],
+                                                                       (unsigned char*)image);
+    return check_launch("gate_tc16_pack");
+}
+
+extern "C" int swe_edge_gate_tc_fwd_listed(const float*, const float*, const float*, const float*, const int32_t*, const int32_t*,
+                                           int64_t, const void*, int32_t, const int32_t*, const float* const*, int32_t, float*,
+                                           const int32_t*, void*);
+
+// image16: swe_gate_tc16_pack; image_tf32: swe_gate_tc_pack of the same weights (the fallback of tiles whose layer-0
+// inputs leave the fp16 window); flag_ws: (number of 128-edge tiles + 1) int32 of scratch
+extern "C" int swe_edge_gate_tc16_fwd(const float* xs, const float* xd_src, const float* xd_dst, const float* a,
+                                      const int32_t* src, const int32_t* dst, int64_t n_edges, const void* image16,
+                                      const void* image_tf32, int32_t k1, const int32_t* act3, const float* const* slope3,
+                                      int32_t normalize, float* s_out, float* dbg, int32_t* flag_ws, void* stream) {
+    SWE_REQUIRE(xs && xd_src && src && dst && s_out && image16 && act3 && slope3 && n_edges >= 0, SWE_E_INVAL,
+                "edge_gate_tc16: bad arguments");
+    SWE_REQUIRE(aligned16(xs) && aligned16(xd_src) && aligned16(s_out) && aligned16(image16) && (!a || aligned16(a)) &&
+                (!xd_dst || aligned16(xd_dst)), SWE_E_ALIGN, "edge_gate_tc16: unaligned buffer");
+    SWE_REQUIRE(k1 == (a ? 5 : 4) * tc16::GF, SWE_E_UNSUPP, "edge_gate_tc16: k1=%d does not match the inputs", k1);
+    SWE_REQUIRE(!flag_ws || image_tf32, SWE_E_INVAL, "edge_gate_tc16: the range-guard work list needs the TF32 image");
+    if (n_edges == 0) return 0;
+    tc16::Gate16Params p;
+    memset(&p, 0, sizeof(p));
+    p.xs = xs; p.xd_src = xd_src; p.xd_dst = xd_dst; p.a = a; p.src = src; p.dst = dst; p.n_edges = n_edges;
+    p.img = (const unsigned char*)image16; p.n_l1_img = k1 / tc16::KC;
+    bool generic = false;
+    for (int i = 0; i < 3; ++i) {
+        p.act[i] = act3[i]; p.slope[i] = slope3[i];
+        generic |= !(act3[i] == SWE_ACT_NONE || act3[i] == SWE_ACT_PRELU || act3[i] == SWE_ACT_RELU || act3[i] == SWE_ACT_LEAKYRELU);
+    }
+    p.normalize = normalize; p.s_out = s_out; p.dbg = dbg; p.flag_ws = flag_ws;
+    p.n_seg = 0;
+    for (int sg = 0; sg < 5; ++sg)
+        if (sg < 3 || (sg == 3 && xd_dst) || (sg == 4 && a)) p.segs[p.n_seg++] = sg;
+    void (*kern)(const tc16::Gate16Params) = generic ? tc16::edge_gate_tc16_kernel<true> : tc16::edge_gate_tc16_kernel<false>;
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc16::SMEM_BYTES);
+    if (e != cudaSuccess) { set_error("edge_gate_tc16 smem opt-in (%zu B): %s", tc16::SMEM_BYTES, cudaGetErrorString(e)); return (int)e; }
+    if (flag_ws) {
+        e = cudaMemsetAsync(flag_ws, 0, sizeof(int32_t), (cudaStream_t)stream);
+        if (e != cudaSuccess) { set_error("edge_gate_tc16 work-list reset: %s", cudaGetErrorString(e)); return (int)e; }
+    }
+    const long long n_tiles = (n_edges + tc16::TILE - 1) / tc16::TILE;
+    kern<<<grid_for(n_tiles, 1), tc16::N_THREADS, tc16::SMEM_BYTES, (cudaStream_t)stream>>>(p);
+    if (int r = check_launch("edge_gate_tc16_fwd")) return r;
+    if (flag_ws)
+        return swe_edge_gate_tc_fwd_listed(xs, xd_src, xd_dst, a, src, dst, n_edges, image_tf32, k1, act3, slope3, normalize,
+                                           s_out, flag_ws, stream);
+    return 0;
+}

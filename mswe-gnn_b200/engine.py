@@ -215,6 +215,36 @@ class PackedGateTC:
         slopes = [a.weight if isinstance(a, nn.PReLU) else None for a in self.acts]
         return codes, slopes
 
+    def image16(self):
+        """fp16 hi|lo image for the kind::f16 gate kernel (swe_gate_tc16_pack); the per-matrix power-of-two scales come
+        from max |w|, read on the host when the weights change (never inside a captured step)."""
+        stamp = tuple((p.data_ptr(), p._version) for l in self.linears for p in l.parameters())
+        if stamp != getattr(self, "_stamp16", None):
+            l1, l2, l3 = self.linears
+            k1 = l1.weight.shape[1]
+            dev = l1.weight.device
+            n = lib.gate_tc16_image_bytes(k1)
+            if getattr(self, "_img16", None) is None or self._img16.numel() != n or self._img16.device != dev:
+                self._img16 = torch.empty(n, dtype=torch.uint8, device=dev)
+            with torch.no_grad():
+                wmax = torch.stack([l.weight.detach().abs().max() for l in self.linears]).tolist()
+                lib.gate_tc16_pack(l1.weight.detach().contiguous(), None if l1.bias is None else l1.bias.detach(),
+                                   l2.weight.detach().contiguous(), None if l2.bias is None else l2.bias.detach(),
+                                   l3.weight.detach().contiguous(), None if l3.bias is None else l3.bias.detach(),
+                                   wmax, self._img16)
+            self._stamp16 = stamp
+        return self._img16
+
+    def flag_ws(self, n_edges: int):
+        """Scratch of the fp16 gate's range guard: tile count + one slot per 128-edge tile."""
+        need = (n_edges + 127) // 128 + 1
+        ws = getattr(self, "_flag_ws", None)
+        dev = self.linears[0].weight.device
+        if ws is None or ws.numel() < need or ws.device != dev:
+            ws = torch.zeros(need, dtype=torch.int32, device=dev)
+            self._flag_ws = ws
+        return ws
+
 
 def rowmlp_backend() -> str:
     """'tc' (tcgen05 row MLPs for encoders / W0 / decoder head, default for F = 64) or 'ffma'."""
@@ -387,9 +417,10 @@ def gate_layer0() -> str:
 
 
 def gate_backend() -> str:
-    """'tc' (tcgen05 3xTF32, default where eligible) or 'ffma' (exact-fp32 CUDA cores)."""
+    """'tc16' (tcgen05 with fp16 hi/lo splits, kind::f16, default where eligible), 'tc' (tcgen05 3xTF32) or 'ffma'
+    (exact-fp32 CUDA cores)."""
     import os
-    return os.environ.get("MSWE_GATE", "tc")
+    return os.environ.get("MSWE_GATE", "tc16")
 
 
 class SweGnnLauncher:
@@ -439,7 +470,14 @@ class SweGnnLauncher:
 
     def gate(self, es, xs, xd_src, xd_dst, a, s_buf, dbg=None, ptab=None):
         m = self.m
-        if self.tc is not None and gate_backend() == "tc":
+        backend = gate_backend()
+        if self.tc is not None and backend == "tc16" and gate_layer0() != "dec":
+            codes, slopes = self.tc.acts_and_slopes()
+            k1 = self.tc.linears[0].weight.shape[1]
+            lib.edge_gate_tc16_fwd(xs, xd_src, xd_dst, a, es.src, es.dst, es.n_edges, self.tc.image16(), self.tc.image(),
+                                   k1, codes, slopes, m.normalize, s_buf, dbg, self.tc.flag_ws(es.n_edges))
+            return
+        if self.tc is not None and backend in ("tc", "tc16"):
             codes, slopes = self.tc.acts_and_slopes()
             k1 = self.tc.linears[0].weight.shape[1]
             img = self.tc.image()

@@ -77,6 +77,12 @@ SIGNATURES = {
     "swe_gate_tc_pack": (C.c_int, [_p, _i32, _p, _p, _p, _p, _p, _p, _p]),
     "swe_edge_gate_tc_fwd": (C.c_int, [_p, _p, _p, _p, _p, _p, _i64, _p, _i32, C.POINTER(C.c_int32),
                                        C.POINTER(C.c_void_p), _i32, _p, _p, _p]),
+    "swe_edge_gate_tc_fwd_listed": (C.c_int, [_p, _p, _p, _p, _p, _p, _i64, _p, _i32, C.POINTER(C.c_int32),
+                                              C.POINTER(C.c_void_p), _i32, _p, _p, _p]),
+    "swe_gate_tc16_image_bytes": (_sz, [_i32]),
+    "swe_gate_tc16_pack": (C.c_int, [_p, _i32, _p, _p, _p, _p, _p, C.POINTER(C.c_float), _p, _p]),
+    "swe_edge_gate_tc16_fwd": (C.c_int, [_p, _p, _p, _p, _p, _p, _i64, _p, _p, _i32, C.POINTER(C.c_int32),
+                                         C.POINTER(C.c_void_p), _i32, _p, _p, _p, _p]),
     "swe_gate_partials_tc": (C.c_int, [_p, _p, _i32, _i32, _p, _i32, _i32, _p, _p]),
     "swe_edge_gate_tc_dec_fwd": (C.c_int, [_p, _p, _p, _p, _p, _i64, _p, _i32, C.POINTER(C.c_int32), C.POINTER(C.c_void_p),
                                            _i32, _p, _p]),
@@ -255,6 +261,37 @@ def edge_gate_tc_fwd(xs, xd_src, xd_dst, a, src, dst, n_edges, image, k1, acts, 
     _check(load().swe_edge_gate_tc_fwd(ptr(xs), ptr(xd_src), ptr(xd_dst), ptr(a), ptr(src, torch.int32),
                                        ptr(dst, torch.int32), n_edges, image.data_ptr(), k1, act3, slope3,
                                        int(normalize), ptr(s_out), ptr(dbg), _stream()), "swe_edge_gate_tc_fwd")
+
+
+def gate_tc16_image_bytes(k1: int) -> int:
+    return int(load().swe_gate_tc16_image_bytes(k1))
+
+
+def gate_tc16_pack(w1, b1, w2, b2, w3, b3, wmax3, image):
+    """wmax3: three host floats, max |w| of the three layers (the power-of-two weight scales are chosen from them)."""
+    wm = (C.c_float * 3)(*[float(v) for v in wmax3])
+    _check(load().swe_gate_tc16_pack(ptr(w1), w1.shape[1], ptr(b1), ptr(w2), ptr(b2), ptr(w3), ptr(b3), wm,
+                                     image.data_ptr(), _stream()), "swe_gate_tc16_pack")
+
+
+def edge_gate_tc16_fwd(xs, xd_src, xd_dst, a, src, dst, n_edges, image16, image_tf32, k1, acts, slopes, normalize, s_out,
+                       dbg=None, flag_ws=None):
+    act3 = (C.c_int32 * 3)(*acts)
+    slope3 = (C.c_void_p * 3)(*[None if s is None else ptr(s) for s in slopes])
+    _check(load().swe_edge_gate_tc16_fwd(ptr(xs), ptr(xd_src), ptr(xd_dst), ptr(a), ptr(src, torch.int32),
+                                         ptr(dst, torch.int32), n_edges, image16.data_ptr(),
+                                         None if image_tf32 is None else image_tf32.data_ptr(), k1, act3, slope3,
+                                         int(normalize), ptr(s_out), ptr(dbg), ptr(flag_ws, torch.int32), _stream()),
+           "swe_edge_gate_tc16_fwd")
+
+
+def edge_gate_tc_fwd_listed(xs, xd_src, xd_dst, a, src, dst, n_edges, image, k1, acts, slopes, normalize, s_out, tile_list):
+    act3 = (C.c_int32 * 3)(*acts)
+    slope3 = (C.c_void_p * 3)(*[None if s is None else ptr(s) for s in slopes])
+    _check(load().swe_edge_gate_tc_fwd_listed(ptr(xs), ptr(xd_src), ptr(xd_dst), ptr(a), ptr(src, torch.int32),
+                                              ptr(dst, torch.int32), n_edges, image.data_ptr(), k1, act3, slope3,
+                                              int(normalize), ptr(s_out), ptr(tile_list, torch.int32), _stream()),
+           "swe_edge_gate_tc_fwd_listed")
 
 
 def gate_static_partials_tc(xs, a, src, dst, n_edges, image, k1, p_out):

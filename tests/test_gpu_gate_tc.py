@@ -206,6 +206,7 @@ def test_rollout_with_hoisted_static_share_matches_full_gate(monkeypatch, with_W
     x2 = d.x.clone()
     x2[:, :2] = torch.randn_like(x2[:, :2]) * 3.0                   # other static features, same dynamic state
     out = {}
+    monkeypatch.setenv("MSWE_GATE", "tc")                            # the hoisting belongs to the 3xTF32 kernel
     with torch.no_grad():
         for mode in ("static", "full"):
             monkeypatch.setenv("MSWE_GATE_L0", mode)

@@ -21,10 +21,13 @@ mlp = make_mlp(320, 64, hidden_size=128, n_layers=3, bias=True, activation="prel
 tc = PackedGateTC(mlp); codes, slopes = tc.acts_and_slopes(); img = tc.image()
 pk = PackedMLP(mlp, [(64, 64)] * 5, {}); st = pk.struct()
 s = torch.empty(E, 64, device=DEV)
-which = os.environ.get("WHICH", "tc,ffma").split(",")
+which = os.environ.get("WHICH", "tc16,tc16ng,tc,ffma").split(",")
+img16 = tc.image16(); ws = tc.flag_ws(E)
 for name in which:
-    fn = (lambda: lib.edge_gate_tc_fwd(xs, xd, xd, a, src, dst, E, img, 320, codes, slopes, True, s, None)) if name == "tc" \
-        else (lambda: lib.edge_gate_fwd(xs, xd, xd, a, src, dst, E, st, True, s, 64))
+    fn = {"tc": lambda: lib.edge_gate_tc_fwd(xs, xd, xd, a, src, dst, E, img, 320, codes, slopes, True, s, None),
+          "tc16": lambda: lib.edge_gate_tc16_fwd(xs, xd, xd, a, src, dst, E, img16, img, 320, codes, slopes, True, s, None, ws),
+          "tc16ng": lambda: lib.edge_gate_tc16_fwd(xs, xd, xd, a, src, dst, E, img16, None, 320, codes, slopes, True, s, None, None),
+          "ffma": lambda: lib.edge_gate_fwd(xs, xd, xd, a, src, dst, E, st, True, s, 64)}[name]
     for _ in range(2): fn()
     torch.cuda.synchronize()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
