@@ -19,20 +19,23 @@
 //     nothing forbids it) is appended to a work list and redone by the TF32 kernel (swe_gate_tc.cu in list mode),
 //     so the result never depends on the window.
 //
-// One CTA, 18 warps, persistent over 128-edge tiles, TWO tiles in flight (ping-pong):
+// One CTA, 20 warps, persistent over 128-edge tiles, TWO tiles in flight (one per group, independent pipelines):
 //   warps 0-7 / 8-15 : row-worker group 0 / 1 (tiles k = g, g + 2, ...): gather + convert the layer-0 input into the
 //                      group's shared-memory ring (UMMA K-major, 64-byte swizzle, 32 fp16 per row), then the three
 //                      epilogues of the tile (thread = TMEM lane = edge, half of the columns): tcgen05.ld ->
 //                      descale, bias, activation -> row scale -> fp16 hi/lo -> tcgen05.st (next layer's A operand
 //                      stays in TMEM) / L2-normalise + store s_ij
-//   warp 16          : weight loader: W2, W3 resident in shared memory (96 KB, loaded once), W1 streamed in 16 KB chunks
-//                      through a 3-slot ring (cp.async.bulk + mbarrier tx) in the order the MMA issuer consumes them
-//   warp 17          : MMA issuer (one thread): a static interleave of the two tiles' layers so that every epilogue
-//                      of one group runs under MMAs of the other group:
-//                        m-th round: P0(2m) Q1(2m-1) P1(2m) Q2(2m-1) Q1(2m) P0(2m+1) Q2(2m) P1(2m+1)
-//                      (P0/P1 = first / second half of layer 0's K-chunks, Q1/Q2 = layers 1 / 2)
+//   warps 16, 17     : MMA issuer of group 0 / 1 (one thread each): layer 0 chunk by chunk as the gather publishes them
+//                      (SS), layers 1 and 2 (TS) as the epilogues publish their operand.  Two issuers because the
+//                      tensor pipe's instruction queue is shallow: a single thread's barrier waits and commits
+//                      (~400 cycles per 6-instruction chunk, on a scheduler it shares with four busy worker warps)
+//                      left the pipe idle half of the time; with one issuer per group the other group's instructions
+//                      fill those gaps, and every epilogue of one group runs under MMAs of the other
+//   warps 18, 19     : weight loader of group 0 / 1: W2 resident in shared memory (64 KB, loaded once); per tile the
+//                      W1 chunks and W3 stream through the group's 2-slot ring (cp.async.bulk + mbarrier tx)
 // TMEM (512 columns): group g owns [256 g, 256 g + 256): D (128 fp32 columns, reused by the three layers),
 // A_hi (64 columns = 128 fp16), A_lo (64 columns).
+#include <stdlib.h>
 #include "swe_tc.cuh"
 
 namespace swe {
@@ -46,25 +49,26 @@ constexpr int A_TILE = TILE * 64;               // [128 x 32] fp16 = 8 KB
 constexpr int A_SLOT = 2 * A_TILE;              // hi | lo
 constexpr int W1_CHUNK = 2 * GH * 64;           // [128 x 32] fp16 hi | lo = 16 KB
 constexpr int W3_CHUNK = 2 * GF * 64;           // [64 x 32]  fp16 hi | lo = 8 KB
-constexpr int W_RES_BYTES = 4 * W1_CHUNK + 4 * W3_CHUNK;      // W2 + W3 = 96 KB
-constexpr int A_STAGES = 2, W_STAGES = 3;
+constexpr int W_RES_BYTES = 4 * W1_CHUNK;       // W2 resident = 64 KB (W3 rides the ring: 2 slots of 2 K-chunks per tile)
+constexpr int A_STAGES = 2, W_STAGES = 2;           // per group
 constexpr int GROUP_THREADS = 256;
-constexpr int N_THREADS = 2 * GROUP_THREADS + 64;             // + loader warp 16 + MMA warp 17
+constexpr int N_THREADS = 2 * GROUP_THREADS + 128;            // + MMA issuers (warps 16, 17) + weight loaders (18, 19)
 constexpr float L0_SCALE = 16.f;
 constexpr int N_IMG_FLOATS = 324;               // bias[320] | descale[3] | pad
 
 struct __align__(8) Bar {
     uint64_t a_full[2][A_STAGES], a_empty[2][A_STAGES];
-    uint64_t w_full[W_STAGES], w_empty[W_STAGES];
-    uint64_t w_res;                             // resident W2 / W3 have landed
+    uint64_t w_full[2][W_STAGES], w_empty[2][W_STAGES];
+    uint64_t w_res;                             // resident W2 has landed
     uint64_t d_full[2];                         // group g: accumulator complete (commit; 3 per tile)
     uint64_t a_ready[2];                        // group g: next layer's A operand is in TMEM (256 arrivals; 2 per tile)
     uint64_t d_free[2];                         // group g: the final epilogue has read D (256 arrivals; 1 per tile)
 };
 
-constexpr size_t SMEM_BYTES = 1024 + (size_t)W_RES_BYTES + (size_t)W_STAGES * W1_CHUNK + 4 * (size_t)A_SLOT +
+constexpr size_t SMEM_BYTES = 1024 + (size_t)W_RES_BYTES + 2 * (size_t)W_STAGES * W1_CHUNK + 2 * (size_t)A_STAGES * A_SLOT +
                               sizeof(float) * N_IMG_FLOATS + sizeof(int32_t) * 512 + sizeof(float) * 512 +
                               sizeof(uint32_t) * 256 + sizeof(int) * 4 + sizeof(Bar) + 16;
+static_assert((size_t)A_STAGES * A_SLOT >= (size_t)TILE * GF * 4, "the output stage lives in the group's A ring");
 
 // image layout (bytes): W1 chunks | W2 chunks | W3 chunks | floats
 __host__ __device__ constexpr size_t img_w1_off(int chunk) { return (size_t)chunk * W1_CHUNK; }
@@ -120,6 +124,7 @@ struct Gate16Params {
     float* dbg;                                   // optional [128*128 + 128*128 + 128*64] pre-activations (no bias) of tile 0
     int n_seg; int segs[5];                       // layer-0 input segments in order (0 x_s[r], 1 x_s[c], 2 x_d[r], 3 x_d[c], 4 a_e)
     int* flag_ws;                                 // [0] = number of flagged tiles, [1 + i] = tile ids (capacity: all tiles)
+    long long* trace;                             // optional [3 roles][16 tiles][8 events] clock64 stamps of CTA 0 (profiling aid)
 };
 
 __device__ __noinline__ float act_generic16(int act, float v, float slope) { return act_apply(act, v, slope); }
@@ -144,10 +149,10 @@ template <bool GENERIC>
 __global__ void __launch_bounds__(N_THREADS, 1) edge_gate_tc16_kernel(const __grid_constant__ Gate16Params p) {
     extern __shared__ unsigned char smem_raw[];
     unsigned char* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
-    unsigned char* w_res = smem;                                           // W2 (4 x 16 KB) | W3 (4 x 8 KB)
+    unsigned char* w_res = smem;                                           // W2 (4 x 16 KB)
     unsigned char* w_ring = w_res + W_RES_BYTES;
-    unsigned char* a_ring = w_ring + (size_t)W_STAGES * W1_CHUNK;          // [group][slot]
-    float* s_f = reinterpret_cast<float*>(a_ring + 4 * (size_t)A_SLOT);   // bias[320] | descale[3]
+    unsigned char* a_ring = w_ring + 2 * (size_t)W_STAGES * W1_CHUNK;      // [group][slot]   (w_ring: [group][slot] too)
+    float* s_f = reinterpret_cast<float*>(a_ring + 2 * (size_t)A_STAGES * A_SLOT);   // bias[320] | descale[3]
     int32_t* s_ids = reinterpret_cast<int32_t*>(s_f + N_IMG_FLOATS);       // [group][src 128 | dst 128]
     float* s_xch = reinterpret_cast<float*>(s_ids + 512);                  // [group][half][128]
     uint32_t* s_rowmax = reinterpret_cast<uint32_t*>(s_xch + 512);         // [group][128] max |x| of the layer-0 input row (bits)
@@ -156,7 +161,7 @@ __global__ void __launch_bounds__(N_THREADS, 1) edge_gate_tc16_kernel(const __gr
     uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(bar + 1);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int n_l1 = 2 * p.n_seg, h_l1 = p.n_seg;
+    const int n_l1 = 2 * p.n_seg;
     const long long n_tiles_all = (p.n_edges + TILE - 1) / TILE;
     const int n_my = (int)((n_tiles_all - blockIdx.x + gridDim.x - 1) / gridDim.x);
 
@@ -165,7 +170,8 @@ __global__ void __launch_bounds__(N_THREADS, 1) edge_gate_tc16_kernel(const __gr
             for (int i = 0; i < A_STAGES; ++i) { mbar_init(&bar->a_full[g][i], GROUP_THREADS); mbar_init(&bar->a_empty[g][i], 1); }
             mbar_init(&bar->d_full[g], 1); mbar_init(&bar->a_ready[g], GROUP_THREADS); mbar_init(&bar->d_free[g], GROUP_THREADS);
         }
-        for (int i = 0; i < W_STAGES; ++i) { mbar_init(&bar->w_full[i], 1); mbar_init(&bar->w_empty[i], 1); }
+        for (int g = 0; g < 2; ++g)
+            for (int i = 0; i < W_STAGES; ++i) { mbar_init(&bar->w_full[g][i], 1); mbar_init(&bar->w_empty[g][i], 1); }
         mbar_init(&bar->w_res, 1);
         fence_barrier_init();
     }
@@ -195,10 +201,15 @@ __global__ void __launch_bounds__(N_THREADS, 1) edge_gate_tc16_kernel(const __gr
         float* xch = s_xch + g * 256;
         uint32_t* rowmax = s_rowmax + g * 128;
         unsigned char* my_ring = a_ring + (size_t)g * A_STAGES * A_SLOT;
-        const int piece = tg & 3, r0 = tg >> 2;                          // gather: rows r0, r0 + 64; 8 floats (32 B) each
-        const uint32_t g_off = sw64_piece_offset(r0, piece);             // row r0 + 64: + 4096
+        float* stage = reinterpret_cast<float*>(my_ring);               // [128][64] output rows, 16-byte pieces XOR-swizzled by row
+        // gather: 8 lanes x 16 B = the 128 contiguous bytes of a row's 32-float chunk (4 rows = 4 full lines per
+        // instruction); this thread: floats [4 l8, 4 l8 + 4) of rows rr + 32 u
+        const int l8 = tg & 7, rr = tg >> 3;
+        const uint32_t g_off = sw64_piece_offset(rr, l8 >> 1) + (l8 & 1) * 8;     // row rr + 32 u: + 2048 u
         uint32_t a_cnt = 0;
         const int n_g = (n_my - g + 1) / 2;
+        const bool tr = p.trace != nullptr && blockIdx.x == 0 && tg == 0;
+#define G_STAMP(j_, ev_) do { if (tr && (j_) < 16) p.trace[g * 128 + (j_) * 8 + (ev_)] = clock64(); } while (0)
 
 #pragma unroll 1
         for (int j = 0; j < n_g; ++j) {
@@ -211,63 +222,72 @@ __global__ void __launch_bounds__(N_THREADS, 1) edge_gate_tc16_kernel(const __gr
                 ids[tg] = tg < 128 ? __ldg(p.src + e) : __ldg(p.dst + e);
                 group_sync(g);
             }
+            G_STAMP(j, 0);
             // ---------------------------------------------------------------- gather + convert layer-0 input chunks
             {
-                float m0 = 0.f, m1 = 0.f;
+                float m[4] = {0.f, 0.f, 0.f, 0.f};
+                // this thread's four rows: endpoint ids and edge numbers once per tile
+                int32_t id_s[4], id_d[4], ea[4];                        // ea: edge number relative to the tile (clamped)
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    id_s[u] = ids[rr + 32 * u]; id_d[u] = ids[128 + rr + 32 * u];
+                    const long long e = e0 + rr + 32 * u;
+                    ea[u] = (int32_t)((e < p.n_edges ? e : p.n_edges - 1) - e0);
+                }
                 auto issue = [&](int c, float4 (&v)[4]) {
                     const int sg = p.segs[c >> 1];
-                    const int koff = (c & 1) * KC + piece * 8;
+                    const int koff = (c & 1) * KC + l8 * 4;
                     if (sg == 4) {
 #pragma unroll
-                        for (int u = 0; u < 2; ++u) {
-                            long long e = e0 + r0 + 64 * u;
-                            if (e >= p.n_edges) e = p.n_edges - 1;
-                            const float* ptr = p.a + e * GF + koff;
-                            v[2 * u] = ldg4_stream(ptr); v[2 * u + 1] = ldg4_stream(ptr + 4);
-                        }
+                        for (int u = 0; u < 4; ++u) v[u] = ldg4_stream(p.a + (e0 + ea[u]) * GF + koff);
                     } else {
-                        const float* base = sg < 2 ? p.xs : (sg == 2 ? p.xd_src : p.xd_dst);
-                        const int32_t* idp = ids + ((sg & 1) ? 128 : 0) + r0;
+                        const float* base = (sg < 2 ? p.xs : (sg == 2 ? p.xd_src : p.xd_dst)) + koff;
 #pragma unroll
-                        for (int u = 0; u < 2; ++u) {
-                            const float* ptr = base + (long long)idp[64 * u] * GF + koff;
-                            v[2 * u] = ldg4(ptr); v[2 * u + 1] = ldg4(ptr + 4);
-                        }
+                        for (int u = 0; u < 4; ++u) v[u] = ldg4(base + (long long)((sg & 1) ? id_d[u] : id_s[u]) * GF);
                     }
                 };
-                // loads run two chunks ahead of the conversion (a chunk's MMAs take ~670 cycles, an L2 round trip more)
-                float4 cur[4], nxt[4], nx2[4];
-                issue(0, cur);
-                if (n_l1 > 1) issue(1, nxt);
-#pragma unroll 1
-                for (int c = 0; c < n_l1; ++c, ++a_cnt) {
-                    if (c + 2 < n_l1) issue(c + 2, nx2);
+                auto convert = [&](const float4 (&v)[4]) {              // chunk a_cnt: split, store, publish
                     const uint32_t slot = a_cnt % A_STAGES;
                     mbar_wait(&bar->a_empty[g][slot], ((a_cnt / A_STAGES) & 1) ^ 1);
                     unsigned char* hi_t = my_ring + (size_t)slot * A_SLOT + g_off;
 #pragma unroll
-                    for (int u = 0; u < 2; ++u) {
-                        const float4 x = cur[2 * u], y = cur[2 * u + 1];
-                        const float mm = fmaxf(fmaxf(fmaxf(fabsf(x.x), fabsf(x.y)), fmaxf(fabsf(x.z), fabsf(x.w))),
-                                               fmaxf(fmaxf(fabsf(y.x), fabsf(y.y)), fmaxf(fabsf(y.z), fabsf(y.w))));
-                        if (u == 0) m0 = fmaxf(m0, mm); else m1 = fmaxf(m1, mm);
-                        uint4 hh, ll;
+                    for (int u = 0; u < 4; ++u) {
+                        const float4 x = v[u];
+                        m[u] = fmaxf(m[u], fmaxf(fmaxf(fabsf(x.x), fabsf(x.y)), fmaxf(fabsf(x.z), fabsf(x.w))));
+                        uint2 hh, ll;
                         split_f16x2(x.x * L0_SCALE, x.y * L0_SCALE, hh.x, ll.x);
                         split_f16x2(x.z * L0_SCALE, x.w * L0_SCALE, hh.y, ll.y);
-                        split_f16x2(y.x * L0_SCALE, y.y * L0_SCALE, hh.z, ll.z);
-                        split_f16x2(y.z * L0_SCALE, y.w * L0_SCALE, hh.w, ll.w);
-                        *reinterpret_cast<uint4*>(hi_t + u * 4096) = hh;
-                        *reinterpret_cast<uint4*>(hi_t + A_TILE + u * 4096) = ll;
+                        *reinterpret_cast<uint2*>(hi_t + u * 2048) = hh;
+                        *reinterpret_cast<uint2*>(hi_t + A_TILE + u * 2048) = ll;
                     }
                     fence_proxy_async_smem();
                     mbar_arrive(&bar->a_full[g][slot]);
-#pragma unroll
-                    for (int u = 0; u < 4; ++u) { cur[u] = nxt[u]; nxt[u] = nx2[u]; }
+                    ++a_cnt;
+                };
+                // Loads run two chunks ahead of the conversion (three register sets rotating BY NAME: a register copy
+                // at the end of an iteration would wait for the loads it copies), the ring three chunks ahead of the
+                // tensor core.
+                float4 b0[4], b1[4], b2[4];
+                issue(0, b0);
+                if (n_l1 > 1) issue(1, b1);
+#pragma unroll 1
+                for (int c = 0; c < n_l1; c += 3) {
+                    if (c + 2 < n_l1) issue(c + 2, b2);
+                    convert(b0);
+                    if (c + 1 < n_l1) {
+                        if (c + 3 < n_l1) issue(c + 3, b0);
+                        convert(b1);
+                    }
+                    if (c + 2 < n_l1) {
+                        if (c + 4 < n_l1) issue(c + 4, b1);
+                        convert(b2);
+                    }
                 }
                 // row maxima of the layer-0 input (range guard); NaN / inf inputs compare as huge and flag the tile
-                atomicMax(rowmax + r0, __float_as_uint(m0) & 0x7fffffffu);
-                atomicMax(rowmax + r0 + 64, __float_as_uint(m1) & 0x7fffffffu);
+#pragma unroll
+                for (int u = 0; u < 4; ++u) atomicMax(rowmax + rr + 32 * u, __float_as_uint(m[u]) & 0x7fffffffu);
             }
+            G_STAMP(j, 1);
             const bool dump = p.dbg != nullptr && blockIdx.x == 0 && g == 0 && j == 0;
             float inv_scale = 1.f;                                       // 2^-e of the row's current A operand
             // ---------------------------------------------------------------- epilogues of layers 0 and 1
@@ -278,8 +298,10 @@ __global__ void __launch_bounds__(N_THREADS, 1) edge_gate_tc16_kernel(const __gr
                 const float dsc = layer == 0 ? s_f[320] : s_f[321] * inv_scale;
                 mbar_wait(&bar->d_full[g], (uint32_t)(3 * j + layer) & 1);
                 tc_fence_after_sync();
-                // pass 1: the row's largest |activation| (this thread's 64 columns), nothing kept in registers
-                float m = 0.f;
+                G_STAMP(j, 2 + 2 * layer);
+                // pass 1: the row's largest |activation| (this thread's 64 columns), nothing kept in registers.
+                // Leaky family: |act(v)| = v (v > 0) or |slope| |v|, so the extremes of v are enough.
+                float m = 0.f, vmin = 0.f;
 #pragma unroll
                 for (int cb = 0; cb < 2; ++cb) {
                     uint32_t v[32];
@@ -291,9 +313,13 @@ __global__ void __launch_bounds__(N_THREADS, 1) edge_gate_tc16_kernel(const __gr
                         for (int i = 0; i < 32; ++i) d[i] = __uint_as_float(v[i]) * dsc;
                     }
 #pragma unroll
-                    for (int i = 0; i < 32; ++i)
-                        m = fmaxf(m, fabsf(act_do<GENERIC>(al, fmaf(__uint_as_float(v[i]), dsc, bias[cb * 32 + i]))));
+                    for (int i = 0; i < 32; ++i) {
+                        const float t = fmaf(__uint_as_float(v[i]), dsc, bias[cb * 32 + i]);
+                        if (GENERIC && !al.leaky) m = fmaxf(m, fabsf(act_generic16(al.act, t, al.slope)));
+                        else { m = fmaxf(m, t); vmin = fminf(vmin, t); }
+                    }
                 }
+                m = fmaxf(m, fabsf(al.slope) * -vmin);
                 xch[hf * 128 + row] = m;
                 group_sync(g);
                 m = fmaxf(m, xch[(hf ^ 1) * 128 + row]);
@@ -330,11 +356,13 @@ __global__ void __launch_bounds__(N_THREADS, 1) edge_gate_tc16_kernel(const __gr
                 tmem_wait_st();
                 tc_fence_before_sync();
                 mbar_arrive(&bar->a_ready[g]);
+                G_STAMP(j, 3 + 2 * layer);
             }
             // ---------------------------------------------------------------- final epilogue: 32 columns per thread
             {
                 mbar_wait(&bar->d_full[g], (uint32_t)(3 * j + 2) & 1);
                 tc_fence_after_sync();
+                G_STAMP(j, 6);
                 const float dsc = s_f[322] * inv_scale;
                 const float* bias = s_f + 256 + hf * 32;
                 uint32_t v[32];
@@ -359,121 +387,153 @@ __global__ void __launch_bounds__(N_THREADS, 1) edge_gate_tc16_kernel(const __gr
                 ss += xch[(hf ^ 1) * 128 + row];
                 float inv = 1.f;
                 if (p.normalize) inv = 1.f / sqrtf(ss);                  // ss == 0 -> inf -> 0 * inf = NaN -> 0 below
-                const long long e = e0 + row;
-                if (e < p.n_edges) {
-                    float* o = p.s_out + e * GF + hf * 32;
+                // rows go through a shared-memory stage (the group's idle A ring) so that the global stores are whole
+                // 256-byte rows, two per warp instruction, instead of 32 scattered 16-byte pieces (16-byte pieces of a row
+                // XOR-ed with the row number: conflict-free on both sides without padding — the ring is exactly 32 KB)
+                float* st = stage + row * GF;
 #pragma unroll
-                    for (int i = 0; i < 32; i += 4) {
-                        float4 r;
-                        r.x = __uint_as_float(v[i]) * inv; r.y = __uint_as_float(v[i + 1]) * inv;
-                        r.z = __uint_as_float(v[i + 2]) * inv; r.w = __uint_as_float(v[i + 3]) * inv;
-                        r.x = (r.x != r.x) ? 0.f : r.x; r.y = (r.y != r.y) ? 0.f : r.y;      // NaN -> 0 (gnn.py:426)
-                        r.z = (r.z != r.z) ? 0.f : r.z; r.w = (r.w != r.w) ? 0.f : r.w;
-                        stg4(o + i, r);
-                    }
+                for (int i = 0; i < 32; i += 4) {
+                    float4 r;
+                    r.x = __uint_as_float(v[i]) * inv; r.y = __uint_as_float(v[i + 1]) * inv;
+                    r.z = __uint_as_float(v[i + 2]) * inv; r.w = __uint_as_float(v[i + 3]) * inv;
+                    r.x = (r.x != r.x) ? 0.f : r.x; r.y = (r.y != r.y) ? 0.f : r.y;      // NaN -> 0 (gnn.py:426)
+                    r.z = (r.z != r.z) ? 0.f : r.z; r.w = (r.w != r.w) ? 0.f : r.w;
+                    *reinterpret_cast<float4*>(st + ((((hf * 32 + i) >> 2) ^ (row & 7)) << 2)) = r;
                 }
-                if (tg == 0 && s_flag[g]) {                              // (set during epilogue 0, two group barriers ago)
+                if (tg == 0 && s_flag[g]) {                              // (set during epilogue 0, group barriers ago)
                     s_flag[g] = 0;
                     if (p.flag_ws) { const int k = atomicAdd(p.flag_ws, 1); p.flag_ws[1 + k] = (int)tile; }
                 }
-                // (the group barrier after the next tile's endpoint load orders this read of xch before its next write)
+                group_sync(g);
+                {
+                    const int c4 = (tg & 15) * 4, r16 = tg >> 4;
+#pragma unroll
+                    for (int it = 0; it < 8; ++it) {
+                        const int r = it * 16 + r16;
+                        const long long e = e0 + r;
+                        const float4 val = *reinterpret_cast<const float4*>(stage + r * GF + (((c4 >> 2) ^ (r & 7)) << 2));
+                        if (e < p.n_edges) stg4(p.s_out + e * GF + c4, val);
+                    }
+                }
+                // (the group barrier after the next tile's endpoint load orders these reads before the next gather's
+                //  writes into the ring, and this tile's xch reads before its next write)
+                G_STAMP(j, 7);
             }
         }
-    } else if (warp == 16) {
+#undef G_STAMP
+    } else if (warp >= 18) {
         // =====================================================================================
-        // weight loader: W2 | W3 once, W1 chunks in the MMA issuer's order
+        // weight loader of group g: W2 once (loader 0); per tile of the group the W1 chunks, then W3 in two halves
         // =====================================================================================
+        const int g = warp - 18;
+        const int n_g = (n_my - g + 1) / 2;
         if (lane == 0 && n_my > 0) {
-            mbar_arrive_expect_tx(&bar->w_res, (uint32_t)W_RES_BYTES);
-            const unsigned char* src = p.img + img_w2_off(p.n_l1_img);
-            for (int i = 0; i < W_RES_BYTES / W1_CHUNK; ++i)
-                bulk_g2s(w_res + (size_t)i * W1_CHUNK, src + (size_t)i * W1_CHUNK, W1_CHUNK, &bar->w_res);
-            uint32_t w_cnt = 0;
-            auto load_p = [&](int c_lo, int c_hi) {
-                for (int c = c_lo; c < c_hi; ++c, ++w_cnt) {
-                    const uint32_t slot = w_cnt % W_STAGES;
-                    mbar_wait(&bar->w_empty[slot], ((w_cnt / W_STAGES) & 1) ^ 1);
-                    mbar_arrive_expect_tx(&bar->w_full[slot], (uint32_t)W1_CHUNK);
-                    bulk_g2s(w_ring + (size_t)slot * W1_CHUNK, p.img + img_w1_off(2 * p.segs[c >> 1] + (c & 1)), W1_CHUNK,
-                             &bar->w_full[slot]);
-                }
+            if (g == 0) {
+                mbar_arrive_expect_tx(&bar->w_res, (uint32_t)W_RES_BYTES);
+                const unsigned char* src = p.img + img_w2_off(p.n_l1_img);
+                for (int i = 0; i < W_RES_BYTES / W1_CHUNK; ++i)
+                    bulk_g2s(w_res + (size_t)i * W1_CHUNK, src + (size_t)i * W1_CHUNK, W1_CHUNK, &bar->w_res);
+            }
+            unsigned char* ring = w_ring + (size_t)g * W_STAGES * W1_CHUNK;
+            uint32_t slot = 0, ph = 0;
+            auto load = [&](const unsigned char* from) {
+                mbar_wait_spin(&bar->w_empty[g][slot], ph ^ 1);
+                mbar_arrive_expect_tx(&bar->w_full[g][slot], (uint32_t)W1_CHUNK);
+                bulk_g2s(ring + (size_t)slot * W1_CHUNK, from, W1_CHUNK, &bar->w_full[g][slot]);
+                if (++slot == W_STAGES) { slot = 0; ph ^= 1; }
             };
-            for (int m = 0; 2 * m - 1 < n_my; ++m) {
-                const int k0 = 2 * m, k1 = 2 * m + 1;
-                if (k0 < n_my) { load_p(0, h_l1); load_p(h_l1, n_l1); }
-                if (k1 < n_my) { load_p(0, h_l1); load_p(h_l1, n_l1); }
+            for (int j = 0; j < n_g; ++j) {
+                for (int c = 0; c < n_l1; ++c) load(p.img + img_w1_off(2 * p.segs[c >> 1] + (c & 1)));
+                load(p.img + img_w3_off(p.n_l1_img));
+                load(p.img + img_w3_off(p.n_l1_img) + W1_CHUNK);
             }
         }
     } else {
         // =====================================================================================
-        // MMA issuer
+        // MMA issuer of group g
         // =====================================================================================
-        if (lane == 0 && n_my > 0) {
+        const int g = warp - 16;
+        const int n_g = (n_my - g + 1) / 2;
+        if (lane == 0 && n_g > 0) {
             const uint32_t idesc128 = make_idesc_f16(128, 128), idesc64 = make_idesc_f16(128, 64);
-            const uint32_t a_ring_u32 = smem_u32(a_ring), w_ring_u32 = smem_u32(w_ring), w_res_u32 = smem_u32(w_res);
-            uint32_t a_cnt[2] = {0u, 0u};
-            uint32_t w_cnt = 0;
-            // layer 0 (SS): D (+)= A_chunk · W_chunkᵀ for chunks [c_lo, c_hi) of local tile k
-            auto P = [&](int k, int c_lo, int c_hi) {
-                const int g = k & 1, j = k >> 1;
-                const uint32_t d = tmem_base + (uint32_t)g * 256u;
-                if (c_lo == 0 && j >= 1) {
-                    mbar_wait(&bar->d_free[g], (uint32_t)(j - 1) & 1);   // the group's previous tile has left D
+            // shared-memory descriptors = constant high word | (address >> 4) | LBO bit: one 32-bit add per operand
+            const uint64_t desc_hi = make_desc_sw64(0) & 0xFFFFFFFF00000000ull;
+            const uint32_t desc_lo0 = (uint32_t)make_desc_sw64(0);
+            auto dsc = [&](uint32_t lo) { return desc_hi | (uint64_t)lo; };
+            const uint32_t a_ring_d = desc_lo0 + ((smem_u32(a_ring) + (uint32_t)g * A_STAGES * A_SLOT) >> 4),
+                           w_ring_d = desc_lo0 + ((smem_u32(w_ring) + (uint32_t)g * W_STAGES * W1_CHUNK) >> 4),
+                           w_res_d = desc_lo0 + (smem_u32(w_res) >> 4);
+            const uint32_t d = tmem_base + (uint32_t)g * 256u, ta_hi = d + 128u, ta_lo = d + 192u;
+            uint32_t a_slot = 0, a_ph = 0, w_slot = 0, w_ph = 0;       // ring positions stepped by compare-and-wrap
+            const bool tr = p.trace != nullptr && blockIdx.x == 0;
+#define M_STAMP(j_, ev_) do { if (tr && (j_) < 8) p.trace[2 * 128 + (2 * (j_) + g) * 8 + (ev_)] = clock64(); } while (0)
+            mbar_wait_spin(&bar->w_res, 0);
+            tc_fence_after_sync();
+#pragma unroll 1
+            for (int j = 0; j < n_g; ++j) {
+                // ---- layer 0 (SS): D (+)= A_chunk · W_chunkᵀ, chunk by chunk as the gather publishes them
+                if (j >= 1) {
+                    mbar_wait_spin(&bar->d_free[g], (uint32_t)(j - 1) & 1);  // the final epilogue of the previous tile has read D
                     tc_fence_after_sync();
                 }
-                for (int c = c_lo; c < c_hi; ++c, ++w_cnt) {
-                    const uint32_t ac = a_cnt[g]++;
-                    const uint32_t sa = ac % A_STAGES, sw = w_cnt % W_STAGES;
-                    mbar_wait(&bar->a_full[g][sa], (ac / A_STAGES) & 1);
-                    mbar_wait(&bar->w_full[sw], (w_cnt / W_STAGES) & 1);
+                M_STAMP(j, 0);
+#pragma unroll 1
+                for (int c = 0; c < n_l1; ++c) {
+                    mbar_wait_spin(&bar->a_full[g][a_slot], a_ph);
+                    mbar_wait_spin(&bar->w_full[g][w_slot], w_ph);
                     tc_fence_after_sync();
-                    const uint32_t a_hi = a_ring_u32 + (uint32_t)(g * A_STAGES + sa) * A_SLOT, a_lo = a_hi + A_TILE;
-                    const uint32_t w_hi = w_ring_u32 + sw * W1_CHUNK, w_lo = w_hi + W1_CHUNK / 2;
-#pragma unroll
-                    for (int ks = 0; ks < KC / 16; ++ks) {
-                        const uint64_t dah = make_desc_sw64(a_hi + ks * 32), dal = make_desc_sw64(a_lo + ks * 32);
-                        const uint64_t dwh = make_desc_sw64(w_hi + ks * 32), dwl = make_desc_sw64(w_lo + ks * 32);
-                        mma_f16_ss(d, dal, dwh, idesc128, (c | ks) ? 1u : 0u);
-                        mma_f16_ss(d, dah, dwl, idesc128, 1u);
-                        mma_f16_ss(d, dah, dwh, idesc128, 1u);
-                    }
-                    mma_commit(&bar->a_empty[g][sa]);
-                    mma_commit(&bar->w_empty[sw]);
-                }
-                if (c_hi == n_l1) mma_commit(&bar->d_full[g]);
-            };
-            // layers 1 / 2 (TS): A from TMEM, weights resident
-            auto Q = [&](int k, int layer) {
-                const int g = k & 1, j = k >> 1;
-                mbar_wait(&bar->a_ready[g], (uint32_t)(2 * j + layer - 1) & 1);
-                tc_fence_after_sync();
-                const uint32_t d = tmem_base + (uint32_t)g * 256u, a_hi = d + 128u, a_lo = d + 192u;
-                const uint32_t idesc = layer == 1 ? idesc128 : idesc64;
-                const uint32_t wb = layer == 1 ? w_res_u32 : w_res_u32 + 4u * W1_CHUNK;
-                const uint32_t chunk = layer == 1 ? (uint32_t)W1_CHUNK : (uint32_t)W3_CHUNK;
-#pragma unroll
-                for (int ks = 0; ks < GH / 16; ++ks) {
-                    const uint32_t w_hi = wb + (uint32_t)(ks >> 1) * chunk + (uint32_t)(ks & 1) * 32u, w_lo = w_hi + chunk / 2;
-                    const uint64_t dwh = make_desc_sw64(w_hi), dwl = make_desc_sw64(w_lo);
-                    mma_f16_ts(d, a_lo + ks * 8, dwh, idesc, ks ? 1u : 0u);
-                    mma_f16_ts(d, a_hi + ks * 8, dwl, idesc, 1u);
-                    mma_f16_ts(d, a_hi + ks * 8, dwh, idesc, 1u);
+                    const uint32_t a_hi = a_ring_d + a_slot * (A_SLOT >> 4), a_lo = a_hi + (A_TILE >> 4);
+                    const uint32_t w_hi = w_ring_d + w_slot * (W1_CHUNK >> 4), w_lo = w_hi + (W1_CHUNK >> 5);
+                    mma_f16_ss(d, dsc(a_lo), dsc(w_hi), idesc128, c ? 1u : 0u);        // + 32 B per K = 16 step
+                    mma_f16_ss(d, dsc(a_hi), dsc(w_lo), idesc128, 1u);
+                    mma_f16_ss(d, dsc(a_hi), dsc(w_hi), idesc128, 1u);
+                    mma_f16_ss(d, dsc(a_lo + 2), dsc(w_hi + 2), idesc128, 1u);
+                    mma_f16_ss(d, dsc(a_hi + 2), dsc(w_lo + 2), idesc128, 1u);
+                    mma_f16_ss(d, dsc(a_hi + 2), dsc(w_hi + 2), idesc128, 1u);
+                    mma_commit(&bar->a_empty[g][a_slot]);
+                    mma_commit(&bar->w_empty[g][w_slot]);
+                    if (++a_slot == A_STAGES) { a_slot = 0; a_ph ^= 1; }
+                    if (++w_slot == W_STAGES) { w_slot = 0; w_ph ^= 1; }
                 }
                 mma_commit(&bar->d_full[g]);
-            };
-            mbar_wait(&bar->w_res, 0);
-            tc_fence_after_sync();
-            for (int m = 0; 2 * m - 1 < n_my; ++m) {
-                const int k0 = 2 * m, k1 = 2 * m + 1, kp = 2 * m - 1;
-                if (k0 < n_my) P(k0, 0, h_l1);
-                if (kp >= 0) Q(kp, 1);
-                if (k0 < n_my) P(k0, h_l1, n_l1);
-                if (kp >= 0) Q(kp, 2);
-                if (k0 < n_my) Q(k0, 1);
-                if (k1 < n_my) P(k1, 0, h_l1);
-                if (k0 < n_my) Q(k0, 2);
-                if (k1 < n_my) P(k1, h_l1, n_l1);
+                M_STAMP(j, 1);
+                // ---- layer 1 (TS): A from TMEM, W2 resident
+                mbar_wait_spin(&bar->a_ready[g], 0u);                        // (2 j) & 1
+                tc_fence_after_sync();
+                M_STAMP(j, 2);
+#pragma unroll
+                for (int ks = 0; ks < GH / 16; ++ks) {
+                    const uint32_t w_hi = w_res_d + (uint32_t)(ks >> 1) * (W1_CHUNK >> 4) + (uint32_t)(ks & 1) * 2u, w_lo = w_hi + (W1_CHUNK >> 5);
+                    mma_f16_ts(d, ta_lo + ks * 8, dsc(w_hi), idesc128, ks ? 1u : 0u);
+                    mma_f16_ts(d, ta_hi + ks * 8, dsc(w_lo), idesc128, 1u);
+                    mma_f16_ts(d, ta_hi + ks * 8, dsc(w_hi), idesc128, 1u);
+                }
+                mma_commit(&bar->d_full[g]);
+                M_STAMP(j, 3);
+                // ---- layer 2 (TS, N = 64): W3 in the group's two ring slots (two K-chunks each)
+                mbar_wait_spin(&bar->a_ready[g], 1u);                        // (2 j + 1) & 1
+                tc_fence_after_sync();
+                M_STAMP(j, 4);
+#pragma unroll
+                for (int half = 0; half < 2; ++half) {
+                    mbar_wait_spin(&bar->w_full[g][w_slot], w_ph);
+                    tc_fence_after_sync();
+#pragma unroll
+                    for (int kk = 0; kk < 4; ++kk) {
+                        const int ks = half * 4 + kk;
+                        const uint32_t w_hi = w_ring_d + w_slot * (W1_CHUNK >> 4) + (uint32_t)(kk >> 1) * (W3_CHUNK >> 4) + (uint32_t)(kk & 1) * 2u,
+                                       w_lo = w_hi + (W3_CHUNK >> 5);
+                        mma_f16_ts(d, ta_lo + ks * 8, dsc(w_hi), idesc64, ks ? 1u : 0u);
+                        mma_f16_ts(d, ta_hi + ks * 8, dsc(w_lo), idesc64, 1u);
+                        mma_f16_ts(d, ta_hi + ks * 8, dsc(w_hi), idesc64, 1u);
+                    }
+                    mma_commit(&bar->w_empty[g][w_slot]);
+                    if (++w_slot == W_STAGES) { w_slot = 0; w_ph ^= 1; }
+                }
+                mma_commit(&bar->d_full[g]);
+                M_STAMP(j, 5);
             }
+#undef M_STAMP
         }
     }
     tc_fence_before_sync();
@@ -485,6 +545,9 @@ __global__ void __launch_bounds__(N_THREADS, 1) edge_gate_tc16_kernel(const __gr
 }  // namespace swe
 
 using namespace swe;
+
+static long long* g_tc16_trace = nullptr;      // profiling aid: consumed by the next launch (tools/bench_gate.py)
+extern "C" void swe_gate_tc16_set_trace(long long* t) { g_tc16_trace = t; }
 
 extern "C" size_t swe_gate_tc16_image_bytes(int32_t k1) { return tc16::img_bytes(k1 / tc16::KC); }
 
@@ -533,6 +596,7 @@ extern "C" int swe_edge_gate_tc16_fwd(const float* xs, const float* xd_src, cons
         generic |= !(act3[i] == SWE_ACT_NONE || act3[i] == SWE_ACT_PRELU || act3[i] == SWE_ACT_RELU || act3[i] == SWE_ACT_LEAKYRELU);
     }
     p.normalize = normalize; p.s_out = s_out; p.dbg = dbg; p.flag_ws = flag_ws;
+    p.trace = g_tc16_trace; g_tc16_trace = nullptr;
     p.n_seg = 0;
     for (int sg = 0; sg < 5; ++sg)
         if (sg < 3 || (sg == 3 && xd_dst) || (sg == 4 && a)) p.segs[p.n_seg++] = sg;

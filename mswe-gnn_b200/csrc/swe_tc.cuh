@@ -50,6 +50,20 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
     }
 }
 
+// Same bounded wait without the nanosleep back-off: for the single-thread roles (MMA issuer, loaders), whose wake-up
+// latency sits on the tensor pipe's critical path and whose polling cannot crowd anything out
+__device__ __forceinline__ void mbar_wait_spin(uint64_t* bar, uint32_t parity) {
+    if (mbar_try_wait(bar, parity)) return;
+    const long long t0 = clock64();
+    while (!mbar_try_wait(bar, parity)) {
+        if (clock64() - t0 > 4000000000ll) {
+            printf("swe tc: mbarrier wait timed out (block %d thread %d bar %p parity %u)\n", blockIdx.x,
+                   threadIdx.x, (void*)bar, parity);
+            __trap();
+        }
+    }
+}
+
 // ---------------------------------------------------------------------------------------------
 // async-proxy data movement
 // ---------------------------------------------------------------------------------------------

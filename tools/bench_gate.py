@@ -108,3 +108,24 @@ if os.environ.get("TRACE_STAT"):
         for tile in range(2, 6):
             for r, nm in enumerate(["rowA(w0)", "rowB(w4)", "mma"]):
                 print("  ", tile, nm, [(int(v) - t0) if int(v) else None for v in t[r, tile, :6]])
+
+if os.environ.get("TRACE16"):
+    import ctypes as C
+    l = lib.load()
+    l.swe_gate_tc16_set_trace.argtypes = [C.c_void_p]
+    trace = torch.zeros(3 * 128 + 64, dtype=torch.int64, device=DEV)
+    l.swe_gate_tc16_set_trace(trace.data_ptr())
+    lib.edge_gate_tc16_fwd(xs, xd, xd, a, src, dst, E, img16, None, 320, codes, slopes, True, s, None, None)
+    torch.cuda.synchronize()
+    tc = trace.cpu()[384:]
+    t = trace.cpu()[:384].view(3, 16, 8)
+    t0 = int(t[0, 0, 0])
+    print("tc16 trace (cycles since group 0's first tile): rows = local tile of the role")
+    print("  groups: [ids done, gather done, D0 ready, E1 done, D1 ready, E2 done, D2 ready, E3 done]")
+    print("  mma   : [P0 start, P0 issued, P1 start, P1 issued, Q1 start, Q1 issued, Q2 start, Q2 issued]  (tile k: group k & 1)")
+    for r, nm in enumerate(["group0", "group1", "mma"]):
+        for tile in range(8):
+            print("  ", nm, tile, [(int(v) - t0) if int(v) else None for v in t[r, tile]])
+    print("  MMA issuer, layer 0 of tile 4, per chunk: [before waits, A chunk ready, W chunk ready, issued]")
+    for c in range(10):
+        print("    chunk", c, [(int(v) - t0) if int(v) else None for v in tc[4 * c:4 * c + 4]])
