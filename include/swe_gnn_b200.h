@@ -201,6 +201,16 @@ int swe_propagate_hop_tc_fwd(const float* o_src, const float* o_dst, const float
                              int32_t with_gradient, int32_t upwind, const float* addend, int32_t act,
                              const float* slope, float* agg_out, float* out, void* stream);
 
+/* The same hop with the filter as fp16 hi/lo splits on kind::f16 (K = 16 per instruction, 64-byte swizzle):
+ * agg rows are scaled per row, the filter per matrix (wmax = max |w|, a HOST value read when the image is packed) by powers
+ * of two; same contract, reference span (models/gnn.py:428-443) and accuracy as swe_propagate_hop_tc_fwd. */
+size_t swe_hop_tc16_image_bytes(void);
+int swe_hop_tc16_pack(const float* w, float wmax, void* image, void* stream);
+int swe_propagate_hop_tc16_fwd(const float* o_src, const float* o_dst, const float* s, const int32_t* rowptr,
+                               const int32_t* src, int32_t dst_lo, int32_t n_dst, const void* w_image,
+                               int32_t with_gradient, int32_t upwind, const float* addend, int32_t act,
+                               const float* slope, float* agg_out, float* out, void* stream);
+
 /* ---------------------------------------------------------------------------------------------
  * Row MLPs on tcgen05 (F = 64): encoders (models/gnn.py:281-294), filter_matrix[0] (gnn.py:401-402) and the decoder
  * head (gnn.py:339-348 + models/models.py:50-91 + utils/dataset.py:508-529) as ONE row-streaming kernel:

@@ -158,6 +158,22 @@ class PackedFilters:
             self._tc_stamp = stamp
         return [self._tc_img[i] for i in range(len(self.linears))]
 
+    def tc16_images(self) -> List[torch.Tensor]:
+        """fp16 hi|lo images (64-byte swizzle) of W_0..W_K for the kind::f16 hop kernel; the per-matrix power-of-two
+        scale comes from max |w|, read on the host when the weights change (never inside a captured step)."""
+        stamp = tuple((l.weight.data_ptr(), l.weight._version) for l in self.linears)
+        if stamp != getattr(self, "_tc16_stamp", None):
+            dev = self.linears[0].weight.device
+            nb = lib.hop_tc16_image_bytes()
+            if getattr(self, "_tc16_img", None) is None or self._tc16_img.device != dev:
+                self._tc16_img = torch.empty(len(self.linears), (nb + 255) // 256 * 256, dtype=torch.uint8, device=dev)
+            with torch.no_grad():
+                wmax = torch.stack([l.weight.detach().abs().max() for l in self.linears]).tolist()
+                for i, lin in enumerate(self.linears):
+                    lib.hop_tc16_pack(lin.weight.detach().contiguous(), wmax[i], self._tc16_img[i])
+            self._tc16_stamp = stamp
+        return [self._tc16_img[i] for i in range(len(self.linears))]
+
     def tensors(self) -> List[torch.Tensor]:
         stamp = tuple((l.weight.data_ptr(), l.weight._version) for l in self.linears)
         if stamp != self._stamp:
@@ -363,7 +379,9 @@ class RowMlpTC:
 
 
 def hop_backend() -> str:
-    """'tc' (tcgen05 filter, default for F = 64) or 'ffma' (exact-fp32 CUDA cores)."""
+    """'tc' (tcgen05 filter as 3xTF32, default for F = 64), 'tc16' (fp16 hi/lo splits: half the MMAs and half the operand
+    bytes, but the row-max shuffles and conversions land on the gather warps, which — not the tensor pipe — bound this
+    kernel: 0.414 vs 0.348 ms at cfg3 level 0) or 'ffma' (exact-fp32 CUDA cores)."""
     import os
     return os.environ.get("MSWE_HOP", "tc")
 
@@ -540,15 +558,17 @@ class SweGnnLauncher:
         if K > 1 and es.src_lo != es.dst_lo:
             raise NotImplementedError("multi-hop propagation needs source and destination in the same node set")
         bufs = [tmp_b, tmp_a] if o_src is tmp_a else [tmp_a, tmp_b]
-        use_tc = m.with_filter_matrix and self.F == 64 and FP == 64 and hop_backend() == "tc"
-        Wtc = self.filters.tc_images() if use_tc else None
+        hb = hop_backend()
+        use_tc = m.with_filter_matrix and self.F == 64 and FP == 64 and hb in ("tc", "tc16")
+        Wtc = (self.filters.tc16_images() if hb == "tc16" else self.filters.tc_images()) if use_tc else None
+        hop_tc = lib.propagate_hop_tc16_fwd if hb == "tc16" else lib.propagate_hop_tc_fwd
         for k in range(K):
             last = k == K - 1
             dst_buf = out if last else bufs[k % 2]
             if use_tc:
-                lib.propagate_hop_tc_fwd(o_src, o_dst, s_buf, es.rowptr, es.src, es.dst_lo, es.n_dst, Wtc[k + 1],
-                                         m.with_gradient, m.upwind_mode, addend if last else None,
-                                         act_code if last else 0, act_slope if last else None, None, dst_buf)
+                hop_tc(o_src, o_dst, s_buf, es.rowptr, es.src, es.dst_lo, es.n_dst, Wtc[k + 1],
+                       m.with_gradient, m.upwind_mode, addend if last else None,
+                       act_code if last else 0, act_slope if last else None, None, dst_buf)
             else:
                 lib.propagate_hop_fwd(o_src, o_dst, s_buf, es.rowptr, es.src, es.dst_lo, es.n_dst, W[k + 1],
                                       m.with_gradient, m.upwind_mode, addend if last else None,

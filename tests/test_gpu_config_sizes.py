@@ -66,8 +66,9 @@ def _csr_of(d):
     return n, rowptr, src, dst, eid
 
 
+@pytest.mark.parametrize("backend", ["tc", "tc16"])
 @pytest.mark.parametrize("act,addend", [(0, False), ("tanh", True), ("prelu", False)])
-def test_hop_tc_stage_vs_fp64(act, addend):
+def test_hop_tc_stage_vs_fp64(act, addend, backend):
     """out[c] = act(o[c] + (sum_p s_p * (o[c] - o[src_p])) W^T + addend[c]) (models/gnn.py:428-443) in fp64 from the
     same fp32 inputs; the aggregation is exact fp32 in edge order, the filter 3xTF32: rel-L2 <= 1e-5 (north_star)."""
     from mswe_gnn_b200.lib import ACT_CODES
@@ -82,11 +83,16 @@ def test_hop_tc_stage_vs_fp64(act, addend):
     W = torch.randn(64, 64, device=DEV) / 8.0
     add = torch.randn(n, 64, device=DEV) if addend else None
     slope = torch.tensor([0.25], device=DEV) if act == "prelu" else None
-    img = torch.empty(lib.hop_tc_image_bytes(), dtype=torch.uint8, device=DEV)
-    lib.hop_tc_pack(W.contiguous(), img)
     out = torch.empty(n, 64, device=DEV)
     code = ACT_CODES[act] if isinstance(act, str) else 0
-    lib.propagate_hop_tc_fwd(o, o, s, rowptr, src, 0, n, img, True, False, add, code, slope, None, out)
+    if backend == "tc16":
+        img = torch.empty(lib.hop_tc16_image_bytes(), dtype=torch.uint8, device=DEV)
+        lib.hop_tc16_pack(W.contiguous(), float(W.abs().max()), img)
+        lib.propagate_hop_tc16_fwd(o, o, s, rowptr, src, 0, n, img, True, False, add, code, slope, None, out)
+    else:
+        img = torch.empty(lib.hop_tc_image_bytes(), dtype=torch.uint8, device=DEV)
+        lib.hop_tc_pack(W.contiguous(), img)
+        lib.propagate_hop_tc_fwd(o, o, s, rowptr, src, 0, n, img, True, False, add, code, slope, None, out)
     # fp64 restatement
     o64, s64, W64 = o.double().cpu(), s.double().cpu(), W.double().cpu()
     srcl, dstl = src.long().cpu(), dst.long().cpu()

@@ -15,17 +15,31 @@ def _csr(ei, n):
     return lib.csr_build(ei[0].contiguous(), ei[1].contiguous(), None, 0, n, 0, n)
 
 
+BACKEND = ["tc"]          # "tc": 3xTF32 (swe_hop_tc.cu), "tc16": fp16 hi/lo splits (swe_hop_tc16.cu); set by the fixture below
+
+
+@pytest.fixture(autouse=True, params=["tc", "tc16"])
+def _backend(request):
+    BACKEND[0] = request.param
+    yield
+
+
 def _run_both(o, s, rowptr, src, n, W, with_grad, addend, act, slope, dst_lo=0, n_dst=None):
     n_dst = n if n_dst is None else n_dst
     wt = torch.empty(64, 64, device=DEV)
     lib.pack_linear(W.contiguous(), 64, wt)
-    img = torch.empty(lib.hop_tc_image_bytes(), dtype=torch.uint8, device=DEV)
-    lib.hop_tc_pack(W.contiguous(), img)
     ref = torch.zeros_like(o)
     out = torch.zeros_like(o)
     agg = torch.zeros_like(o)
     lib.propagate_hop_fwd(o, o, s, rowptr, src, dst_lo, n_dst, wt, with_grad, 0, addend, act, slope, ref, 64)
-    lib.propagate_hop_tc_fwd(o, o, s, rowptr, src, dst_lo, n_dst, img, with_grad, 0, addend, act, slope, agg, out)
+    if BACKEND[0] == "tc16":
+        img = torch.empty(lib.hop_tc16_image_bytes(), dtype=torch.uint8, device=DEV)
+        lib.hop_tc16_pack(W.contiguous(), float(W.abs().max()), img)
+        lib.propagate_hop_tc16_fwd(o, o, s, rowptr, src, dst_lo, n_dst, img, with_grad, 0, addend, act, slope, agg, out)
+    else:
+        img = torch.empty(lib.hop_tc_image_bytes(), dtype=torch.uint8, device=DEV)
+        lib.hop_tc_pack(W.contiguous(), img)
+        lib.propagate_hop_tc_fwd(o, o, s, rowptr, src, dst_lo, n_dst, img, with_grad, 0, addend, act, slope, agg, out)
     torch.cuda.synchronize()
     return ref, out, agg
 
@@ -77,3 +91,23 @@ def test_hop_tc_high_degree_and_row_range():
     ref, out, _ = _run_both(o, s_sub, rp_sub, src_sub, n, W, 1, None, 0, None, dst_lo=lo, n_dst=cnt)
     assert float((out - ref).abs().max()) <= 4e-6 * scale
     assert float(out[:lo].abs().max()) == 0 and float(out[lo + cnt:].abs().max()) == 0
+
+
+@pytest.mark.parametrize("mag", [1e-12, 1e-4, 1.0, 1e6])
+def test_hop_tc_rows_of_any_magnitude(mag):
+    """The fp16 kernel scales every agg row by its own power of two: node states of any magnitude (and rows that differ
+    by many orders of magnitude inside one tile) keep the same relative accuracy."""
+    torch.manual_seed(3)
+    d = make_single_scale_mesh(40, 31, seed=2)
+    n, e = d.x.shape[0], d.edge_index.shape[1]
+    rowptr, src, dst, eid = _csr(d.edge_index.to(DEV), n)
+    o = torch.randn(n, 64, device=DEV) * mag
+    o[::7] *= 1e3
+    o[3::11] *= 1e-3
+    s = torch.randn(e, 64, device=DEV)
+    s = s / s.norm(dim=1, keepdim=True)
+    W = torch.randn(64, 64, device=DEV) / 8
+    ref, out, _ = _run_both(o, s, rowptr, src, n, W, 1, None, 0, None)
+    err = (out.double() - ref.double()).norm(dim=1) / ref.double().norm(dim=1).clamp_min(1e-300)
+    assert bool(torch.isfinite(out).all())
+    assert float(err.max()) < 5e-6, float(err.max())           # per ROW, not per tile

@@ -14,6 +14,7 @@ rowptr, src, dst, eid = lib.csr_build(ei[0].contiguous(), ei[1].contiguous(), No
 o = torch.randn(n, 64, device=DEV); s = torch.randn(e, 64, device=DEV); W = torch.randn(64, 64, device=DEV) / 8
 wt = torch.empty(64, 64, device=DEV); lib.pack_linear(W, 64, wt)
 img = torch.empty(lib.hop_tc_image_bytes(), dtype=torch.uint8, device=DEV); lib.hop_tc_pack(W, img)
+img16 = torch.empty(lib.hop_tc16_image_bytes(), dtype=torch.uint8, device=DEV); lib.hop_tc16_pack(W, float(W.abs().max()), img16)
 out = torch.empty_like(o)
 bytes_alg = 4 * 64 * (e + 2 * n) + 4 * (e + n + 1)
 def run(which):
@@ -21,9 +22,11 @@ def run(which):
         lib.propagate_hop_fwd(o, o, s, rowptr, src, 0, n, None, 1, 0, None, 0, None, out, 64)
     elif which == "ffma":
         lib.propagate_hop_fwd(o, o, s, rowptr, src, 0, n, wt, 1, 0, None, 0, None, out, 64)
+    elif which == "tc16":
+        lib.propagate_hop_tc16_fwd(o, o, s, rowptr, src, 0, n, img16, 1, 0, None, 0, None, None, out)
     else:
         lib.propagate_hop_tc_fwd(o, o, s, rowptr, src, 0, n, img, 1, 0, None, 0, None, None, out)
-for which in os.environ.get("WHICH", "ffma,tc").split(","):
+for which in os.environ.get("WHICH", "nofilter,ffma,tc,tc16").split(","):
     for _ in range(3): run(which)
     torch.cuda.synchronize()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
