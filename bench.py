@@ -167,16 +167,59 @@ def run_reference(args):
 # our arm
 # --------------------------------------------------------------------------------------------------
 def mesh_for(world, wl):
-    """Workload mesh.  N=1: the named config.  N>1 (default workload): the cfg3 mesh grown so that every GPU keeps
-    cfg3's node count (weak scaling of ONE partitioned mesh): tri(712a, 712b) with a*b = N."""
+    """Workload mesh.  N=1: the named config.  N>1 (default workload): ONE partitioned mesh with a fixed share of
+    2 x cfg3's nodes per GPU (weak scaling), tri(712a, 712b) with a*b = 2N — so that N=8 is tri(2848,2848) = 21.5 M
+    nodes, the >= 16 M-node mesh of BASELINE.json configs[3] (cfg4 itself, tri(2832,2832), is `--workload cfg4`)."""
     nx, ny = WORKLOADS[wl]
     if world > 1 and wl == "cfg3":
         a = 1
-        while a * a < world:
+        while a * a < 2 * world:
             a *= 2
-        b = world // a
+        b = 2 * world // a
         nx, ny = nx * a, ny * b
     return nx, ny
+
+
+def partition_parity_check(model, dev, world, rank, full_graph=None, steps=3):
+    """Before anything is timed: a mesh partitioned over the ranks (peer-memory halo exchange, device-side flags, captured
+    step) against the same rollout un-partitioned on one GPU, owned rows compared BIT FOR BIT on every rank.  Small mesh
+    by default (every rank runs the un-partitioned rollout itself); with `full_graph` (cfg4) rank 0 runs the whole mesh
+    and broadcasts its predictions."""
+    import torch.distributed as dist
+    from mswe_gnn_b200.parallel import PartitionedRollout
+    from mswe_gnn_b200.training.train import rollout_test
+    from mswe_gnn_b200.utils.synthetic import make_tri_mesh
+    if full_graph is None:
+        nx, ny = 160, 96
+        g = make_tri_mesh(nx, ny, S, rollout_steps=steps, seed=3, with_y=False)
+        g.y = torch.empty(0, 2, steps)
+        name = f"tri({nx},{ny})"
+    else:
+        g, name = full_graph, "the benchmark mesh itself"
+    pr = PartitionedRollout(model, g, steps, dev, transport="peer")
+    preds = pr.run()
+    mine, gids = pr.owned_predictions()
+    mine = mine.clone()
+    torch.cuda.synchronize()
+    pr.close()
+    if full_graph is None:
+        ref = rollout_test(model, g.to(dev)).permute(2, 0, 1).contiguous()                  # [T, N, 2]
+    else:
+        n = int(g.x.shape[0])
+        ref = torch.empty(steps, n, 2, device=dev)
+        if rank == 0:
+            gg = g.to(dev)
+            gg.y = torch.empty(0, 2, steps)
+            ref.copy_(rollout_test(model, gg).permute(2, 0, 1))
+            del gg
+        dist.broadcast(ref, 0)
+    same = torch.equal(mine, ref[:, torch.from_numpy(gids).to(dev)])
+    flag = torch.tensor([1 if same else 0], device=dev)
+    dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+    del ref
+    torch.cuda.empty_cache()
+    return {"peer_bit_exact": bool(flag.item()), "mesh": name, "nodes": int(g.x.shape[0]), "steps": steps, "ranks": world,
+            "what": "owned rows of every rank == single-GPU rollout, torch.equal"}
 
 
 def run_ours(args):
@@ -209,10 +252,16 @@ def run_ours(args):
             dist.barrier()
         torch.cuda.synchronize()
 
+    parity = None
     if partitioned:
-        # ONE mesh cut over the ranks (blocks of coarsest cells, halo exchange per hop over NCCL)
+        # ONE mesh cut over the ranks (blocks of coarsest cells); halo rows stored straight into the neighbours' arrays over
+        # NVLink (parallel.PeerHalo), the step captured in a CUDA graph
+        parity = partition_parity_check(model, dev, world, rank)
+        if args.check_full:
+            host.y = torch.empty(0, 2, 2)
+            parity["full_mesh"] = partition_parity_check(model, dev, world, rank, full_graph=host, steps=2)
         part = partition_graph(host, world, rank)
-        runner = PartitionedRollout(model, host, K + W, dev, transport="nccl", part=part)
+        runner = PartitionedRollout(model, host, K + W, dev, transport=args.transport, part=part)
         N_nodes = sum(part.n_owned)
         N_total = N_global
     else:
@@ -261,10 +310,11 @@ def run_ours(args):
             import copy
             pp = copy.copy(part_p)
             pp.graph = host_p                           # pinned local graph: PartitionedRollout uploads it
-            r = PartitionedRollout(model, None, K, dev, transport="nccl", part=pp)
+            r = PartitionedRollout(model, None, K, dev, transport=args.transport, part=pp)
             preds = r.run()
             out_host.copy_(preds[:, owned_rows], non_blocking=True)
             torch.cuda.synchronize()
+            r.close()
     else:
         def e2e_call():
             ta = time.perf_counter()
@@ -294,9 +344,9 @@ def run_ours(args):
     e2e_value = N_total * K / e2e_s
     halo_info = None
     if partitioned:
-        hb = torch.tensor([float(runner.halo.bytes_sent) / max(runner.halo.n_exchanges, 1), float(sum(part.n_halo))], device=dev)
+        hb = torch.tensor([float(runner.halo_bytes_per_step) / max(runner.exchanges_per_step, 1), float(sum(part.n_halo))], device=dev)
         dist.all_reduce(hb, op=dist.ReduceOp.MAX)
-        halo_info = {"exchanges_per_step": runner.halo.n_exchanges // (K + W), "max_bytes_per_exchange": int(hb[0].item()),
+        halo_info = {"exchanges_per_step": int(runner.exchanges_per_step), "max_bytes_per_exchange": int(hb[0].item()),
                      "max_halo_nodes_per_rank": int(hb[1].item())}
 
     # ---- per-kernel timing of one eager (non-graph) step with CUDA events (roofline of the dominant kernel);
@@ -307,6 +357,8 @@ def run_ours(args):
     kern = profile_kernels(runner, alg) if (partitioned or rank == 0) else None
     if rank != 0:
         if world > 1:
+            if partitioned:
+                runner.close()
             dist.destroy_process_group()
         return
     pk = peaks()
@@ -335,9 +387,10 @@ def run_ours(args):
 
     if partitioned:
         multi = (f"ONE mesh tri({nx},{ny}) = {N_global} nodes cut over {world} GPUs by blocks of coarsest cells "
-                 f"(every level sharded, {halo_info['exchanges_per_step']} NCCL halo exchanges per step, "
-                 f"<= {halo_info['max_bytes_per_exchange']} B each); " +
-                 ("per-GPU work fixed at cfg3's size (weak scaling)" if wl == "cfg3" else "fixed total mesh (strong scaling)"))
+                 f"(every level sharded, {halo_info['exchanges_per_step']} halo exchanges per step, "
+                 f"<= {halo_info['max_bytes_per_exchange']} B each, transport {args.transport}: " +
+                 ("boundary rows stored into the neighbours' IPC-mapped arrays by one kernel per exchange, device-side flags" if args.transport == "peer" else "NCCL send/recv") +
+                 "); " + ("per-GPU share fixed at 2 x cfg3's nodes (weak scaling; N=1 is cfg3 itself)" if wl == "cfg3" else "fixed total mesh (strong scaling)"))
     elif world > 1:
         multi = "independent simulations per rank (replicas, no collective)"
     else:
@@ -349,7 +402,7 @@ def run_ours(args):
             "config": {"workload": f"{wl}: default config.yaml mSWE-GNN (K=4,F=64,mlp_layers=3,S=4) autoregressive rollout on "
                                    f"tri({nx},{ny}) = {N_global} nodes ({N_nodes} owned per GPU); random-init weights seed 666; 30% wet nodes",
                        "l2": f"working set {alg['total'] / 1e9:.1f} GB per step per GPU >> 126 MB L2 (inputs larger than L2, no flush needed)",
-                       "multi_gpu": multi, "cuda_graph": not partitioned},
+                       "multi_gpu": multi, "cuda_graph": bool(getattr(runner, "use_cuda_graph", False))},
             "clocks": clocks,
             "e2e": {"value": e2e_value, "unit": "node-steps/s", "h2d_bytes_per_step": h2d // K, "d2h_bytes_per_step": n_out * 8,
                     "what": ("PartitionedRollout(model, pinned local graph): upload, plan build, K steps with halo exchange, owned "
@@ -361,9 +414,12 @@ def run_ours(args):
                                         "frac_of_peak": step_gbs / pk["hbm"], "peak_source": pk["hbm_src"]},
             "kernels": sorted(kern.values(), key=lambda r: -r["ms_per_step"]),
             "halo": halo_info,
+            "parity_check": parity,
             "cpu_baseline": cpu}
     print(json.dumps(line), flush=True)
     if world > 1:
+        if partitioned:
+            runner.close()
         dist.destroy_process_group()
 
 
@@ -593,7 +649,7 @@ def profile_kernels(runner, alg):
     orig = {}
     names = ["row_mlp_tc", "node_encode_fwd", "edge_gate_fwd", "edge_gate_tc_fwd", "edge_gate_tc16_fwd", "propagate_hop_tc16_fwd", "edge_gate_tc_dec_fwd", "gate_partials_tc", "edge_gate_tc_stat_fwd",
              "gate_static_partials_tc", "node_linear_fwd", "propagate_hop_fwd", "propagate_hop_tc_fwd", "pool_mean_fwd",
-             "decode_head_fwd", "edge_encode_fwd", "apply_bc", "step_advance"]
+             "decode_head_fwd", "edge_encode_fwd", "apply_bc", "step_advance", "halo_exchange", "pack_rows"]
 
     def wrap(name):
         fn = getattr(lib, name)
@@ -661,6 +717,10 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default=None, choices=[None, *WORKLOADS, *TRAIN_WORKLOADS])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--transport", default="peer", choices=["peer", "nccl"],
+                    help="N>1 halo exchange: peer-memory stores + device flags in a captured step (default) or NCCL send/recv (eager)")
+    ap.add_argument("--check-full", action="store_true",
+                    help="N>1: also compare the partitioned rollout of the benchmark mesh itself with rank 0's single-GPU rollout")
     ap.add_argument("--multi", default="partitioned", choices=["partitioned", "replicas"],
                     help="N>1: one mesh partitioned over the GPUs with halo exchange (default) or independent replicas")
     args = ap.parse_args()

@@ -481,6 +481,26 @@ int swe_head_bwd(const float* dpred, const float* pre3, int32_t ldp, int32_t act
                  const float* res_w, float eps, float* dh3, float* dx0, float* res_part, int32_t* grid_out,
                  void* stream);
 
+/* ---------------------------------------------------------------------------------------------
+ * Multi-GPU: halo exchange of a partitioned mesh over peer memory (one process per GPU; no reference counterpart,
+ * contract = SURVEY.md §8(e): owned rows bit-identical to the single-GPU result).
+ * swe_ipc_*: a cudaMalloc'ed, zero-filled arena with its 64-byte CUDA IPC handle; peers map it with swe_ipc_open.
+ * swe_halo_exchange: rows send_idx[q][0..n_send[q]) of `arr` ([*, width] fp32, width % 4 == 0) are stored to
+ * remote_rows[q] (peer-mapped first halo row of this rank in neighbour q's copy of the array), then *seq + 1 is stored
+ * (release, system scope) to remote_flags[q]; do_wait: the launch then waits until local_flags[q] >= *seq + 1 for every
+ * neighbour and sets *seq += 1.  All pointer arrays are HOST arrays of n_peers (<= 16) DEVICE pointers; `seq` and `done`
+ * are device words owned by the caller (zero-initialised).  One kernel, capturable in a CUDA graph.  do_push / do_wait
+ * select the two halves (tests drive them separately with a host barrier in between).
+ * ------------------------------------------------------------------------------------------- */
+int swe_ipc_alloc(size_t bytes, void** ptr_out, unsigned char* handle64);
+int swe_ipc_open(const unsigned char* handle64, void** ptr_out);
+int swe_ipc_close(void* ptr);
+int swe_ipc_free(void* ptr);
+int swe_halo_exchange(const float* arr, int32_t width, int32_t n_peers, const int32_t* const* send_idx,
+                      const int64_t* n_send, float* const* remote_rows, uint32_t* const* remote_flags,
+                      const uint32_t* const* local_flags, uint32_t* seq, uint32_t* done, int32_t do_push,
+                      int32_t do_wait, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -355,11 +355,12 @@ class RowMlpTC:
         lib.row_mlp_tc(d)
 
     def decode(self, h, act_in, slope_in, x0, perm, n_nodes, previous_t, res_mode, res_w, eps, pred, step_ptr, pred_stride,
-               x_next):
+               x_next, row_lo: int = 0):
+        """Rows [row_lo, row_lo + n_nodes) (a rank of a partitioned mesh decodes its owned rows only, scale by scale)."""
         d = lib.SweRowMlp()
         d.x_rows, d.act_in = lib.ptr(h), act_in
         d.slope_in = None if slope_in is None else slope_in.data_ptr()
-        d.row_lo, d.n_rows = 0, n_nodes
+        d.row_lo, d.n_rows = row_lo, n_nodes
         self._fill_tc(d, [0, 1])
         lin, act = self.linears[2], self.acts[2]
         d.head = 1
@@ -543,8 +544,12 @@ class SweGnnLauncher:
                 else:
                     lib.node_linear_fwd(x, lo, n, W[0], tmp_a, FP)
             if xd_dst is not None:
-                w0(xd_dst, es.dst_lo, es.n_dst)
-                if es.src_lo != es.dst_lo:
+                if es.src_lo == es.dst_lo:
+                    # same node set: one launch over the sources (on a rank of a partitioned mesh they extend beyond the
+                    # owned destination rows by the halo rows the hops read)
+                    w0(xd_dst, es.dst_lo, max(es.n_dst, es.src_hi - es.src_lo))
+                else:
+                    w0(xd_dst, es.dst_lo, es.n_dst)
                     w0(xd_src, es.src_lo, es.src_hi - es.src_lo)
                 o_src, o_dst = tmp_a, tmp_a
             else:

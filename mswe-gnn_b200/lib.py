@@ -101,6 +101,12 @@ SIGNATURES = {
     "swe_apply_bc": (C.c_int, [_p, _i32, _i32, _i32, _i32, _p, _i32, _p, _i32, _p, _p]),
     "swe_step_advance": (C.c_int, [_p, _p]),
     "swe_pack_rows": (C.c_int, [_p, _p, _i64, _i32, _p, _p]),
+    "swe_ipc_alloc": (C.c_int, [_sz, C.POINTER(C.c_void_p), C.c_char_p]),
+    "swe_ipc_open": (C.c_int, [C.c_char_p, C.POINTER(C.c_void_p)]),
+    "swe_ipc_close": (C.c_int, [_p]),
+    "swe_ipc_free": (C.c_int, [_p]),
+    "swe_halo_exchange": (C.c_int, [_p, _i32, _i32, C.POINTER(C.c_void_p), C.POINTER(C.c_int64), C.POINTER(C.c_void_p),
+                                    C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), _p, _p, _i32, _i32, _p]),
     # training path
     "swe_mlp_layer_fwd": (C.c_int, [_rows, _i64, _p, _p, _i32, _p, _p]),
     "swe_mlp_layer_bwd_dx": (C.c_int, [_p, _p, _i32, _p, _i64, _i32, _p, _i32, _i32, _i32, _i32, _p, _i32, _i32, _p,
@@ -421,6 +427,38 @@ def apply_bc(x, n_static_raw, previous_t, type_bc, node_bc, bc, step_ptr):
 def pack_rows(src, idx, n_rows, dst):
     _check(load().swe_pack_rows(ptr(src), ptr(idx, torch.int32), n_rows, src.shape[1], ptr(dst), _stream()),
            "swe_pack_rows")
+
+
+def ipc_alloc(nbytes: int):
+    """(device pointer, 64-byte IPC handle) of a zero-filled cudaMalloc'ed arena."""
+    out = C.c_void_p()
+    handle = C.create_string_buffer(64)
+    _check(load().swe_ipc_alloc(int(nbytes), C.byref(out), handle), "swe_ipc_alloc")
+    return int(out.value), handle.raw
+
+
+def ipc_open(handle: bytes) -> int:
+    out = C.c_void_p()
+    _check(load().swe_ipc_open(handle, C.byref(out)), "swe_ipc_open")
+    return int(out.value)
+
+
+def ipc_close(ptr_: int):
+    _check(load().swe_ipc_close(ptr_), "swe_ipc_close")
+
+
+def ipc_free(ptr_: int):
+    _check(load().swe_ipc_free(ptr_), "swe_ipc_free")
+
+
+def halo_exchange(arr, send_idx_ptrs, n_send, remote_rows, remote_flags, local_flags, seq_ptr, done_ptr, do_push=True,
+                  do_wait=True):
+    """All *_ptrs / remote_* / *_flags arguments: lists of raw device addresses (ints), one per neighbour."""
+    n = len(n_send)
+    vp = lambda xs: (C.c_void_p * max(n, 1))(*[x if x else None for x in xs])
+    _check(load().swe_halo_exchange(ptr(arr), int(arr.shape[1]), n, vp(send_idx_ptrs), (C.c_int64 * max(n, 1))(*n_send),
+                                    vp(remote_rows), vp(remote_flags), vp(local_flags), seq_ptr, done_ptr, int(do_push),
+                                    int(do_wait), _stream()), "swe_halo_exchange")
 
 
 def step_advance(step_ptr):

@@ -182,7 +182,11 @@ class _EncodeDecodeMixin:
         if ws is None:
             dev = plan.edges[0].rowptr.device
             FP, N = self._FP, plan.n_nodes
-            ws = {n: torch.empty(N, FP, dtype=torch.float32, device=dev) for n in names}
+            # node arrays of a partitioned mesh live in the rank's IPC arena (parallel.PeerHalo): neighbours store their
+            # boundary rows straight into the halo rows
+            alloc = getattr(self, "_ws_alloc", None)
+            ws = {n: (alloc(n, N, FP) if alloc is not None else torch.empty(N, FP, dtype=torch.float32, device=dev))
+                  for n in names}
             ws["s"] = torch.empty(plan.max_edges, FP, dtype=torch.float32, device=dev)
             # per-node partial tables of the decomposed edge-MLP layer 0 (tcgen05 gate, F = 64)
             ws["ptab"] = (torch.empty(N, 2 * FP, dtype=torch.float32, device=dev),
@@ -223,13 +227,21 @@ class _EncodeDecodeMixin:
         self._edge_cache_ref = ea            # identity, not just address: a freed tensor's address can be reused
         return ws["a"]
 
-    def _decode(self, h, act_name, act_module, x, plan, pred, step_ptr=None, pred_stride=0, x_next=None):
+    def _decode(self, h, act_name, act_module, x, plan, pred, step_ptr=None, pred_stride=0, x_next=None, owned_only=False):
         slope = act_module.weight if isinstance(act_module, nn.PReLU) else None
         res_w = self.residual_weights.detach().contiguous() if self._residual_mode() in (1, 2) else None
         if self._tc_decoder is not None and rowmlp_backend() == "tc" and x.shape[1] <= 16:
+            if owned_only and plan.scale_owned is not None:
+                # the halo rows of x / pred belong to their owners (who store them into our copy): decode owned rows only
+                for lo, n in zip(plan.scale_lo, plan.scale_owned):
+                    self._tc_decoder.decode(h, ACT_CODES[act_name], slope, x, plan.perm, n, self.previous_t,
+                                            self._residual_mode(), res_w, 1e-4, pred, step_ptr, pred_stride, x_next, row_lo=lo)
+                return
             self._tc_decoder.decode(h, ACT_CODES[act_name], slope, x, plan.perm, plan.n_nodes, self.previous_t,
                                     self._residual_mode(), res_w, 1e-4, pred, step_ptr, pred_stride, x_next)
             return
+        if owned_only:
+            raise NotImplementedError("the peer-memory halo transport needs the tcgen05 decoder (F = 64, 3-layer decoder)")
         lib.decode_head_fwd(h, ACT_CODES[act_name], slope, self._pk_decoder.struct(), x, plan.perm, plan.n_nodes,
                             self.previous_t, self._residual_mode(), res_w, 1e-4, pred, step_ptr, pred_stride,
                             x_next, self._FP)
@@ -253,6 +265,8 @@ class GNN(BaseFloodModel, _EncodeDecodeMixin):
     mlp_layers / mlp_activation / gnn_activation / with_WL / normalize / with_filter_matrix /
     with_gradient / base_model_kwargs: as in the reference
     '''
+
+    _WS_NAMES = ["xs", "h0", "h1", "ta", "tb"]          # node arrays of one forward (engine / parallel.PeerHalo)
 
     def __init__(self, num_node_features, num_edge_features, hid_features=32, K=2, n_GNN_layers=2, type_GNN="SWEGNN",
                  mlp_layers=1, mlp_activation='prelu', gnn_activation='prelu', dropout=0,
@@ -309,7 +323,7 @@ class GNN(BaseFloodModel, _EncodeDecodeMixin):
     def _launch(self, plan, graph, x, pred, step_ptr=None, pred_stride=0, x_next=None, halo=None):
         FP = self._FP
         n_layers = len(self.gnn_processor)
-        ws = self._workspace(plan, ["xs", "h0", "h1", "ta", "tb"])
+        ws = self._workspace(plan, self._WS_NAMES)
         a = self._encoded_edges(plan, graph, ws)
         N = plan.n_nodes
         self._encode_nodes(x, plan, N, ws["xs"], ws["h0"])
@@ -324,7 +338,8 @@ class GNN(BaseFloodModel, _EncodeDecodeMixin):
                                 act_code=ACT_CODES[self._gnn_activation_name], act_slope=slope, halo=halo, scale=0,
                                 ptab=ws["ptab"])
             cur, nxt = nxt, cur
-        self._decode(cur, None, None, x, plan, pred, step_ptr, pred_stride, x_next)
+        self._decode(cur, None, None, x, plan, pred, step_ptr, pred_stride, x_next,
+                     owned_only=bool(getattr(halo, "owned_only", False)))
 
 
 class MSGNN(BaseFloodModel, _EncodeDecodeMixin):
@@ -338,6 +353,8 @@ class MSGNN(BaseFloodModel, _EncodeDecodeMixin):
     skip_connections, with_WL, normalize, with_filter_matrix, edge_mlp, with_gradient,
     base_model_kwargs: as in the reference
     '''
+
+    _WS_NAMES = ["xs", "cur", "down", "up", "ta", "tb"]  # node arrays of one forward (engine / parallel.PeerHalo)
 
     def __init__(self, num_node_features, num_edge_features, num_scales, hid_features=32, K=2,
                  mlp_layers=2, mlp_activation='prelu', gnn_activation='tanh',
@@ -413,7 +430,7 @@ class MSGNN(BaseFloodModel, _EncodeDecodeMixin):
     def _launch(self, plan, graph, x, pred, step_ptr=None, pred_stride=0, x_next=None, halo=None):
         """halo: ``parallel.HaloExchanger`` when `graph` is one rank's part of a partitioned mesh."""
         FP, S = self._FP, self.num_scales
-        ws = self._workspace(plan, ["xs", "cur", "down", "up", "ta", "tb"])
+        ws = self._workspace(plan, self._WS_NAMES)
         a = self._encoded_edges(plan, graph, ws)
         xs, cur, down, up, ta, tb, s_buf = ws["xs"], ws["cur"], ws["down"], ws["up"], ws["ta"], ws["tb"], ws["s"]
         self._encode_nodes(x, plan, plan.scale_n[0], xs, cur)
@@ -450,4 +467,5 @@ class MSGNN(BaseFloodModel, _EncodeDecodeMixin):
                 # pooling zeroed them), so the gate skips that block and the hop starts from 0
                 self.intra_scale_gnn[i].launcher().run(ue, xs, up, None, None, s_buf, True, ta, tb, cur,
                                                        addend=down if self.skip_connections else None, ptab=ws["ptab"])
-        self._decode(up, self._gnn_activation_name, self.gnn_activation, x, plan, pred, step_ptr, pred_stride, x_next)
+        self._decode(up, self._gnn_activation_name, self.gnn_activation, x, plan, pred, step_ptr, pred_stride, x_next,
+                     owned_only=bool(getattr(halo, "owned_only", False)))

@@ -203,6 +203,7 @@ def partition_graph(graph, world: int, rank: int, owner: Optional[np.ndarray] = 
     for k in ("previous_t", "temporal_res"):
         if hasattr(graph, k):
             setattr(local, k, getattr(graph, k))
+    local.n_owned = list(n_owned)            # plan.build_plan: every edge set ends in owned rows only
     owned_rows = np.concatenate([scale_lo[s] + np.arange(n_owned[s]) for s in range(S)]) if S else np.zeros(0, np.int64)
     return LocalPartition(rank, world, S, local, l2g, n_owned, n_halo, scale_lo, send, recv, inter_cross,
                           owned_rows.astype(np.int64), l2g[owned_rows.astype(np.int64)])
@@ -271,6 +272,137 @@ class HaloExchanger:
         self.n_exchanges += 1
 
 
+class _RawCuda:
+    """Zero-copy view of raw device memory for torch.as_tensor (CUDA array interface)."""
+
+    def __init__(self, ptr: int, shape, typestr: str):
+        self.__cuda_array_interface__ = {"shape": tuple(shape), "typestr": typestr, "data": (int(ptr), False), "version": 2,
+                                         "strides": None}
+
+
+class PeerHalo:
+    """Halo exchange over peer memory (NVLink / NVSwitch) — the production transport of the partitioned rollout.
+
+    Every node array that takes part in an exchange (the model's per-forward arrays and the node inputs x) lives in ONE
+    cudaMalloc'ed arena per rank, exported through CUDA IPC and mapped by every other rank.  ``exchange`` is a single
+    kernel (``swe_halo_exchange``): it stores this rank's boundary rows straight into the halo rows of its neighbours'
+    copies of the array, signals them through a sequence-numbered flag and waits for theirs.  No pack buffers, no NCCL, no
+    host synchronisation: the step is a fixed kernel sequence and is captured in a CUDA graph.
+
+    ``sync='host'`` (tests that run several ranks on ONE GPU, where kernels of different processes must not wait for one
+    another): push kernel, device synchronise + process-group barrier, then the wait kernel (which finds its flags set).
+    """
+    owned_only = True           # local kernels write owned rows only; the halo rows belong to the neighbours' stores
+
+    def __init__(self, part: LocalPartition, device, group=None, n_arrays: int = 8, width: int = 64, x_cols: int = 8,
+                 sync: str = "device"):
+        import torch.distributed as dist
+        from . import lib
+        self.lib, self.dist, self.group = lib, dist, group
+        self.part, self.device, self.sync = part, torch.device(device), sync
+        self.rank, self.world = part.rank, part.world
+        n_local = int(part.local_to_global.shape[0])
+        al = lambda b: (b + 255) // 256 * 256
+        self.size = al(n_local * x_cols * 4) + n_arrays * al(n_local * width * 4) + 4096
+        with torch.cuda.device(self.device):
+            self.base, handle = lib.ipc_alloc(self.size)
+        self.cursor = 0
+        self.offsets: Dict[str, int] = {}
+        self._names: Dict[int, str] = {}
+        self._keep: List[torch.Tensor] = []
+        self.flags = self._carve("_flags", (self.world + 8,), torch.int32)       # [q]: latest exchange of neighbour q; seq; done
+        handles = [None] * self.world
+        dist.all_gather_object(handles, handle, group=group)
+        self.peer_base = {}
+        with torch.cuda.device(self.device):
+            for q in range(self.world):
+                if q != self.rank:
+                    self.peer_base[q] = lib.ipc_open(handles[q])
+        self.send_idx = [{q: torch.from_numpy(v.astype(np.int32)).to(self.device) for q, v in d.items()} for d in part.send]
+        # symmetric neighbour sets per scale: every exchange signals and awaits the same peers on both sides
+        self.peers = [sorted(set(part.send[s]) | set(part.recv[s])) for s in range(part.num_scales)]
+        self._remote = None
+        self.n_exchanges = 0
+        self.bytes_sent = 0
+        self.closed = False
+
+    # ---- arena -------------------------------------------------------------------------------------------------
+    def _carve(self, name, shape, dtype):
+        nbytes = int(np.prod(shape)) * torch.empty(0, dtype=dtype).element_size()
+        off = (self.cursor + 255) // 256 * 256
+        if off + nbytes > self.size:
+            raise RuntimeError(f"peer arena of {self.size} bytes is full (array '{name}')")
+        self.cursor = off + nbytes
+        typestr = {torch.float32: "<f4", torch.int32: "<i4"}[dtype]
+        t = torch.as_tensor(_RawCuda(self.base + off, shape, typestr), device=self.device)
+        self.offsets[name] = off
+        self._names[t.data_ptr()] = name
+        self._keep.append(t)
+        return t
+
+    def alloc(self, name: str, rows: int, cols: int) -> torch.Tensor:
+        """A [rows, cols] fp32 array inside the arena (the model's workspace hook and the runner's x)."""
+        return self._carve(name, (rows, cols), torch.float32)
+
+    def finalize(self):
+        """After every exchanged array has been allocated: learn where the neighbours put theirs."""
+        meta = [None] * self.world
+        mine = (dict(self.offsets), [{int(q): (int(r0), int(n)) for q, (r0, n) in d.items()} for d in self.part.recv])
+        self.dist.all_gather_object(meta, mine, group=self.group)
+        self._remote = meta
+
+    # ---- exchange ----------------------------------------------------------------------------------------------
+    def exchange(self, arr: torch.Tensor, scale: int):
+        peers = self.peers[scale]
+        if not peers:
+            return
+        name = self._names.get(arr.data_ptr())
+        if name is None:
+            raise RuntimeError("PeerHalo.exchange: the array does not live in the peer arena")
+        if self._remote is None:
+            self.finalize()
+        width = int(arr.shape[1])
+        fl_off = self.offsets["_flags"]
+        idx_ptrs, n_send, rrows, rflags, lflags = [], [], [], [], []
+        for q in peers:
+            idx = self.send_idx[scale].get(q)
+            n = 0 if idx is None else int(idx.numel())
+            offs_q, recv_q = self._remote[q]
+            row0 = recv_q[scale].get(self.rank, (0, 0))[0]
+            if n and recv_q[scale].get(self.rank, (0, 0))[1] != n:
+                raise RuntimeError("halo maps of the ranks disagree")
+            idx_ptrs.append(idx.data_ptr() if n else 0)
+            n_send.append(n)
+            rrows.append(self.peer_base[q] + offs_q[name] + row0 * width * 4 if n else 0)
+            rflags.append(self.peer_base[q] + offs_q["_flags"] + 4 * self.rank)
+            lflags.append(self.base + fl_off + 4 * q)
+            self.bytes_sent += n * width * 4
+        seq_ptr = self.base + fl_off + 4 * self.world
+        done_ptr = seq_ptr + 4
+        if self.sync == "device":
+            self.lib.halo_exchange(arr, idx_ptrs, n_send, rrows, rflags, lflags, seq_ptr, done_ptr, True, True)
+        else:
+            self.lib.halo_exchange(arr, idx_ptrs, n_send, rrows, rflags, lflags, seq_ptr, done_ptr, True, False)
+            torch.cuda.synchronize(self.device)
+            self.dist.barrier(group=self.group)
+            self.lib.halo_exchange(arr, idx_ptrs, n_send, rrows, rflags, lflags, seq_ptr, done_ptr, False, True)
+        self.n_exchanges += 1
+
+    def close(self):
+        """Unmap the neighbours' arenas and free this rank's (collective: nobody may still be storing into it)."""
+        if self.closed:
+            return
+        self.closed = True
+        torch.cuda.synchronize(self.device)
+        self.dist.barrier(group=self.group)
+        with torch.cuda.device(self.device):
+            for p_ in self.peer_base.values():
+                self.lib.ipc_close(p_)
+            self.dist.barrier(group=self.group)
+            self._keep.clear()
+            self.lib.ipc_free(self.base)
+
+
 class PartitionedRollout:
     """Autoregressive rollout of one large mesh cut over the ranks of ``group``.
 
@@ -288,12 +420,29 @@ class PartitionedRollout:
         self.part = part if part is not None else partition_graph(graph_cpu, world, rank)
         self.model, self.T = model, int(n_steps)
         self.graph = self.part.graph.to(device, non_blocking=True)
-        self.halo = HaloExchanger(self.part, device, transport, group)
+        self.peer = transport in ("peer", "peer-hostsync")
+        if self.peer:
+            self.halo = PeerHalo(self.part, device, group, n_arrays=len(model._WS_NAMES) + 1, width=model._FP,
+                                 x_cols=int(self.graph.x.shape[1]), sync="device" if transport == "peer" else "host")
+        else:
+            self.halo = HaloExchanger(self.part, device, transport, group)
         model._check_input(self.graph)
         multiscale = model.type_model == "MSGNN"
         self.plan = model._plans.get(self.graph, getattr(model, "num_scales", 1), multiscale)
         N = self.plan.n_nodes
-        self.x = self.graph.x.detach().clone().contiguous()
+        if self.peer:
+            # node arrays of the forward and the node inputs live in the IPC arena; the neighbours learn their offsets
+            model._ws_alloc = self.halo.alloc
+            try:
+                model._ws.pop((self.plan.key, self.plan.n_nodes), None)
+                model._workspace(self.plan, model._WS_NAMES)
+            finally:
+                model._ws_alloc = None
+            self.x = self.halo.alloc("x", N, int(self.graph.x.shape[1]))
+            self.x.copy_(self.graph.x)
+            self.halo.finalize()
+        else:
+            self.x = self.graph.x.detach().clone().contiguous()
         self.preds = torch.empty(self.T, N, NUM_WATER_VARS, dtype=torch.float32, device=device)
         self.step = torch.zeros(1, dtype=torch.int32, device=device)
         self.type_BC = int(self.graph.type_BC)
@@ -304,10 +453,24 @@ class PartitionedRollout:
         self.launches_per_step = 0
         self.done = 0                             # host mirror of the device step counter (bounds check in run())
         self._token = new_static_token()
+        # the peer transport's step is a fixed kernel sequence without host synchronisation: captured and replayed
+        self.use_cuda_graph = transport == "peer" and self.T > 2
+        self._graph = None
+
+    def close(self):
+        """Release the peer arena (collective).  The model's cached workspace of this plan pointed into it."""
+        if not self.peer:
+            return
+        if not self.halo.closed:
+            self._graph = None
+            self.model._ws.pop((self.plan.key, self.plan.n_nodes), None)
+            self.model._plans.clear()
+            self.halo.close()
 
     def _one_step(self):
         lib, m = self.lib, self.model
         c0 = lib.launch_count
+        x0, b0 = self.halo.n_exchanges, self.halo.bytes_sent
         if self.node_BC.numel():
             lib.apply_bc(self.x, self.n_static_raw, m.previous_t, self.type_BC, self.node_BC, self.bc, self.step)
         with static_inputs(self._token, xs_static=not m.with_WL):         # static columns, mesh part and weights are constant over the rollout
@@ -318,18 +481,39 @@ class PartitionedRollout:
         for s in range(self.part.num_scales):
             self.halo.exchange(self.x, s)
         self.launches_per_step = lib.launch_count - c0
+        self.exchanges_per_step = self.halo.n_exchanges - x0
+        self.halo_bytes_per_step = self.halo.bytes_sent - b0
 
     def reset(self):
+        """Collective for the peer transport: nobody may still be storing x rows of the previous rollout."""
+        if self.peer:
+            torch.cuda.synchronize()
+            self.halo.dist.barrier(group=self.halo.group)
         self.x.copy_(self.graph.x)
         self.step.zero_()
         self.done = 0
+        if self.peer:
+            torch.cuda.synchronize()
+            self.halo.dist.barrier(group=self.halo.group)
 
     def run(self, n_steps: Optional[int] = None):
         n = self.T - self.done if n_steps is None else int(n_steps)
         if n < 0 or self.done + n > self.T:
             raise ValueError(f"rollout of {self.T} steps: {self.done} done, {n} more requested (call reset() first)")
-        for _ in range(n):
-            self._one_step()
+        done = 0
+        if self.use_cuda_graph and self._graph is None and n > 1:
+            self._one_step()                     # eager: lazy packing / allocation happen here
+            done = 1
+            g = torch.cuda.CUDAGraph()
+            torch.cuda.synchronize()
+            with torch.cuda.graph(g):
+                self._one_step()
+            self._graph = g
+        for _ in range(done, n):
+            if self._graph is not None:
+                self._graph.replay()
+            else:
+                self._one_step()
         self.done += n
         return self.preds
 

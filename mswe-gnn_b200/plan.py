@@ -56,6 +56,9 @@ class GraphPlan:
     unpool: List[EdgeSet] = field(default_factory=list)    # level j: keyed by fine (scale j), src = coarse
     edge_slices: List[Tuple[int, int]] = field(default_factory=list)   # [lo, hi) of each scale in edge_index
     key: tuple = ()
+    # partitioned meshes (parallel.partition_graph): per scale the first scale_owned[s] rows are owned by this rank, the
+    # rest are halo copies; every edge set then ends in owned rows only (None: all rows are owned)
+    scale_owned: Optional[List[int]] = None
 
     @property
     def n_edges_total(self) -> int:
@@ -93,8 +96,11 @@ def build_plan(graph, num_scales: int, multiscale: bool) -> GraphPlan:
     key = _topology_key(graph, multiscale)
 
     if not multiscale:
-        es = _build_edge_set(ei[0], ei[1], None, 0, N, 0, N)
-        return GraphPlan(N, 1, [0], [N], None, None, [es], edge_slices=[(0, int(ei.shape[1]))], key=key)
+        owned = getattr(graph, "n_owned", None)
+        n_dst = N if owned is None else int(owned[0])
+        es = _build_edge_set(ei[0], ei[1], None, 0, n_dst, 0, N)
+        return GraphPlan(N, 1, [0], [N], None, None, [es], edge_slices=[(0, int(ei.shape[1]))], key=key,
+                         scale_owned=None if owned is None else [n_dst])
 
     S = num_scales
     node_ptr = graph.node_ptr.detach().to("cpu", torch.int64)
@@ -131,26 +137,41 @@ def build_plan(graph, num_scales: int, multiscale: bool) -> GraphPlan:
         perm = perm64.to(torch.int32).to(dev)
         inv = inv64.to(torch.int32).to(dev)
 
+    # A rank's part of a partitioned mesh: destinations are the OWNED rows only (the halo rows behind them are written by
+    # their owners' exchanges, never by a local kernel); inter-scale edges whose destination is a halo row are dropped
+    owned = getattr(graph, "n_owned", None)
+    if owned is not None:
+        owned = [int(v) for v in owned]
+        if G != 1 or len(owned) != S or any(o < 0 or o > n for o, n in zip(owned, scale_n)):
+            raise ValueError("n_owned must give, for an un-batched graph, the number of owned rows of every scale")
+    dst_n = owned if owned is not None else scale_n
+
     edges, pool, unpool, slices = [], [], [], []
     for s in range(S):
         lo, hi = edge_ptr[s], edge_ptr[s + 1]
         slices.append((lo, hi))
         try:
-            edges.append(_build_edge_set(ei[0, lo:hi], ei[1, lo:hi], inv, scale_lo[s], scale_n[s],
+            edges.append(_build_edge_set(ei[0, lo:hi], ei[1, lo:hi], inv, scale_lo[s], dst_n[s],
                                          scale_lo[s], scale_lo[s] + scale_n[s]))
         except ValueError as e:
-            raise ValueError(f"scale {s}: edges must connect nodes of the same scale: {e}") from e
+            raise ValueError(f"scale {s}: edges must connect nodes of the same scale"
+                             f"{' and end in owned rows' if owned is not None else ''}: {e}") from e
     for j in range(S - 1):
         lo, hi = intra_ptr[j], intra_ptr[j + 1]
         coarse, fine = ie[0, lo:hi], ie[1, lo:hi]
         f_lo, f_n, c_lo, c_n = scale_lo[j], scale_n[j], scale_lo[j + 1], scale_n[j + 1]
+        pc, pf, uc, uf = coarse, fine, coarse, fine
+        if owned is not None:
+            keep_p = coarse < c_lo + dst_n[j + 1]                    # pooling: destination = coarse row
+            keep_u = fine < f_lo + dst_n[j]                          # un-pooling: destination = fine row
+            pc, pf, uc, uf = coarse[keep_p], fine[keep_p], coarse[keep_u], fine[keep_u]
         try:
-            pool.append(_build_edge_set(fine, coarse, inv, c_lo, c_n, f_lo, f_lo + f_n))
-            unpool.append(_build_edge_set(coarse, fine, inv, f_lo, f_n, c_lo, c_lo + c_n))
+            pool.append(_build_edge_set(pf, pc, inv, c_lo, dst_n[j + 1], f_lo, f_lo + f_n))
+            unpool.append(_build_edge_set(uc, uf, inv, f_lo, dst_n[j], c_lo, c_lo + c_n))
         except ValueError as e:
             raise ValueError(f"inter-scale level {j}: row 0 must hold scale-{j + 1} (coarse) and row 1 "
                              f"scale-{j} (fine) nodes: {e}") from e
-    return GraphPlan(N, S, scale_lo, scale_n, perm, inv, edges, pool, unpool, slices, key)
+    return GraphPlan(N, S, scale_lo, scale_n, perm, inv, edges, pool, unpool, slices, key, scale_owned=owned)
 
 
 class PlanCache:

@@ -21,7 +21,7 @@ def _free_port():
     return port
 
 
-def _worker(rank, world, port, steps, mesh_kw, out):
+def _worker(rank, world, port, steps, mesh_kw, out, transport="staged"):
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
     dist.init_process_group("gloo", rank=rank, world_size=world)
     try:
@@ -34,10 +34,11 @@ def _worker(rank, world, port, steps, mesh_kw, out):
         torch.cuda.set_device(dev)
         model = MSGNN(**CTOR).to(dev)
         g = make_tri_mesh(24, 16, 3, rollout_steps=steps, seed=5, **mesh_kw)
-        pr = PartitionedRollout(model, g, steps, dev, transport="staged")
+        pr = PartitionedRollout(model, g, steps, dev, transport=transport)
         pr.run()
         preds, gids = pr.owned_predictions()
         out[rank] = (preds.cpu().numpy(), gids, pr.halo.n_exchanges)
+        pr.close()
         if rank == 0:
             with torch.no_grad():
                 ref = rollout_test(model, g.to(dev), use_cuda_graph=False)      # [N, 2, T]
@@ -46,12 +47,17 @@ def _worker(rank, world, port, steps, mesh_kw, out):
         dist.destroy_process_group()
 
 
+@pytest.mark.parametrize("transport", ["staged", "peer-hostsync"])
 @pytest.mark.parametrize("world,mesh_kw", [(2, dict()), (3, dict()), (2, dict(extra_parent_every=4, orphan_every=7))])
-def test_partitioned_rollout_equals_single_gpu_bit_exact(world, mesh_kw):
+def test_partitioned_rollout_equals_single_gpu_bit_exact(world, mesh_kw, transport):
+    """'staged': the halo rows travel through pinned host buffers (gloo); 'peer-hostsync': the production transport —
+    boundary rows stored straight into the neighbours' IPC-mapped arrays by swe_halo_exchange — with the cross-rank
+    wait done on the host, because kernels of several processes sharing ONE GPU must not wait for one another (the
+    device-side flag wait is exercised on real multi-GPU boxes by bench.py's parity check)."""
     steps = 3
     with mp.Manager() as m:
         out = m.dict()
-        mp.spawn(_worker, args=(world, _free_port(), steps, mesh_kw, out), nprocs=world, join=True)
+        mp.spawn(_worker, args=(world, _free_port(), steps, mesh_kw, out, transport), nprocs=world, join=True)
         ref = out["ref"]
         seen = np.zeros(ref.shape[1], dtype=int)
         for r in range(world):
