@@ -494,17 +494,21 @@ def run_train(args):
         v = getattr(batch_host, k)
         if torch.is_tensor(v):
             setattr(batch_host, k, v.pin_memory())
+    from mswe_gnn_b200.training.optim import FlatAdamW
+    from mswe_gnn_b200.training.train import TrainStepRunner
     batch = batch_host.to(dev)
-    opt = torch.optim.AdamW(model.parameters(), lr=3e-3, weight_decay=0.0, fused=True)   # config.yaml lr_info (one fused update kernel)
+    # config.yaml lr_info; gradient_clip_val = 1 (main.py:109); loss, clip and AdamW are device kernels on flat buffers
+    opt = FlatAdamW(model, lr=3e-3, weight_decay=0.0, max_norm=1.0)
     n_nodes = batch.x.shape[0]
     K, W = args.steps, max(args.warmup, 3)
+    # one GPU: the whole step (forward, loss, backward, clip, AdamW) is ONE captured CUDA graph; data parallel: eager, with
+    # the all-reduce of the flat gradient between backward and update
+    runner = TrainStepRunner(model, batch, opt, rollout_steps=R, use_cuda_graph=(world == 1 and not args.no_graph))
 
     def step(b):
-        opt.zero_grad(set_to_none=True)
-        loss = training_step(model, b, R, only_where_water=True, velocity_scaler=7.0)
-        torch.nn.utils.clip_grad_norm_(model.parameters(), 1.0)                   # main.py:109 gradient_clip_val=1
-        opt.step()
-        return loss
+        if world == 1:
+            return runner.step(b.x, b.y, b.BC) if b is not batch else runner.step()
+        return training_step(model, b, R, only_where_water=True, velocity_scaler=7.0, optimizer=opt)
 
     def barrier():
         if world > 1:
@@ -517,14 +521,13 @@ def run_train(args):
     if rank == 0:
         sampler.start()
     barrier()
-    l0 = lib.launch_count
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     ev0.record()
     for _ in range(K):
         step(batch)
     ev1.record()
     barrier()
-    launches = lib.launch_count - l0
+    launches = runner.launches_per_step * K
     ms = ev0.elapsed_time(ev1)
     clocks = sampler.stop() if rank == 0 else None
     # e2e: the batch comes from pinned host memory every step, the loss goes back to the host
@@ -533,7 +536,8 @@ def run_train(args):
     barrier()
     t0 = time.perf_counter()
     for _ in range(K):
-        loss_host = float(step(batch_host.to(dev, non_blocking=True)))
+        loss_host = float(step(batch_host.to(dev, non_blocking=True)) if world > 1 else
+                          runner.step(batch_host.x, batch_host.y, batch_host.BC))
     barrier()
     e2e_s = time.perf_counter() - t0
     if world > 1:
@@ -541,7 +545,7 @@ def run_train(args):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         ms, e2e_s = float(t[0]), float(t[1])
     value = n_nodes * R * world * K / (ms * 1e-3)
-    kern = profile_train_kernels(lambda: step(batch))
+    kern = profile_train_kernels(lambda: training_step(model, batch, R, only_where_water=True, velocity_scaler=7.0, optimizer=opt))
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -556,12 +560,13 @@ def run_train(args):
             "n_gpus": world, "steps": K, "warmup": W, "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": f"{wl}: {kind} (config.yaml hyper-parameters: F=64, K=4, mlp_layers=3) training step, {G} x tri({nx},{ny}) "
-                                   f"graphs per GPU = {n_nodes} nodes, {R} rollout step(s), loss RMSE on wet cells, grad-clip 1, AdamW",
+                                   f"graphs per GPU = {n_nodes} nodes, {R} rollout step(s), loss RMSE on wet cells, grad-clip 1, AdamW "
+                                   f"(device kernels on flat buffers); " + ("whole step = one captured CUDA graph" if runner._graph is not None else "eager step"),
                        "l2": "saved activations >> 126 MB L2 (inputs larger than L2, no flush needed)",
                        "multi_gpu": "data parallel over simulations, one all-reduce of the flat fp32 gradient per step" if world > 1 else "single GPU"},
             "clocks": clocks,
             "e2e": {"value": n_nodes * R * world * K / e2e_s, "unit": "node-steps/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4,
-                    "what": "training_step(model, batch.to(device)) from pinned host memory every step, loss.item() back"},
+                    "what": "step(x, y, BC of the batch from pinned host memory -> captured buffers), loss.item() back, every step"},
             "gpu_launches": launches,
             "roofline": {"bound": "tensor", "kernel": dom["name"], "achieved": dom["tflops"], "peak": pk["bf16"], "unit": "TFLOP/s",
                          "frac": dom["tflops"] / pk["bf16"], "traffic": _traffic_of(dom["name"]),
@@ -717,6 +722,8 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default=None, choices=[None, *WORKLOADS, *TRAIN_WORKLOADS])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-graph", action="store_true", help="training workloads: eager step instead of the captured graph")
+    ap.add_argument("--no-training-extra", action="store_true", help="default workload: skip the secondary training measurement")
     ap.add_argument("--transport", default="peer", choices=["peer", "nccl"],
                     help="N>1 halo exchange: peer-memory stores + device flags in a captured step (default) or NCCL send/recv (eager)")
     ap.add_argument("--check-full", action="store_true",

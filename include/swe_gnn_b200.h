@@ -482,6 +482,45 @@ int swe_head_bwd(const float* dpred, const float* pre3, int32_t ldp, int32_t act
                  void* stream);
 
 /* ---------------------------------------------------------------------------------------------
+ * Rest of the training step on the device: loss with its gradient, gradient clipping and AdamW, so that
+ * forward + backward + update is a fixed kernel sequence (capturable in a CUDA graph).
+ * swe_loss_fwd_bwd: /root/reference/training/loss.py:76-118 with conservation = 0: err_v = RMSE (mae = 0) or MAE (mae = 1) of
+ *   pred - real over the rows with rows[i] != 0 (NULL: all) and, with only_where_water, a non-zero difference
+ *   (mask_on_water, loss.py:30-36); *loss (+)= scale (w0 err_0 + w1 err_1) / (w0 + w1); dpred [n, 2] = d loss / d pred.
+ *   real element (i, v) = real[i * real_stride + v * real_stride / 2] (a [n, 2, T] target at one time step: stride 2 T).
+ *   ws: swe_train_step_ws_bytes() bytes of scratch.
+ * swe_clip_adamw_step: torch.nn.utils.clip_grad_norm_(max_norm) (Lightning gradient_clip_val, /root/reference/main.py:109;
+ *   max_norm <= 0: none) followed by one torch.optim.AdamW step (/root/reference/training/train.py:147-155) on flat fp32
+ *   buffers of n elements; lr is a DEVICE scalar; state = {step count, last gradient norm, last clip coefficient}.
+ * ------------------------------------------------------------------------------------------- */
+size_t swe_train_step_ws_bytes(void);
+int swe_loss_fwd_bwd(const float* pred, const float* real, int64_t real_stride, const unsigned char* rows, int64_t n,
+                     int32_t only_where_water, int32_t mae, float w0, float w1, float scale, int32_t accumulate,
+                     float* loss, float* dpred, void* ws, void* stream);
+int swe_clip_adamw_step(float* params, float* grads, float* exp_avg, float* exp_avg_sq, int64_t n, const float* lr,
+                        float beta1, float beta2, float eps, float weight_decay, float max_norm, float* state,
+                        void* ws, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Dataset-side helpers on the device.
+ * swe_temporal_window: the temporal sample starting at init_time of a resident simulation — x [n, n_static + 2 previous_t],
+ *   y [n, 2, rollout_steps], bc_out [n_bc, previous_t, rollout_steps + 1] — as /root/reference/utils/dataset.py:410-471
+ *   (`to_temporal`) builds it: dry-bed prefix of previous_t - 1 zero steps, BC's last step repeated once.
+ *   wd, v: [n, t_sim]; bc: [n_bc, t_bc].
+ * swe_rollout_metrics: per time step, for up to 4 depth thresholds, TP / TN / FP / FN of pred vs real
+ *   (/root/reference/utils/miscellaneous.py:123-151), and the error sums of get_rollout_loss (miscellaneous.py:177-199):
+ *   out [T, swe_rollout_metrics_cols()] doubles = {TP, TN, FP, FN} x 4 thresholds | sum d0^2, sum d1^2, sum |d0|, sum |d1| |
+ *   the same four over rows with a non-zero difference | number of those rows.  pred, real: [n, 2, T].
+ * ------------------------------------------------------------------------------------------- */
+int swe_temporal_window(const float* x_static, int32_t n_static, const float* wd, const float* v, int64_t n, int32_t t_sim,
+                        const float* bc, int32_t n_bc, int32_t t_bc, int32_t init_time, int32_t previous_t,
+                        int32_t rollout_steps, float* x, float* y, float* bc_out, void* stream);
+int32_t swe_rollout_metrics_cols(void);
+size_t swe_rollout_metrics_ws_bytes(int32_t T);
+int swe_rollout_metrics(const float* pred, const float* real, int64_t n, int32_t T, const float* thr, int32_t n_thr,
+                        double* out, void* ws, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
  * Multi-GPU: halo exchange of a partitioned mesh over peer memory (one process per GPU; no reference counterpart,
  * contract = SURVEY.md §8(e): owned rows bit-identical to the single-GPU result).
  * swe_ipc_*: a cudaMalloc'ed, zero-filled arena with its 64-byte CUDA IPC handle; peers map it with swe_ipc_open.

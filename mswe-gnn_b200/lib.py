@@ -101,6 +101,13 @@ SIGNATURES = {
     "swe_apply_bc": (C.c_int, [_p, _i32, _i32, _i32, _i32, _p, _i32, _p, _i32, _p, _p]),
     "swe_step_advance": (C.c_int, [_p, _p]),
     "swe_pack_rows": (C.c_int, [_p, _p, _i64, _i32, _p, _p]),
+    "swe_temporal_window": (C.c_int, [_p, _i32, _p, _p, _i64, _i32, _p, _i32, _i32, _i32, _i32, _i32, _p, _p, _p, _p]),
+    "swe_rollout_metrics_cols": (_i32, []),
+    "swe_rollout_metrics_ws_bytes": (_sz, [_i32]),
+    "swe_rollout_metrics": (C.c_int, [_p, _p, _i64, _i32, _p, _i32, _p, _p, _p]),
+    "swe_train_step_ws_bytes": (_sz, []),
+    "swe_loss_fwd_bwd": (C.c_int, [_p, _p, _i64, _p, _i64, _i32, _i32, _f32, _f32, _f32, _i32, _p, _p, _p, _p]),
+    "swe_clip_adamw_step": (C.c_int, [_p, _p, _p, _p, _i64, _p, _f32, _f32, _f32, _f32, _f32, _p, _p, _p]),
     "swe_ipc_alloc": (C.c_int, [_sz, C.POINTER(C.c_void_p), C.c_char_p]),
     "swe_ipc_open": (C.c_int, [C.c_char_p, C.POINTER(C.c_void_p)]),
     "swe_ipc_close": (C.c_int, [_p]),
@@ -427,6 +434,42 @@ def apply_bc(x, n_static_raw, previous_t, type_bc, node_bc, bc, step_ptr):
 def pack_rows(src, idx, n_rows, dst):
     _check(load().swe_pack_rows(ptr(src), ptr(idx, torch.int32), n_rows, src.shape[1], ptr(dst), _stream()),
            "swe_pack_rows")
+
+
+def temporal_window(x_static, wd, v, bc, init_time, previous_t, rollout_steps, x, y, bc_out):
+    n, t_sim = wd.shape
+    n_static = 0 if x_static is None else int(x_static.shape[1])
+    n_bc, t_bc = (0, 1) if bc is None else (int(bc.shape[0]), int(bc.shape[1]))
+    _check(load().swe_temporal_window(ptr(x_static), n_static, ptr(wd), ptr(v), int(n), int(t_sim), ptr(bc), n_bc, t_bc,
+                                      int(init_time), int(previous_t), int(rollout_steps), ptr(x), ptr(y), ptr(bc_out), _stream()),
+           "swe_temporal_window")
+
+
+def rollout_metrics_cols() -> int:
+    return int(load().swe_rollout_metrics_cols())
+
+
+def rollout_metrics(pred, real, thr, out, ws):
+    n, _, T = pred.shape
+    _check(load().swe_rollout_metrics(ptr(pred), ptr(real), int(n), int(T), ptr(thr), 0 if thr is None else int(thr.numel()),
+                                      out.data_ptr(), ws.data_ptr(), _stream()), "swe_rollout_metrics")
+
+
+def train_step_ws_bytes() -> int:
+    return int(load().swe_train_step_ws_bytes())
+
+
+def loss_fwd_bwd(pred, real, real_stride, rows, n, only_where_water, mae, w0, w1, scale, accumulate, loss, dpred, ws):
+    """real: tensor whose data_ptr() is element (0, 0) of the target; rows: optional uint8 / bool [n] tensor."""
+    _check(load().swe_loss_fwd_bwd(ptr(pred), real.data_ptr(), int(real_stride), None if rows is None else rows.data_ptr(),
+                                   int(n), int(only_where_water), int(mae), float(w0), float(w1), float(scale), int(accumulate),
+                                   ptr(loss), ptr(dpred), ws.data_ptr(), _stream()), "swe_loss_fwd_bwd")
+
+
+def clip_adamw_step(params, grads, exp_avg, exp_avg_sq, lr, beta1, beta2, eps, weight_decay, max_norm, state, ws):
+    _check(load().swe_clip_adamw_step(ptr(params), ptr(grads), ptr(exp_avg), ptr(exp_avg_sq), int(params.numel()), ptr(lr),
+                                      float(beta1), float(beta2), float(eps), float(weight_decay), float(max_norm), ptr(state),
+                                      ws.data_ptr(), _stream()), "swe_clip_adamw_step")
 
 
 def ipc_alloc(nbytes: int):

@@ -224,15 +224,36 @@ def _adapt_cached(batch):
     return temp
 
 
+def loss_backend() -> str:
+    """'device' (default): the loss and its gradient are two kernels (training/optim.py:device_loss); 'torch': the mirror
+    of the reference's loss.py in torch ops (training/loss.py)."""
+    return os.environ.get("MSWE_LOSS", "device")
+
+
 def training_step(model, batch, rollout_steps: int = 1, type_loss: str = "RMSE", only_where_water: bool = True,
-                  velocity_scaler: float = 7.0, group=None):
+                  velocity_scaler: float = 7.0, group=None, optimizer=None):
     """One training step of the reference's ``LightningTrainer.training_step`` (``training/train.py:125-145``):
     BPTT through ``rollout_steps`` model calls (no detach), mean of the per-step losses, ``backward()``; with a
-    process group the flat gradient is all-reduced (data parallel over simulations).  Returns the detached loss.
-    The optimizer step stays with the caller (``torch.optim.AdamW`` in the reference, ``train.py:147-155``)."""
+    process group the gradient is all-reduced (data parallel over simulations).  Returns the detached loss.
+    ``optimizer``: a ``training.optim.FlatAdamW`` — its flat gradient is zeroed before and all-reduced in one piece after
+    the backward, and its (clip + AdamW) step is taken; otherwise the optimizer step stays with the caller
+    (``torch.optim.AdamW`` in the reference, ``train.py:147-155``)."""
     from .loss import loss_function
+    from .optim import device_loss
     temp = _adapt_cached(batch) if _is_batch(batch) else batch.clone()
     dyn = model.previous_t * NUM_WATER_VARS
+    if optimizer is not None:
+        optimizer.zero_grad()
+    use_dev = loss_backend() == "device"
+    rows = getattr(temp, "_finest_rows", None) if "node_ptr" in temp.keys() else None
+    if use_dev and "node_ptr" in temp.keys() and rows is None:
+        # finest-scale rows (loss.py:49-74), read from node_ptr once per graph object and kept on it
+        ptr = temp.node_ptr.reshape(-1, temp.node_ptr.shape[-1]).tolist()
+        rows = torch.zeros(temp.x.shape[0], dtype=torch.bool, device=temp.x.device)
+        for r in ptr:
+            rows[r[0]:r[1]] = True
+        temp._finest_rows = rows
+        batch._finest_rows = rows
     roll = []
     x = temp.x
     for i in range(rollout_steps):
@@ -241,12 +262,67 @@ def training_step(model, batch, rollout_steps: int = 1, type_loss: str = "RMSE",
         temp.x = torch.cat((x[:, :-dyn], xd), 1)
         preds = model(temp)
         x = use_prediction(temp.x, preds, model.previous_t)
-        roll.append(loss_function(preds, temp.y[:, :, i], temp, None, type_loss=type_loss,
-                                  only_where_water=only_where_water, velocity_scaler=velocity_scaler))
-    loss = torch.stack(roll).mean()
+        if use_dev:
+            roll.append(device_loss(preds, temp.y[:, :, i], rows, type_loss, only_where_water, velocity_scaler))
+        else:
+            roll.append(loss_function(preds, temp.y[:, :, i], temp, None, type_loss=type_loss,
+                                      only_where_water=only_where_water, velocity_scaler=velocity_scaler))
+    loss = roll[0] if len(roll) == 1 else torch.stack(roll).mean()
     loss.backward()
     if group is not None or (torch.distributed.is_available() and torch.distributed.is_initialized()
                              and torch.distributed.get_world_size() > 1):
-        from ..parallel import allreduce_gradients
-        allreduce_gradients(list(model.parameters()), group)
+        if optimizer is not None:
+            import torch.distributed as dist
+            dist.all_reduce(optimizer.grad, op=dist.ReduceOp.SUM, group=group)
+            optimizer.grad /= dist.get_world_size(group)
+        else:
+            from ..parallel import allreduce_gradients
+            allreduce_gradients(list(model.parameters()), group)
+    if optimizer is not None:
+        optimizer.step()
     return loss.detach()
+
+
+class TrainStepRunner:
+    """The whole training step — BC injection, ``rollout_steps`` forwards, loss, backward, gradient clipping, AdamW — as
+    ONE captured CUDA graph replayed per step (no host reads anywhere on the path).  The batch topology is fixed at
+    construction; ``step(x, y, BC)`` copies a new sample's values into the captured buffers.  Single GPU (a data-parallel
+    step has an all-reduce between backward and update and runs eagerly through ``training_step``)."""
+
+    def __init__(self, model, batch, optimizer, rollout_steps: int = 1, type_loss: str = "RMSE", only_where_water: bool = True,
+                 velocity_scaler: float = 7.0, use_cuda_graph: bool = True, warmup: int = 3):
+        self.model, self.batch, self.opt = model, batch, optimizer
+        self.kw = dict(rollout_steps=rollout_steps, type_loss=type_loss, only_where_water=only_where_water,
+                       velocity_scaler=velocity_scaler, optimizer=optimizer)
+        self.loss = torch.zeros((), dtype=torch.float32, device=batch.x.device)
+        self._graph = None
+        self.launches_per_step = 0
+        if use_cuda_graph:
+            s = torch.cuda.Stream()
+            s.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(s):                                   # warm-up off the capture stream (torch's recipe)
+                for _ in range(max(warmup, 1)):
+                    self._eager()
+            torch.cuda.current_stream().wait_stream(s)
+            torch.cuda.synchronize()
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                self._eager()
+            self._graph = g
+
+    def _eager(self):
+        c0 = lib.launch_count
+        self.loss.copy_(training_step(self.model, self.batch, **self.kw))
+        self.launches_per_step = lib.launch_count - c0
+
+    def step(self, x=None, y=None, BC=None) -> torch.Tensor:
+        """One optimizer step on the current (or the given) sample values; returns the device loss scalar (no host read)."""
+        for name, v in (("x", x), ("y", y), ("BC", BC)):
+            if v is not None:
+                getattr(self.batch, name).copy_(v, non_blocking=True)
+        if self._graph is not None:
+            self._graph.replay()
+            self.opt.mark_updated()          # the replay rewrote the parameters through raw pointers
+        else:
+            self._eager()
+        return self.loss
