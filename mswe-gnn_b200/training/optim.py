@@ -32,17 +32,22 @@ class FlatAdamW:
         if any(p.dtype != torch.float32 or p.device != dev for p in params):
             raise TypeError("all parameters must be float32 tensors on one CUDA device")
         self.params = params
-        n = sum(p.numel() for p in params)
-        self.flat = torch.empty(n, dtype=torch.float32, device=dev)
+        # every parameter starts on a 128-byte boundary of the flat buffer (the kernels read weights with 16-byte loads);
+        # the padding elements stay zero in the parameters, the gradient and both moments
+        al = lambda k: (k + 31) // 32 * 32
+        self.offsets = []
+        n = 0
+        for p in params:
+            self.offsets.append(n)
+            n += al(p.numel())
+        self.flat = torch.zeros(n, dtype=torch.float32, device=dev)
         self.grad = torch.zeros(n, dtype=torch.float32, device=dev)
-        off = 0
         with torch.no_grad():
-            for p in params:
+            for p, off in zip(params, self.offsets):
                 k = p.numel()
                 self.flat[off:off + k].copy_(p.detach().reshape(-1))
                 p.data = self.flat[off:off + k].view_as(p)              # the parameter IS a slice of the flat buffer now
                 p.grad = self.grad[off:off + k].view_as(p)              # autograd accumulates in place into the flat gradient
-                off += k
         self.exp_avg = torch.zeros_like(self.flat)
         self.exp_avg_sq = torch.zeros_like(self.flat)
         self.state = torch.zeros(4, dtype=torch.float32, device=dev)    # step count, last grad norm, last clip coefficient
@@ -60,11 +65,8 @@ class FlatAdamW:
                 break
 
     def _rebind_grads(self):
-        off = 0
-        for p in self.params:
-            k = p.numel()
-            p.grad = self.grad[off:off + k].view_as(p)
-            off += k
+        for p, off in zip(self.params, self.offsets):
+            p.grad = self.grad[off:off + p.numel()].view_as(p)
 
     def set_lr(self, lr: float):
         """A scheduler's new learning rate (device scalar: a captured step sees it on its next replay)."""

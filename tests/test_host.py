@@ -159,3 +159,27 @@ def test_sync_free_loss_equals_boolean_indexed_loss(type_loss):
         out[cached] = (loss.detach(), preds.grad.clone())
     assert torch.allclose(out[True][0], out[False][0], rtol=1e-6, atol=1e-8)
     assert torch.allclose(out[True][1], out[False][1], rtol=1e-5, atol=1e-9)
+
+
+def test_adapt_batch_device_equals_adapt_batch_training():
+    """The vectorised batch adaptation (one gather per edge list) against the mirror of the reference's Python slicing,
+    field by field, bit for bit — multi-scale batches with ragged graphs and a single-scale batch."""
+    import torch
+    from mswe_gnn_b200.training.train import adapt_batch_device, adapt_batch_training
+    from mswe_gnn_b200.utils.data import Batch
+    from mswe_gnn_b200.utils.synthetic import make_single_scale_mesh, make_tri_mesh
+    cases = [[make_tri_mesh(8 * (1 + s % 2), 8, 3, seed=s, orphan_every=5 if s == 1 else 0, extra_parent_every=4 if s == 2 else 0)
+              for s in range(4)],
+             [make_tri_mesh(16, 8, 4, seed=7)],
+             [make_single_scale_mesh(6 + s, 5, seed=s) for s in range(3)]]
+    for graphs in cases:
+        batch = Batch.from_data_list(graphs)
+        a, b = adapt_batch_training(batch), adapt_batch_device(batch)
+        assert sorted(a.keys()) == sorted(b.keys())
+        for k in a.keys():
+            va, vb = getattr(a, k), getattr(b, k)
+            if torch.is_tensor(va):
+                assert va.shape == vb.shape and torch.equal(va.to(torch.int64) if not va.is_floating_point() else va,
+                                                            vb.to(torch.int64) if not vb.is_floating_point() else vb), k
+            elif isinstance(va, (int, float)):
+                assert va == vb, k
