@@ -357,6 +357,8 @@ def run_ours(args):
     kern = profile_kernels(runner, alg) if (partitioned or rank == 0) else None
     if rank != 0:
         if world > 1:
+            if not args.no_training_extra:
+                training_extra(world, rank, dev)
             if partitioned:
                 runner.close()
             dist.destroy_process_group()
@@ -385,6 +387,9 @@ def run_ours(args):
         r = cpu_reference_rate(1, 1, wl=wl if wl != "cfg4" else "cfg3")
         cpu = {"value": r["value"], "unit": "node-steps/s", "cores": r["cores"], "kind": "port", "sample": r["sample"]}
 
+    training = None
+    if not args.no_training_extra:
+        training = training_extra(world, rank, dev)
     if partitioned:
         multi = (f"ONE mesh tri({nx},{ny}) = {N_global} nodes cut over {world} GPUs by blocks of coarsest cells "
                  f"(every level sharded, {halo_info['exchanges_per_step']} halo exchanges per step, "
@@ -415,6 +420,7 @@ def run_ours(args):
             "kernels": sorted(kern.values(), key=lambda r: -r["ms_per_step"]),
             "halo": halo_info,
             "parity_check": parity,
+            "training": training,
             "cpu_baseline": cpu}
     print(json.dumps(line), flush=True)
     if world > 1:
@@ -473,6 +479,48 @@ def cpu_training_rate(wl, threads=None):
     return dict(value=n / times[-1], cores=threads,
                 sample=f"1 training step (fwd+bwd, {R} rollout step) of the same {kind} on one tri({nx},{ny}) graph ({g.x.shape[0]} nodes), "
                        f"torch {torch.__version__} CPU autograd, {threads} threads")
+
+
+def training_extra(world, rank, dev, steps=10, warmup=3):
+    """Secondary metric on the default line (driver-visible): the training step.  N=1: cfg2-train (BASELINE.json configs[1],
+    single-scale SWE-GNN, 8 x 51,201-node graphs) as one captured graph; N>1: cfg5-train (configs[4]) data parallel over
+    simulations, 4 x 133,284-node graphs per GPU, one all-reduce of the flat gradient per step."""
+    import torch.distributed as dist
+    from mswe_gnn_b200.training.optim import FlatAdamW
+    from mswe_gnn_b200.training.train import TrainStepRunner, training_step
+    wl = "cfg2-train" if world == 1 else "cfg5-train"
+    kind, ctor, model, batch_host, R, (nx, ny, G) = _train_setup(wl, rank, dev)
+    batch = batch_host.to(dev)
+    opt = FlatAdamW(model, lr=3e-3, weight_decay=0.0, max_norm=1.0)
+    runner = TrainStepRunner(model, batch, opt, rollout_steps=R, use_cuda_graph=(world == 1), warmup=warmup)
+    step = (lambda: runner.step()) if world == 1 else \
+        (lambda: training_step(model, batch, R, only_where_water=True, velocity_scaler=7.0, optimizer=opt))
+    from mswe_gnn_b200 import lib as _lib
+    c0 = _lib.launch_count
+    for _ in range(warmup if world > 1 else 1):
+        step()
+    launches = (_lib.launch_count - c0) // (warmup if world > 1 else 1) if world > 1 else runner.launches_per_step
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        step()
+    e1.record()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1)
+    if world > 1:
+        t = torch.tensor([ms], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+    n = int(batch.x.shape[0])
+    return {"metric": "mSWE-GNN training node-steps/sec (forward+backward+clip+AdamW)", "workload": wl, "value": n * R * world * steps / (ms * 1e-3),
+            "unit": "node-steps/s", "ms_per_step": ms / steps, "n_gpus": world, "steps": steps, "nodes_per_gpu": n,
+            "cuda_graph": runner._graph is not None, "launches_per_step": launches,
+            "parallelism": "single GPU" if world == 1 else f"data parallel over simulations (dp{world}), all-reduce of the flat fp32 gradient"}
 
 
 def run_train(args):

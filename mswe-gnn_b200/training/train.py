@@ -182,9 +182,31 @@ class RolloutRunner:
         self.x.copy_(self.graph.x if x is None else x)
         self.step.zero_()
         self.done = 0
-        if x is not None:
-            self._token = new_static_token() # other static columns: the hoisted tables are recomputed (and the
-            self._graph = None               # captured step, which does not contain their producer, is re-captured)
+        if x is not None and not self.model.with_WL:
+            # other static columns and a model whose encoded static features are hoisted out of the step (with_WL=False):
+            # the hoisted tables are recomputed and the captured step, which does not contain their producer, re-captured.
+            # With with_WL=True (config.yaml) x_s is encoded inside every step and nothing of x is hoisted.
+            self._token = new_static_token()
+            self._graph = None
+
+    def rebind(self, graph) -> bool:
+        """Reuse this runner (plan, workspaces, captured step) for another graph object with the SAME topology: the
+        values that may differ — node inputs, boundary series, edge attributes — are copied / re-encoded into the buffers
+        the captured step reads.  False if the graph does not fit (the caller builds a new runner)."""
+        bc = graph.BC
+        if int(graph.type_BC) != self.type_BC or tuple(bc.shape) != tuple(self.bc.shape) or \
+                graph.node_BC.numel() != self.node_BC.numel() or tuple(graph.x.shape) != tuple(self.x.shape):
+            return False
+        self.graph = graph
+        self.bc.copy_(bc)
+        self.node_BC.copy_(graph.node_BC)
+        self.reset(graph.x)
+        ws = self.model._ws.get((self.plan.key, self.plan.n_nodes))
+        if ws is not None and ws.get("_plan") is self.plan:
+            self.model._encoded_edges(self.plan, graph, ws)       # edge attributes of the new object -> the cached buffer
+        else:
+            self._graph = None
+        return True
 
     def run(self, n_steps: Optional[int] = None):
         """Advance `n_steps` (default: all remaining) steps; returns the prediction buffer
@@ -232,14 +254,50 @@ def rollout_test(model, batch, use_cuda_graph: Optional[bool] = None):
     model: GNN or MSGNN from ``mswe_gnn_b200.models.gnn``
     batch: a single graph (``Data``) or several graphs stacked in a ``Batch``
     '''
-    temp = adapt_batch_training(batch) if _is_batch(batch) else batch.clone()
+    temp = adapt_batch_device(batch) if _is_batch(batch) else batch.clone()
     dynamic_vars = model.previous_t * model.NUM_WATER_VARS
     assert temp.x.shape[-1] >= dynamic_vars, \
         "The number of dynamic variables is greater than the number of node features"
     final_step = batch.y.shape[-1]
+    # Repeated calls on the same mesh (validation epochs, ensembles of boundary conditions) reuse plan, workspaces and the
+    # captured step: the runner is cached under a CONTENT hash of the topology (the tensors of a freshly loaded graph are
+    # new objects every time, so their addresses say nothing)
+    key = None
+    if temp.x.is_cuda and os.environ.get("MSWE_RUNNER_CACHE", "1") != "0":
+        key = (id(model), _topology_hash(temp), int(final_step), tuple(temp.x.shape), str(temp.x.device), use_cuda_graph)
+        hit = _RUNNER_CACHE.get(key)
+        if hit is not None and hit.model is model and hit.rebind(temp):
+            return hit.run().clone().permute(1, 2, 0)              # (a copy: the runner's buffer is rewritten by the next call)
     runner = RolloutRunner(model, temp, final_step, use_cuda_graph)
+    if key is not None:
+        if len(_RUNNER_CACHE) >= 2:
+            _RUNNER_CACHE.pop(next(iter(_RUNNER_CACHE)))
+        _RUNNER_CACHE[key] = runner
+        return runner.run().clone().permute(1, 2, 0)
     preds = runner.run()
     return preds.permute(1, 2, 0)
+
+
+_RUNNER_CACHE = {}
+_HASH_W = {}
+
+
+def _topology_hash(graph) -> tuple:
+    """Two 64-bit checksums (position-weighted sum, sum of squares; wrap-around arithmetic) of every topology tensor,
+    computed on the device and read back once (~1 ms for the 4 M-edge cfg3 mesh)."""
+    parts = []
+    for name in ("edge_index", "node_ptr", "edge_ptr", "intra_mesh_edge_index", "intra_edge_ptr", "node_BC"):
+        t = getattr(graph, name, None)
+        if not torch.is_tensor(t):
+            continue
+        v = t.reshape(-1).to(graph.x.device, torch.int64)
+        w = _HASH_W.get((v.numel(), v.device))
+        if w is None:
+            if len(_HASH_W) > 16:
+                _HASH_W.clear()
+            w = _HASH_W[(v.numel(), v.device)] = torch.arange(1, v.numel() + 1, dtype=torch.int64, device=v.device) * 0x9E3779B1 + 1
+        parts += [(v * w).sum(), (v * v).sum() + v.numel()]
+    return tuple(torch.stack(parts).tolist()) + tuple(tuple(getattr(graph, n).shape) for n in ("edge_index",))
 
 
 _ADAPT_CACHE = {}        # topology identity of a collated batch -> (tensors kept alive, adapted batch)

@@ -266,3 +266,31 @@ def test_large_mesh_properties():
     with torch.no_grad():
         z = m(d)
     assert float(z.abs().max()) == 0.0
+
+
+def test_rollout_test_reuses_runner_for_same_topology_with_new_values():
+    """Repeated rollout_test calls on freshly loaded copies of the same mesh reuse plan / workspaces / captured step (cache
+    keyed by a content hash of the topology): results equal a cold call bit for bit, also when node inputs, boundary
+    series and edge attributes change between calls; earlier results are not overwritten."""
+    from mswe_gnn_b200.training import train as T
+    ctor = dict(num_node_features=8, num_edge_features=1, num_scales=3, previous_t=3, **REF_CONFIG_MODELS)
+    m = build_model(dict(model="MSGNN", ctor=ctor), device=DEV)
+    base = make_tri_mesh(24, 16, 3, seed=4, rollout_steps=5)
+    variants = []
+    for k in range(3):
+        g = base.clone()
+        if k:
+            g.x[:, 2:] = g.x[:, 2:] * (1.0 + 0.3 * k)
+            g.BC = g.BC * (1.0 + k)
+            g.edge_attr = g.edge_attr * (1.0 - 0.2 * k)
+        variants.append(g)
+    T._RUNNER_CACHE.clear()
+    warm = [T.rollout_test(m, g.to(DEV)) for g in variants]          # first call builds, the others re-bind
+    assert len(T._RUNNER_CACHE) == 1
+    cold = []
+    for g in variants:
+        T._RUNNER_CACHE.clear()
+        cold.append(T.rollout_test(m, g.to(DEV)))
+    for a, b in zip(warm, cold):
+        assert torch.equal(a, b)
+    assert not torch.equal(warm[0], warm[1])                         # the variants really differ, and the results are copies
