@@ -97,9 +97,12 @@ __global__ void __launch_bounds__(NT) mlp_layer_bwd_dx_kernel(
     constexpr int LDD = KSUB + 4;
     float* D = smem;                       // [TM][KSUB + 4]: delta columns [c0, c0 + KSUB)
     float* Wb = smem + TM * LDD;           // [KSUB][KO]:     W rows     [c0, c0 + KSUB), columns k_off..
-    __shared__ float red[NT / 32];
+    __shared__ double red[NT / 32];
     const float slope = (act == SWE_ACT_PRELU && slope_p) ? __ldg(slope_p) : 0.f;
-    float db_acc0 = 0.f, db_acc1 = 0.f, ds_acc = 0.f;     // bias-gradient partials of columns t and KSUB + t (n <= 2 KSUB)
+    float db_acc0 = 0.f, db_acc1 = 0.f;                    // bias-gradient partials of columns t and KSUB + t (n <= 2 KSUB)
+    // PReLU-slope gradient: ONE scalar summed over rows x columns with heavy cancellation — accumulated in fp64 (in fp32
+    // the summation order alone moved it by 3e-4 relative on a 51 k-node graph)
+    double ds_acc = 0.0;
     const long long n_tiles = (n_rows + TM - 1) / TM;
     for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
         const long long row0 = tile * TM;
@@ -122,8 +125,8 @@ __global__ void __launch_bounds__(NT) mlp_layer_bwd_dx_kernel(
                     if (pre) {
                         const float4 p = ldg4(pre + g * n + c0 + 4 * q);
                         if (act == SWE_ACT_PRELU) {
-                            ds_acc += (p.x > 0.f ? 0.f : d.x * p.x) + (p.y > 0.f ? 0.f : d.y * p.y) +
-                                      (p.z > 0.f ? 0.f : d.z * p.z) + (p.w > 0.f ? 0.f : d.w * p.w);
+                            ds_acc += (double)((p.x > 0.f ? 0.f : d.x * p.x) + (p.y > 0.f ? 0.f : d.y * p.y)) +
+                                      (double)((p.z > 0.f ? 0.f : d.z * p.z) + (p.w > 0.f ? 0.f : d.w * p.w));
                         }
                         d.x *= act_grad(act, p.x, slope); d.y *= act_grad(act, p.y, slope);
                         d.z *= act_grad(act, p.z, slope); d.w *= act_grad(act, p.w, slope);
@@ -172,9 +175,9 @@ __global__ void __launch_bounds__(NT) mlp_layer_bwd_dx_kernel(
         if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = ds_acc;
         __syncthreads();
         if (threadIdx.x == 0) {
-            float t = 0.f;
+            double t = 0.0;
             for (int i = 0; i < NT / 32; ++i) t += red[i];
-            my[n] = t;
+            my[n] = (float)t;
         }
     }
 }
@@ -232,9 +235,9 @@ __global__ void reduce_partials_kernel(const float* __restrict__ part, int n_par
     for (int j = blockIdx.x * blockDim.x + threadIdx.x; j < n_items; j += gridDim.x * blockDim.x) {
         const int k = j % ko;
         if (k >= k_valid) continue;
-        float t = 0.f;
+        double t = 0.0;                                      // per-CTA partials combined in fp64, in CTA order
         for (int c = 0; c < n_parts; ++c) t += part[(long long)c * part_stride + item_off + j];
-        out[(long long)(j / ko) * ld_out + k_off + k] += t;
+        out[(long long)(j / ko) * ld_out + k_off + k] += (float)t;
     }
 }
 
@@ -323,15 +326,15 @@ __global__ void __launch_bounds__(NT) act_fwd_kernel(const float* __restrict__ x
 __global__ void __launch_bounds__(NT) act_bwd_kernel(const float* __restrict__ g, const float* __restrict__ x, long long n4,
                                                      int act, const float* __restrict__ slope_p, float* __restrict__ gx,
                                                      float* __restrict__ slope_part) {
-    __shared__ float red[NT / 32];
+    __shared__ double red[NT / 32];
     const float slope = (act == SWE_ACT_PRELU && slope_p) ? __ldg(slope_p) : 0.f;
-    float ds_acc = 0.f;
+    double ds_acc = 0.0;                                     // fp64: one heavily cancelling scalar (see mlp_layer_bwd_dx)
     for (long long i = (long long)blockIdx.x * NT + threadIdx.x; i < n4; i += (long long)gridDim.x * NT) {
         const float4 p = ldg4(x + 4 * i);
         float4 d = ldg4(g + 4 * i);
         if (act == SWE_ACT_PRELU)
-            ds_acc += (p.x > 0.f ? 0.f : d.x * p.x) + (p.y > 0.f ? 0.f : d.y * p.y) +
-                      (p.z > 0.f ? 0.f : d.z * p.z) + (p.w > 0.f ? 0.f : d.w * p.w);
+            ds_acc += (double)((p.x > 0.f ? 0.f : d.x * p.x) + (p.y > 0.f ? 0.f : d.y * p.y)) +
+                      (double)((p.z > 0.f ? 0.f : d.z * p.z) + (p.w > 0.f ? 0.f : d.w * p.w));
         d.x *= act_grad(act, p.x, slope); d.y *= act_grad(act, p.y, slope);
         d.z *= act_grad(act, p.z, slope); d.w *= act_grad(act, p.w, slope);
         stg4(gx + 4 * i, d);
@@ -342,9 +345,9 @@ __global__ void __launch_bounds__(NT) act_bwd_kernel(const float* __restrict__ g
         if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = ds_acc;
         __syncthreads();
         if (threadIdx.x == 0) {
-            float t = 0.f;
+            double t = 0.0;
             for (int i = 0; i < NT / 32; ++i) t += red[i];
-            slope_part[blockIdx.x] = t;
+            slope_part[blockIdx.x] = (float)t;
         }
     }
 }

@@ -370,7 +370,8 @@ __global__ void __launch_bounds__(TR_THREADS, 1) mlp_dx_tc_kernel(const __grid_c
         const float fslope = FUSED ? leaky_slope_of(p.act, p.slope_p) : 1.f;
         const bool prelu = FUSED && p.act == SWE_ACT_PRELU;
         float bacc[4][4];                                          // FUSED: Σ_rows delta of this thread's 4 columns per chunk
-        float sacc = 0.f;                                          //        Σ dh · pre over pre <= 0 (PReLU slope gradient)
+        double sacc = 0.0;                                         //        Σ dh · pre over pre <= 0 (PReLU slope gradient): fp64,
+                                                                   //        one heavily cancelling scalar (see swe_backward.cu)
 #pragma unroll
         for (int c = 0; c < 4; ++c) { bacc[c][0] = bacc[c][1] = bacc[c][2] = bacc[c][3] = 0.f; }
         auto stage = [&](int i) {
@@ -400,8 +401,8 @@ __global__ void __launch_bounds__(TR_THREADS, 1) mlp_dx_tc_kernel(const __grid_c
                         if (FUSED) {
                             const float4 q = pnx[j];
                             if (prelu)
-                                sacc += (q.x > 0.f ? 0.f : d.x * q.x) + (q.y > 0.f ? 0.f : d.y * q.y) +
-                                        (q.z > 0.f ? 0.f : d.z * q.z) + (q.w > 0.f ? 0.f : d.w * q.w);
+                                sacc += (double)((q.x > 0.f ? 0.f : d.x * q.x) + (q.y > 0.f ? 0.f : d.y * q.y)) +
+                                        (double)((q.z > 0.f ? 0.f : d.z * q.z) + (q.w > 0.f ? 0.f : d.w * q.w));
                             d.x *= q.x > 0.f ? 1.f : fslope; d.y *= q.y > 0.f ? 1.f : fslope;
                             d.z *= q.z > 0.f ? 1.f : fslope; d.w *= q.w > 0.f ? 1.f : fslope;
                             bacc[c][0] += d.x; bacc[c][1] += d.y; bacc[c][2] += d.z; bacc[c][3] += d.w;
@@ -466,7 +467,8 @@ __global__ void __launch_bounds__(TR_THREADS, 1) mlp_dx_tc_kernel(const __grid_c
             for (int c = 0; c < 4; ++c)
 #pragma unroll
                 for (int u = 0; u < 4; ++u) red[r0 * 128 + c * 32 + piece * 4 + u] = bacc[c][u];
-            red[32 * 128 + threadIdx.x] = sacc;
+            double* redd = reinterpret_cast<double*>(red + 32 * 128);
+            redd[threadIdx.x] = sacc;
             asm volatile("bar.sync 1, 256;" ::: "memory");
             float* my = p.part + (long long)blockIdx.x * (n + 1);
             if ((int)threadIdx.x < n) {
@@ -475,9 +477,9 @@ __global__ void __launch_bounds__(TR_THREADS, 1) mlp_dx_tc_kernel(const __grid_c
                 my[threadIdx.x] = t;
             }
             if (threadIdx.x == 0) {
-                float t = 0.f;
-                for (int r = 0; r < TR_ROW_THREADS; ++r) t += red[32 * 128 + r];
-                my[n] = t;
+                double t = 0.0;
+                for (int r = 0; r < TR_ROW_THREADS; ++r) t += redd[r];
+                my[n] = (float)t;
             }
         }
     } else if (lane == 0) {

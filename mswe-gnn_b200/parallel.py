@@ -496,6 +496,28 @@ class PartitionedRollout:
             torch.cuda.synchronize()
             self.halo.dist.barrier(group=self.halo.group)
 
+    def rebind(self, graph_cpu):
+        """Another simulation on the SAME partitioned mesh (new node inputs, boundary series, edge attributes — e.g. the
+        next sample of an ensemble, given as this rank's local graph on the host): the values are copied into the buffers
+        the captured step reads; plan, peer arena and captured graph are reused.  Collective."""
+        if self.peer:
+            torch.cuda.synchronize()
+            self.halo.dist.barrier(group=self.halo.group)
+        self.graph.x.copy_(graph_cpu.x, non_blocking=True)
+        self.graph.edge_attr.copy_(graph_cpu.edge_attr, non_blocking=True)      # (in place: bumps the version the encoder cache checks)
+        self.bc.copy_(graph_cpu.BC, non_blocking=True)
+        self.x.copy_(self.graph.x)
+        self.step.zero_()
+        self.done = 0
+        ws = self.model._ws.get((self.plan.key, self.plan.n_nodes))
+        if ws is not None and ws.get("_plan") is self.plan:
+            self.model._encoded_edges(self.plan, self.graph, ws)
+        else:
+            self._graph = None
+        if self.peer:
+            torch.cuda.synchronize()
+            self.halo.dist.barrier(group=self.halo.group)
+
     def run(self, n_steps: Optional[int] = None):
         n = self.T - self.done if n_steps is None else int(n_steps)
         if n < 0 or self.done + n > self.T:
