@@ -163,8 +163,8 @@ int swe_edge_gate_tc_fwd_listed(const float* xs, const float* xd_src, const floa
  * instructions of the 3xTF32 kernel, same three products, same fp32 accumulation).  Same contract and
  * reference span as swe_edge_gate_fwd (models/gnn.py:414-426).  Operands are scaled by powers of two into fp16's
  * exponent window: per matrix for the weights (wmax3 = HOST array of max |w| of the three layers, read when the
- * image is packed), per row for the hidden activations, a fixed factor for the gathered layer-0 inputs — whose
- * rows are range-checked while they are converted: tiles with a row maximum outside [2^-9, 2^11] are listed in
+ * image is packed), per row for the hidden activations, none for the gathered layer-0 inputs — whose
+ * rows are range-checked while they are converted: tiles with a row maximum outside [2^-5, 2^15] are listed in
  * flag_ws ((number of tiles + 1) int32 of scratch) and re-evaluated by swe_edge_gate_tc_fwd_listed from image_tf32
  * (the swe_gate_tc_pack image of the same weights).  flag_ws == NULL skips the guard (tests).
  * ------------------------------------------------------------------------------------------- */

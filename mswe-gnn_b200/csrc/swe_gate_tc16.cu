@@ -13,9 +13,9 @@
 //   * hidden activations (layers 1, 2): one exponent per ROW (max |y'| in [2^13, 2^14)), formed in the epilogue that
 //     produces the row (the thread owns it) and undone in the next epilogue — no range restriction at all;
 //   * layer-0 inputs (five gathered segments, converted by different threads before the row's maximum is known):
-//     the fixed factor 16, i.e. an absolute resolution of 2^-29 (<= 2^-20 of the row's maximum inside the
-//     guarded window) and a ceiling of 4094.  The kernel tracks max |x| per
-//     row while it converts; a tile with a row outside [2^-9, 2^11] (never seen with O(1) encoder outputs, but
+//     unscaled, i.e. an absolute resolution of 2^-25 (<= 2^-20 of the row's maximum inside the guarded window) and
+//     a ceiling of 65504.  The kernel tracks max |x| per
+//     row while it converts; a tile with a row outside [2^-5, 2^15] (never seen with O(1) encoder outputs, but
 //     nothing forbids it) is appended to a work list and redone by the TF32 kernel (swe_gate_tc.cu in list mode),
 //     so the result never depends on the window.
 //
@@ -53,7 +53,7 @@ constexpr int W_RES_BYTES = 4 * W1_CHUNK;       // W2 resident = 64 KB (W3 rides
 constexpr int A_STAGES = 2, W_STAGES = 2;           // per group
 constexpr int GROUP_THREADS = 256;
 constexpr int N_THREADS = 2 * GROUP_THREADS + 128;            // + MMA issuers (warps 16, 17) + weight loaders (18, 19)
-constexpr float L0_SCALE = 16.f;
+constexpr float L0_SCALE = 1.f;                 // layer-0 inputs go in unscaled (a multiply per element less in the gather)
 constexpr int N_IMG_FLOATS = 324;               // bias[320] | descale[3] | pad
 
 struct __align__(8) Bar {
@@ -255,8 +255,8 @@ __global__ void __launch_bounds__(N_THREADS, 1) edge_gate_tc16_kernel(const __gr
                         const float4 x = v[u];
                         m[u] = fmaxf(m[u], fmaxf(fmaxf(fabsf(x.x), fabsf(x.y)), fmaxf(fabsf(x.z), fabsf(x.w))));
                         uint2 hh, ll;
-                        split_f16x2(x.x * L0_SCALE, x.y * L0_SCALE, hh.x, ll.x);
-                        split_f16x2(x.z * L0_SCALE, x.w * L0_SCALE, hh.y, ll.y);
+                        split_f16x2(x.x, x.y, hh.x, ll.x);
+                        split_f16x2(x.z, x.w, hh.y, ll.y);
                         *reinterpret_cast<uint2*>(hi_t + u * 2048) = hh;
                         *reinterpret_cast<uint2*>(hi_t + A_TILE + u * 2048) = ll;
                     }
@@ -324,10 +324,10 @@ __global__ void __launch_bounds__(N_THREADS, 1) edge_gate_tc16_kernel(const __gr
                 group_sync(g);
                 m = fmaxf(m, xch[(hf ^ 1) * 128 + row]);
                 if (layer == 0 && hf == 0) {
-                    // range guard of the layer-0 conversion: every row's max |x| inside [2^-9, 2^11] (or exactly 0)
+                    // range guard of the layer-0 conversion: every row's max |x| inside [2^-5, 2^15] (or exactly 0)
                     const uint32_t mb = rowmax[row];
                     rowmax[row] = 0u;
-                    if (mb != 0u && (mb < 0x3B000000u || mb > 0x45000000u)) atomicOr(s_flag + g, 1);
+                    if (mb != 0u && (mb < 0x3D000000u || mb > 0x47000000u)) atomicOr(s_flag + g, 1);
                 }
                 // row scale: max |y'| in [2^13, 2^14)  (biased exponent E of m -> 2^(140 - E), clamped)
                 const uint32_t E = __float_as_uint(m) >> 23;
@@ -454,7 +454,7 @@ __global__ void __launch_bounds__(N_THREADS, 1) edge_gate_tc16_kernel(const __gr
         // =====================================================================================
         const int g = warp - 16;
         const int n_g = (n_my - g + 1) / 2;
-        if (lane == 0 && n_g > 0) {
+        if (n_g > 0) {                                                 // the whole warp, converged (see mma_f16_ss_warp)
             const uint32_t idesc128 = make_idesc_f16(128, 128), idesc64 = make_idesc_f16(128, 64);
             // shared-memory descriptors = constant high word | (address >> 4) | LBO bit: one 32-bit add per operand
             const uint64_t desc_hi = make_desc_sw64(0) & 0xFFFFFFFF00000000ull;
@@ -465,7 +465,7 @@ __global__ void __launch_bounds__(N_THREADS, 1) edge_gate_tc16_kernel(const __gr
                            w_res_d = desc_lo0 + (smem_u32(w_res) >> 4);
             const uint32_t d = tmem_base + (uint32_t)g * 256u, ta_hi = d + 128u, ta_lo = d + 192u;
             uint32_t a_slot = 0, a_ph = 0, w_slot = 0, w_ph = 0;       // ring positions stepped by compare-and-wrap
-            const bool tr = p.trace != nullptr && blockIdx.x == 0;
+            const bool tr = p.trace != nullptr && blockIdx.x == 0 && lane == 0;
 #define M_STAMP(j_, ev_) do { if (tr && (j_) < 8) p.trace[2 * 128 + (2 * (j_) + g) * 8 + (ev_)] = clock64(); } while (0)
             mbar_wait_spin(&bar->w_res, 0);
             tc_fence_after_sync();
@@ -484,18 +484,18 @@ __global__ void __launch_bounds__(N_THREADS, 1) edge_gate_tc16_kernel(const __gr
                     tc_fence_after_sync();
                     const uint32_t a_hi = a_ring_d + a_slot * (A_SLOT >> 4), a_lo = a_hi + (A_TILE >> 4);
                     const uint32_t w_hi = w_ring_d + w_slot * (W1_CHUNK >> 4), w_lo = w_hi + (W1_CHUNK >> 5);
-                    mma_f16_ss(d, dsc(a_lo), dsc(w_hi), idesc128, c ? 1u : 0u);        // + 32 B per K = 16 step
-                    mma_f16_ss(d, dsc(a_hi), dsc(w_lo), idesc128, 1u);
-                    mma_f16_ss(d, dsc(a_hi), dsc(w_hi), idesc128, 1u);
-                    mma_f16_ss(d, dsc(a_lo + 2), dsc(w_hi + 2), idesc128, 1u);
-                    mma_f16_ss(d, dsc(a_hi + 2), dsc(w_lo + 2), idesc128, 1u);
-                    mma_f16_ss(d, dsc(a_hi + 2), dsc(w_hi + 2), idesc128, 1u);
-                    mma_commit(&bar->a_empty[g][a_slot]);
-                    mma_commit(&bar->w_empty[g][w_slot]);
+                    mma_f16_ss_warp(d, dsc(a_lo), dsc(w_hi), idesc128, c ? 1u : 0u);        // + 32 B per K = 16 step
+                    mma_f16_ss_warp(d, dsc(a_hi), dsc(w_lo), idesc128, 1u);
+                    mma_f16_ss_warp(d, dsc(a_hi), dsc(w_hi), idesc128, 1u);
+                    mma_f16_ss_warp(d, dsc(a_lo + 2), dsc(w_hi + 2), idesc128, 1u);
+                    mma_f16_ss_warp(d, dsc(a_hi + 2), dsc(w_lo + 2), idesc128, 1u);
+                    mma_f16_ss_warp(d, dsc(a_hi + 2), dsc(w_hi + 2), idesc128, 1u);
+                    mma_commit_warp(&bar->a_empty[g][a_slot]);
+                    mma_commit_warp(&bar->w_empty[g][w_slot]);
                     if (++a_slot == A_STAGES) { a_slot = 0; a_ph ^= 1; }
                     if (++w_slot == W_STAGES) { w_slot = 0; w_ph ^= 1; }
                 }
-                mma_commit(&bar->d_full[g]);
+                mma_commit_warp(&bar->d_full[g]);
                 M_STAMP(j, 1);
                 // ---- layer 1 (TS): A from TMEM, W2 resident
                 mbar_wait_spin(&bar->a_ready[g], 0u);                        // (2 j) & 1
@@ -504,11 +504,11 @@ __global__ void __launch_bounds__(N_THREADS, 1) edge_gate_tc16_kernel(const __gr
 #pragma unroll
                 for (int ks = 0; ks < GH / 16; ++ks) {
                     const uint32_t w_hi = w_res_d + (uint32_t)(ks >> 1) * (W1_CHUNK >> 4) + (uint32_t)(ks & 1) * 2u, w_lo = w_hi + (W1_CHUNK >> 5);
-                    mma_f16_ts(d, ta_lo + ks * 8, dsc(w_hi), idesc128, ks ? 1u : 0u);
-                    mma_f16_ts(d, ta_hi + ks * 8, dsc(w_lo), idesc128, 1u);
-                    mma_f16_ts(d, ta_hi + ks * 8, dsc(w_hi), idesc128, 1u);
+                    mma_f16_ts_warp(d, ta_lo + ks * 8, dsc(w_hi), idesc128, ks ? 1u : 0u);
+                    mma_f16_ts_warp(d, ta_hi + ks * 8, dsc(w_lo), idesc128, 1u);
+                    mma_f16_ts_warp(d, ta_hi + ks * 8, dsc(w_hi), idesc128, 1u);
                 }
-                mma_commit(&bar->d_full[g]);
+                mma_commit_warp(&bar->d_full[g]);
                 M_STAMP(j, 3);
                 // ---- layer 2 (TS, N = 64): W3 in the group's two ring slots (two K-chunks each)
                 mbar_wait_spin(&bar->a_ready[g], 1u);                        // (2 j + 1) & 1
@@ -523,14 +523,14 @@ __global__ void __launch_bounds__(N_THREADS, 1) edge_gate_tc16_kernel(const __gr
                         const int ks = half * 4 + kk;
                         const uint32_t w_hi = w_ring_d + w_slot * (W1_CHUNK >> 4) + (uint32_t)(kk >> 1) * (W3_CHUNK >> 4) + (uint32_t)(kk & 1) * 2u,
                                        w_lo = w_hi + (W3_CHUNK >> 5);
-                        mma_f16_ts(d, ta_lo + ks * 8, dsc(w_hi), idesc64, ks ? 1u : 0u);
-                        mma_f16_ts(d, ta_hi + ks * 8, dsc(w_lo), idesc64, 1u);
-                        mma_f16_ts(d, ta_hi + ks * 8, dsc(w_hi), idesc64, 1u);
+                        mma_f16_ts_warp(d, ta_lo + ks * 8, dsc(w_hi), idesc64, ks ? 1u : 0u);
+                        mma_f16_ts_warp(d, ta_hi + ks * 8, dsc(w_lo), idesc64, 1u);
+                        mma_f16_ts_warp(d, ta_hi + ks * 8, dsc(w_hi), idesc64, 1u);
                     }
-                    mma_commit(&bar->w_empty[g][w_slot]);
+                    mma_commit_warp(&bar->w_empty[g][w_slot]);
                     if (++w_slot == W_STAGES) { w_slot = 0; w_ph ^= 1; }
                 }
-                mma_commit(&bar->d_full[g]);
+                mma_commit_warp(&bar->d_full[g]);
                 M_STAMP(j, 5);
             }
 #undef M_STAMP

@@ -126,6 +126,6 @@ if os.environ.get("TRACE16"):
     for r, nm in enumerate(["group0", "group1", "mma"]):
         for tile in range(8):
             print("  ", nm, tile, [(int(v) - t0) if int(v) else None for v in t[r, tile]])
-    print("  MMA issuer, layer 0 of tile 4, per chunk: [before waits, A chunk ready, W chunk ready, issued]")
+    print("  gather of group 0, its tile 2, per chunk: [before a_empty wait, slot free, converted + stored, fenced + arrived]")
     for c in range(10):
         print("    chunk", c, [(int(v) - t0) if int(v) else None for v in tc[4 * c:4 * c + 4]])
