@@ -371,7 +371,7 @@ def run_ours(args):
     pk = peaks()
     dom = max(kern.values(), key=lambda r: r["ms_per_step"])
     try:                                                 # measured DRAM bytes of one level-0 launch (ncu --set full capture)
-        tr = json.load(open(os.path.join(ROOT, "profiles", "traffic_r01.json"))).get(dom["name"])
+        tr = json.load(open(os.path.join(ROOT, "profiles", "traffic_r02.json"))).get(dom["name"])
         traffic = {"dram_bytes_per_level0_launch": tr["dram_bytes_per_launch"],
                    "algorithmic_bytes_per_level0_launch": tr["algorithmic_bytes_per_launch"], "capture": tr["capture"]} if tr else None
     except Exception:
@@ -638,7 +638,7 @@ def run_train(args):
 def _traffic_of(name):
     """Measured DRAM bytes of one launch of `name` from the committed ncu --set full captures (or None)."""
     try:
-        tr = json.load(open(os.path.join(ROOT, "profiles", "traffic_r01.json"))).get(name)
+        tr = json.load(open(os.path.join(ROOT, "profiles", "traffic_r02.json"))).get(name)
         return {"dram_bytes_per_launch": tr["dram_bytes_per_launch"],
                 "algorithmic_bytes_per_launch": tr["algorithmic_bytes_per_launch"], "capture": tr["capture"]} if tr else None
     except Exception:
