@@ -54,7 +54,7 @@ constexpr int A_STAGES = 2, W_STAGES = 2;           // per group
 constexpr int GROUP_THREADS = 256;
 constexpr int N_THREADS = 2 * GROUP_THREADS + 128;            // + MMA issuers (warps 16, 17) + weight loaders (18, 19)
 constexpr float L0_SCALE = 1.f;                 // layer-0 inputs go in unscaled (a multiply per element less in the gather)
-constexpr int N_IMG_FLOATS = 324;               // bias[320] | descale[3] | pad
+constexpr int N_IMG_FLOATS = 328;               // bias[320] | descale[3] | pad | max |bias| of layers 0, 1 | pad
 
 struct __align__(8) Bar {
     uint64_t a_full[2][A_STAGES], a_empty[2][A_STAGES];
@@ -109,6 +109,10 @@ __global__ void gate_tc16_pack_kernel(const float* __restrict__ w1, int k1, cons
         else if (i == 320) v = ldexpf(1.f / L0_SCALE, -e1);          // D0 -> pre-activation of layer 0
         else if (i == 321) v = ldexpf(1.f, -e2);                     // x the row's own 2^-e
         else if (i == 322) v = ldexpf(1.f, -e3);
+        else if (i == 324 || i == 325) {                             // max |bias| of layers 0 / 1 (the epilogues' row-scale bound)
+            const float* b = i == 324 ? b1 : b2;
+            for (int j = 0; b && j < 128; ++j) v = fmaxf(v, fabsf(b[j]));
+        }
         f[i] = v;
     }
 }
@@ -299,9 +303,11 @@ __global__ void __launch_bounds__(N_THREADS, 1) edge_gate_tc16_kernel(const __gr
                 mbar_wait(&bar->d_full[g], (uint32_t)(3 * j + layer) & 1);
                 tc_fence_after_sync();
                 G_STAMP(j, 2 + 2 * layer);
-                // pass 1: the row's largest |activation| (this thread's 64 columns), nothing kept in registers.
-                // Leaky family: |act(v)| = v (v > 0) or |slope| |v|, so the extremes of v are enough.
-                float m = 0.f, vmin = 0.f;
+                // pass 1: an UPPER BOUND of the row's largest |activation| (this thread's 64 columns), nothing kept in
+                // registers.  Leaky family: |act(v)| <= |v| <= dsc max|D| + max|bias| — one FMNMX per element; the bound only
+                // has to keep the scaled row inside fp16 (it is at most the row maximum plus the largest bias, i.e. it costs a
+                // bit or two of the 14 bits of headroom above fp16's normal range, never accuracy of the leading part).
+                float m = 0.f;
 #pragma unroll
                 for (int cb = 0; cb < 2; ++cb) {
                     uint32_t v[32];
@@ -312,14 +318,16 @@ __global__ void __launch_bounds__(N_THREADS, 1) edge_gate_tc16_kernel(const __gr
 #pragma unroll
                         for (int i = 0; i < 32; ++i) d[i] = __uint_as_float(v[i]) * dsc;
                     }
+                    if (GENERIC && !al.leaky) {
 #pragma unroll
-                    for (int i = 0; i < 32; ++i) {
-                        const float t = fmaf(__uint_as_float(v[i]), dsc, bias[cb * 32 + i]);
-                        if (GENERIC && !al.leaky) m = fmaxf(m, fabsf(act_generic16(al.act, t, al.slope)));
-                        else { m = fmaxf(m, t); vmin = fminf(vmin, t); }
+                        for (int i = 0; i < 32; ++i)
+                            m = fmaxf(m, fabsf(act_generic16(al.act, fmaf(__uint_as_float(v[i]), dsc, bias[cb * 32 + i]), al.slope)));
+                    } else {
+#pragma unroll
+                        for (int i = 0; i < 32; ++i) m = fmaxf(m, fabsf(__uint_as_float(v[i])));
                     }
                 }
-                m = fmaxf(m, fabsf(al.slope) * -vmin);
+                if (!(GENERIC && !al.leaky)) m = fmaf(m, fabsf(dsc), s_f[324 + layer]) * fmaxf(1.f, fabsf(al.slope));   // + max |bias|; a learned slope may exceed 1
                 xch[hf * 128 + row] = m;
                 group_sync(g);
                 m = fmaxf(m, xch[(hf ^ 1) * 128 + row]);
