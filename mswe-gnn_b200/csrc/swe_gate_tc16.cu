@@ -129,6 +129,7 @@ struct Gate16Params {
     int n_seg; int segs[5];                       // layer-0 input segments in order (0 x_s[r], 1 x_s[c], 2 x_d[r], 3 x_d[c], 4 a_e)
     int* flag_ws;                                 // [0] = number of flagged tiles, [1 + i] = tile ids (capacity: all tiles)
     long long* trace;                             // optional [3 roles][16 tiles][8 events] clock64 stamps of CTA 0 (profiling aid)
+    unsigned stagger_ns;                          // start offset of group 1 (see the kernel)
 };
 
 __device__ __noinline__ float act_generic16(int act, float v, float slope) { return act_apply(act, v, slope); }
@@ -144,7 +145,10 @@ __device__ __forceinline__ ActSel act_select(int act, const float* slope_p) {
 template <bool GENERIC>
 __device__ __forceinline__ float act_do(const ActSel& a, float v) {
     if (GENERIC) { if (!a.leaky) return act_generic16(a.act, v, a.slope); }
-    return fmaxf(v, 0.f) + a.slope * fminf(v, 0.f);
+    // v > 0 ? v : slope v  as one multiply and one min/max (slope <= 1: the larger of v and slope v, else the smaller);
+    // the selection is loop-invariant and becomes FMNMX's predicate operand
+    const float t = a.slope * v;
+    return a.slope <= 1.f ? fmaxf(v, t) : fminf(v, t);
 }
 
 __device__ __forceinline__ void group_sync(int g) { asm volatile("bar.sync %0, 256;" ::"r"(1 + g) : "memory"); }
@@ -215,6 +219,9 @@ __global__ void __launch_bounds__(N_THREADS, 1) edge_gate_tc16_kernel(const __gr
         const bool tr = p.trace != nullptr && blockIdx.x == 0 && tg == 0;
 #define G_STAMP(j_, ev_) do { if (tr && (j_) < 16) p.trace[g * 128 + (j_) * 8 + (ev_)] = clock64(); } while (0)
 
+        // the two groups start half a tile period apart, so that one gathers (LSU, conversion ALU, layer-0 MMAs) while the
+        // other runs its epilogues (TMEM, ALU) instead of both doing the same thing at the same time
+        if (g == 1 && n_g > 0 && p.stagger_ns > 0) __nanosleep(p.stagger_ns);
 #pragma unroll 1
         for (int j = 0; j < n_g; ++j) {
             const long long tile = (long long)blockIdx.x + (long long)(g + 2 * j) * gridDim.x;
@@ -394,7 +401,7 @@ __global__ void __launch_bounds__(N_THREADS, 1) edge_gate_tc16_kernel(const __gr
                 group_sync(g);
                 ss += xch[(hf ^ 1) * 128 + row];
                 float inv = 1.f;
-                if (p.normalize) inv = 1.f / sqrtf(ss);                  // ss == 0 -> inf -> 0 * inf = NaN -> 0 below
+                if (p.normalize) inv = ss > 0.f ? 1.f / sqrtf(ss) : 0.f; // all-zero row: 0 / 0 = NaN -> 0 in the reference (gnn.py:425-426)
                 // rows go through a shared-memory stage (the group's idle A ring) so that the global stores are whole
                 // 256-byte rows, two per warp instruction, instead of 32 scattered 16-byte pieces (16-byte pieces of a row
                 // XOR-ed with the row number: conflict-free on both sides without padding — the ring is exactly 32 KB)
@@ -404,8 +411,6 @@ __global__ void __launch_bounds__(N_THREADS, 1) edge_gate_tc16_kernel(const __gr
                     float4 r;
                     r.x = __uint_as_float(v[i]) * inv; r.y = __uint_as_float(v[i + 1]) * inv;
                     r.z = __uint_as_float(v[i + 2]) * inv; r.w = __uint_as_float(v[i + 3]) * inv;
-                    r.x = (r.x != r.x) ? 0.f : r.x; r.y = (r.y != r.y) ? 0.f : r.y;      // NaN -> 0 (gnn.py:426)
-                    r.z = (r.z != r.z) ? 0.f : r.z; r.w = (r.w != r.w) ? 0.f : r.w;
                     *reinterpret_cast<float4*>(st + ((((hf * 32 + i) >> 2) ^ (row & 7)) << 2)) = r;
                 }
                 if (tg == 0 && s_flag[g]) {                              // (set during epilogue 0, group barriers ago)
@@ -605,6 +610,7 @@ extern "C" int swe_edge_gate_tc16_fwd(const float* xs, const float* xd_src, cons
     }
     p.normalize = normalize; p.s_out = s_out; p.dbg = dbg; p.flag_ws = flag_ws;
     p.trace = g_tc16_trace; g_tc16_trace = nullptr;
+    { static int st = -1; if (st < 0) { const char* e = getenv("MSWE_TC16_STAGGER_NS"); st = e ? atoi(e) : 8000; } p.stagger_ns = (unsigned)st; }
     p.n_seg = 0;
     for (int sg = 0; sg < 5; ++sg)
         if (sg < 3 || (sg == 3 && xd_dst) || (sg == 4 && a)) p.segs[p.n_seg++] = sg;
