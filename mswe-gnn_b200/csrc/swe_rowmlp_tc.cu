@@ -31,8 +31,11 @@ constexpr int R_A_TILE = R_TILE * 128;          // [128 x 32] tf32 tile, bytes
 constexpr int R_A_SLOT = 4 * R_A_TILE;          // 2 chunks x (hi | lo)
 constexpr int R_W_TILE = RF * 128;              // [64 x 32] tf32 tile
 constexpr size_t R_W_IMAGE = 4 * (size_t)R_W_TILE;       // 32 KB per layer (same layout as swe_hop_tc_pack)
-constexpr int R_ROW_WARPS = 16, R_ROW_THREADS = 512, R_EPI_WARPS = 4;
-constexpr int R_THREADS = R_ROW_THREADS + R_EPI_WARPS * 32 + 32;    // 672
+#ifndef SWE_R_EPI_WARPS
+#define SWE_R_EPI_WARPS 4
+#endif
+constexpr int R_ROW_WARPS = 16, R_ROW_THREADS = 512, R_EPI_WARPS = SWE_R_EPI_WARPS;   // 4 or 8 (2 per TMEM lane quarter, 32 columns each)
+constexpr int R_THREADS = R_ROW_THREADS + R_EPI_WARPS * 32 + 32;    // 800
 constexpr int R_STAGE_LD = RF + 4;
 constexpr size_t R_STAGE_BYTES = (size_t)R_TILE * R_STAGE_LD * 4;
 // TMEM columns (512 allocated): everything between the two tensor-core layers is double-buffered by tile parity, so
@@ -51,7 +54,7 @@ __device__ __forceinline__ float tanh_inline(float x) {
     const float ax = fabsf(x), x2 = x * x;
     const float poly = x * fmaf(x2, fmaf(x2, fmaf(x2, fmaf(x2, 0.021869488f, -0.053968254f), 0.13333333f), -0.33333333f), 1.f);
     const float t = __expf(-2.f * ax);
-    const float big = copysignf((1.f - t) / (1.f + t), x);
+    const float big = copysignf(__fdividef(1.f - t, 1.f + t), x);        // rcp.approx + mul: 2 ulp, no IEEE-division subroutine
     return ax < 0.25f ? poly : big;
 }
 struct ActSel { int act; float slope; bool leaky; };
@@ -198,6 +201,20 @@ __global__ void __launch_bounds__(R_THREADS, 1) row_mlp_tc_kernel(const __grid_c
             for (int c = 0; c < 4; ++c) bf[c] = s_bf[q4 + c];
         }
         const int n_static_raw = p.n_cols - 2 * p.previous_t;
+        // head constants of this lane (column q of a node's inputs, columns [4 q, 4 q + 4) of the last hidden layer), read once
+        float4 wh0 = make_float4(0.f, 0.f, 0.f, 0.f), wh1 = wh0;
+        float res_w0 = 0.f, res_w1 = 0.f, bh0 = 0.f, bh1 = 0.f;
+        if (p.head) {
+            wh0 = *reinterpret_cast<const float4*>(s_wh + q4); wh1 = *reinterpret_cast<const float4*>(s_wh + 64 + q4);
+            const int rel = q - n_static_raw;
+            if (rel >= 0 && q < p.n_cols && p.res_mode != 0) {
+                const int t = rel >> 1, jv = rel & 1;
+                const float w = p.res_mode == 1 ? __ldg(p.res_w + t) : p.res_mode == 2 ? __ldg(p.res_w + 2 * t + jv)
+                                : (t == p.previous_t - 1 ? 1.f : 0.f);
+                if (jv) res_w1 = w; else res_w0 = w;
+            }
+            if (p.b_head) { bh0 = __ldg(p.b_head); bh1 = __ldg(p.b_head + 1); }
+        }
         auto finish_tile = [&](int j) {
             const long long r0 = (tile0 + j) * R_TILE;
             // head: lane c (< n_cols <= 16) of a row's 16 lanes owns input column c of that row: one coalesced
@@ -217,6 +234,7 @@ __global__ void __launch_bounds__(R_THREADS, 1) row_mlp_tc_kernel(const __grid_c
                 }
             }
             const float* stg = stage + (j & 1) * (R_TILE * R_STAGE_LD);
+            float* pred_step = (p.head && q < 2) ? p.pred + (p.step_ptr ? (long long)(*p.step_ptr) * p.pred_step_stride : 0) : nullptr;
             mbar_wait(&bar->st_full[j & 1], ((uint32_t)j >> 1) & 1);
             if (warp == 0) R_STAMP(0, j + 2, 6);
 #pragma unroll
@@ -228,17 +246,10 @@ __global__ void __launch_bounds__(R_THREADS, 1) row_mlp_tc_kernel(const __grid_c
                     if (row < p.n_rows) stg4(p.out_rows + ((long long)p.row_lo + row) * RF + q4, d);
                 } else {
                     // last decoder layer 64 -> 2: every lane holds 4 of the 64 inputs
-                    float y0 = d.x * s_wh[q4] + d.y * s_wh[q4 + 1] + d.z * s_wh[q4 + 2] + d.w * s_wh[q4 + 3];
-                    float y1 = d.x * s_wh[64 + q4] + d.y * s_wh[64 + q4 + 1] + d.z * s_wh[64 + q4 + 2] + d.w * s_wh[64 + q4 + 3];
+                    float y0 = d.x * wh0.x + d.y * wh0.y + d.z * wh0.z + d.w * wh0.w;
+                    float y1 = d.x * wh1.x + d.y * wh1.y + d.z * wh1.z + d.w * wh1.w;
                     // residual (models/models.py:50-77): this lane's column contributes to variable (c - n_static) & 1
-                    float c0 = 0.f, c1 = 0.f;
-                    const int rel = q - n_static_raw;
-                    if (rel >= 0 && q < p.n_cols && p.res_mode != 0) {
-                        const int t = rel >> 1, jv = rel & 1;
-                        const float w = p.res_mode == 1 ? __ldg(p.res_w + t) : p.res_mode == 2 ? __ldg(p.res_w + 2 * t + jv)
-                                        : (t == p.previous_t - 1 ? 1.f : 0.f);
-                        if (jv) c1 = xr[k] * w; else c0 = xr[k] * w;
-                    }
+                    float c0 = xr[k] * res_w0, c1 = xr[k] * res_w1;
 #pragma unroll
                     for (int off = 8; off >= 1; off >>= 1) {
                         y0 += __shfl_xor_sync(0xffffffffu, y0, off);
@@ -247,16 +258,13 @@ __global__ void __launch_bounds__(R_THREADS, 1) row_mlp_tc_kernel(const __grid_c
                         c1 += __shfl_xor_sync(0xffffffffu, c1, off);
                     }
                     const float shifted = __shfl_down_sync(0xffffffffu, xr[k], 2, 16);       // column c + 2 of the same row
-                    if (p.b_head) { y0 += __ldg(p.b_head); y1 += __ldg(p.b_head + 1); }
+                    y0 += bh0; y1 += bh1;
                     y0 = fmaxf(act_do(a_h, y0) + c0, 0.f);
                     y1 = fmaxf(act_do(a_h, y1) + c1, 0.f);
                     const float oh = (fabsf(y0) > p.eps) ? y0 : 0.f;                        // h · [|h| > eps]
                     const float oq = (y0 != 0.f) ? y1 : 0.f;                                 // q · [h != 0] (un-thresholded h)
                     if (row < p.n_rows) {
-                        if (q < 2) {
-                            float* pr = p.pred + (p.step_ptr ? (long long)(*p.step_ptr) * p.pred_step_stride : 0) + orow[k] * 2;
-                            pr[q] = q ? oq : oh;
-                        }
+                        if (q < 2) pred_step[orow[k] * 2 + q] = q ? oq : oh;
                         if (p.x_next && q < p.n_cols) {
                             const float v = q < n_static_raw ? xr[k] : (q < p.n_cols - 2 ? shifted : (q == p.n_cols - 2 ? oh : oq));
                             p.x_next[orow[k] * p.n_cols + q] = v;
@@ -276,13 +284,9 @@ __global__ void __launch_bounds__(R_THREADS, 1) row_mlp_tc_kernel(const __grid_c
                 for (int k = 0; k < 4; ++k) {
                     const long long row = r0 + g + 32 * k;
                     x[k] = make_float4(0.f, 0.f, 0.f, 0.f);
-                    if (row < p.n_rows) {
-                        x[k] = ldg4(p.x_rows + ((long long)p.row_lo + row) * RF + q4);
-                        if (p.act_in != SWE_ACT_NONE) {
-                            x[k].x = act_in_do(a_in, x[k].x); x[k].y = act_in_do(a_in, x[k].y);
-                            x[k].z = act_in_do(a_in, x[k].z); x[k].w = act_in_do(a_in, x[k].w);
-                        }
-                    }
+                    // (the input activation is applied one phase later, activate_tile: the loads fly while tile i - 2 is
+                    //  written out; rows past the end stay zero or become act(0) — they are computed but never stored)
+                    if (row < p.n_rows) x[k] = ldg4(p.x_rows + ((long long)p.row_lo + row) * RF + q4);
                 }
             } else {
                 // first encoder layer on CUDA cores: the 8 raw inputs of this thread's 4 rows, then one pass over k with
@@ -343,6 +347,15 @@ __global__ void __launch_bounds__(R_THREADS, 1) row_mlp_tc_kernel(const __grid_c
                 }
             }
         };
+        auto activate_tile = [&]() {
+            if (p.x_rows && p.act_in != SWE_ACT_NONE) {
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    x[k].x = act_in_do(a_in, x[k].x); x[k].y = act_in_do(a_in, x[k].y);
+                    x[k].z = act_in_do(a_in, x[k].z); x[k].w = act_in_do(a_in, x[k].w);
+                }
+            }
+        };
         // one loop with ONE call site per phase (the phases are big inlined lambdas; with a prologue and two epilogue
         // copies the kernel was 10.9 k SASS instructions): iteration i stores tile i, requests tile i + 1 and writes
         // out tile i - 2.  The output lags two tiles behind the input: waiting for tile i - 1 (whose layer 1 is only
@@ -351,6 +364,7 @@ __global__ void __launch_bounds__(R_THREADS, 1) row_mlp_tc_kernel(const __grid_c
         for (int i = -1; i < n_my + 2; ++i) {
             if (i >= 0 && i < n_my) {
                 if (warp == 0) R_STAMP(0, i, 0);
+                activate_tile();
                 mbar_wait(&bar->a_empty, ((uint32_t)i & 1) ^ 1);           // layer-0 MMAs of the previous tile are done
                 if (warp == 0) R_STAMP(0, i, 2);
                 unsigned char* base = a_slot + (size_t)chunk * 2 * R_A_TILE;
@@ -375,7 +389,7 @@ __global__ void __launch_bounds__(R_THREADS, 1) row_mlp_tc_kernel(const __grid_c
         // epilogue warps.  Two-layer stacks:  E0(0) ; for i: { E0(i + 1) ; E1(i) }  — the operand of layer 1 of the next
         // tile is produced before this tile's layer-1 result is awaited, so the tensor pipe always has work queued.
         // =====================================================================================
-        const int lq = warp & 3;
+        const int lq = warp & 3, hf0 = (warp - R_ROW_WARPS) >> 2;       // lane quarter, first column half
         const uint32_t lane_addr = tmem_base + ((uint32_t)(lq * 32) << 16);
         // everything indexed by the layer is selected into registers HERE: a runtime index into the parameter
         // struct (or a local array) becomes a local-memory load + a dependent branch per element in the loops below
@@ -390,7 +404,7 @@ __global__ void __launch_bounds__(R_THREADS, 1) row_mlp_tc_kernel(const __grid_c
             mbar_wait(&bar->d0_full[b], bph);
             tc_fence_after_sync();
 #pragma unroll 1
-            for (int hf = 0; hf < 2; ++hf) {
+            for (int hf = hf0; hf < 2; hf += R_EPI_WARPS / 4) {
                 uint32_t v[32], lo[32];
                 tmem_ld32(lane_addr + RC_D0 + bo + hf * 32, v);
                 tmem_wait_ld();
@@ -414,15 +428,15 @@ __global__ void __launch_bounds__(R_THREADS, 1) row_mlp_tc_kernel(const __grid_c
             if (two && i + 1 < n_my) e0(i + 1);
             if (i < 0) continue;
             const uint32_t b = (uint32_t)i & 1, bph = ((uint32_t)i >> 1) & 1, bo = b * 64;
-            if (lq == 0) R_STAMP(1, i, 1);
+            if (warp == R_ROW_WARPS) R_STAMP(1, i, 1);
             if (two) mbar_wait(&bar->d1_full[b], bph); else mbar_wait(&bar->d0_full[b], bph);
             tc_fence_after_sync();
             mbar_wait(&bar->st_empty[b], bph ^ 1);                        // this stage buffer consumed (tile i-2)
             float* my_row = my_row0 + b * (R_TILE * R_STAGE_LD);
-            if (lq == 0) R_STAMP(1, i, 2);
+            if (warp == R_ROW_WARPS) R_STAMP(1, i, 2);
             const uint32_t dcol = (two ? RC_D1 : RC_D0) + bo;
 #pragma unroll 1
-            for (int hf = 0; hf < 2; ++hf) {
+            for (int hf = hf0; hf < 2; hf += R_EPI_WARPS / 4) {
                 uint32_t v[32];
                 tmem_ld32(lane_addr + dcol + hf * 32, v);
                 tmem_wait_ld();
@@ -439,7 +453,7 @@ __global__ void __launch_bounds__(R_THREADS, 1) row_mlp_tc_kernel(const __grid_c
             tc_fence_before_sync();
             if (two) mbar_arrive(&bar->d1_free[b]); else mbar_arrive(&bar->d0_free[b]);
             mbar_arrive(&bar->st_full[b]);
-            if (lq == 0) R_STAMP(1, i, 3);
+            if (warp == R_ROW_WARPS) R_STAMP(1, i, 3);
         }
     } else {
         // =====================================================================================
