@@ -382,9 +382,10 @@ def run_ours(args):
     else:
         roof = {"bound": "tensor", "kernel": dom["name"], "achieved": dom["tflops"], "peak": pk["bf16"], "unit": "TFLOP/s",
                 "frac": dom["tflops"] / pk["bf16"], "traffic": traffic, "peak_source": pk["hbm_src"] + " (sustained bf16)",
-                "note": "algorithmic FLOPs of the reference edge MLP / time; executed as 3 TF32 MMAs per product (error-free "
-                        "hi/lo splits for fp32 parity), and tcgen05 issues one 128x128x8 TF32 instruction per >= 94 cycles "
-                        "(tools/microbench/mma_rate.cu), so the ceiling of this formulation is ~0.19 of the bf16 peak"}
+                "note": ("algorithmic FLOPs of the reference edge MLP / time; executed as 3 MMAs per product (hi/lo splits for fp32 "
+                         "parity): fp16 hi/lo on kind::f16 = 108 instructions of 64 cycles per 128 edges "
+                         "(tools/microbench/mma_rate3.cu), i.e. a ceiling of ~0.50 of the bf16 peak for this formulation; the "
+                         "3xTF32 kernel (MSWE_GATE=tc) needs 216 instructions: ~0.25")}
     step_gbs = alg["total"] / (ms * 1e-3 / K) / 1e9
 
     cpu = None
