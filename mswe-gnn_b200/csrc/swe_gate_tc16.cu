@@ -2,8 +2,8 @@
 // hi/lo splits on kind::tf32 (K = 8).  Same arithmetic contract as swe_gate_tc.cu (models/gnn.py:414-426, F = 64,
 // 3-layer edge MLP 5F|4F -> 2F -> 2F -> F, fp32 accumulation in TMEM, result within rel 1e-5 per layer of fp32),
 // half the tensor-core instructions: 108 instead of 216 per 128-edge tile — the instruction count is what bounds the
-// TF32 kernel (tools/microbench/mma_rate2.cu: one tcgen05.mma with M = 128, N <= 128 retires per ~105-111 cycles
-// whatever its kind, so K = 16 per instruction does twice the work of K = 8).
+// TF32 kernel (tools/microbench/mma_rate3.cu: one tcgen05.mma with M = 128, N = 128 retires per 64 cycles whatever its
+// kind, operand source or swizzle, so K = 16 per instruction does twice the work of K = 8).
 //
 // Precision.  x' = 2^e x is split as hi = rn16(x'), lo = rn16(x' - hi); |x' - hi - lo| <= max(2^-24 |x'|, 2^-25).
 // A·W ≈ A_lo·W_hi + A_hi·W_lo + A_hi·W_hi (dropped A_lo·W_lo <= 2^-22 |A||W|): the same three products as 3xTF32.

@@ -1,5 +1,5 @@
 // Hop kernel with the F×F filter on the 5th-generation tensor cores (F = 64), fp16 hi/lo edition (kind::f16, K = 16 per
-// instruction, 64-byte swizzle: 12 tcgen05.mma of 64 cycles per 128-node tile instead of 24 of ~105, and an A operand of
+// instruction, 64-byte swizzle: 12 tcgen05.mma per 128-node tile instead of 24 (same cycles each), and an A operand of
 // 32 KB instead of 64 KB — the shared-memory / L1 pipe this kernel's gathers live on gets that bandwidth and capacity
 // back).  Same contract as swe_hop_tc.cu.  agg rows are scaled per row by a power of two (max |agg'| in [2^13, 2^14),
 // exact) before the split, the filter per matrix; the epilogue undoes both.  Replaces
