@@ -100,9 +100,10 @@ __global__ void __launch_bounds__(NT) mlp_layer_bwd_dx_kernel(
     __shared__ double red[NT / 32];
     const float slope = (act == SWE_ACT_PRELU && slope_p) ? __ldg(slope_p) : 0.f;
     float db_acc0 = 0.f, db_acc1 = 0.f;                    // bias-gradient partials of columns t and KSUB + t (n <= 2 KSUB)
-    // PReLU-slope gradient: ONE scalar summed over rows x columns with heavy cancellation — accumulated in fp64 (in fp32
-    // the summation order alone moved it by 3e-4 relative on a 51 k-node graph)
-    double ds_acc = 0.0;
+    // PReLU-slope gradient: ONE scalar summed over rows x columns with heavy cancellation.  Per thread in fp32 (fp64 here
+    // cost two F2F.F64 per float4 on the quarter-rate pipe: +2 ms per cfg2-train step, and did not move the error, which
+    // comes from the forward's rounding at the PReLU kinks); the cross-thread and cross-CTA sums are fp64.
+    float ds_acc = 0.f;
     const long long n_tiles = (n_rows + TM - 1) / TM;
     for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
         const long long row0 = tile * TM;
@@ -125,8 +126,8 @@ __global__ void __launch_bounds__(NT) mlp_layer_bwd_dx_kernel(
                     if (pre) {
                         const float4 p = ldg4(pre + g * n + c0 + 4 * q);
                         if (act == SWE_ACT_PRELU) {
-                            ds_acc += (double)((p.x > 0.f ? 0.f : d.x * p.x) + (p.y > 0.f ? 0.f : d.y * p.y)) +
-                                      (double)((p.z > 0.f ? 0.f : d.z * p.z) + (p.w > 0.f ? 0.f : d.w * p.w));
+                            ds_acc += (p.x > 0.f ? 0.f : d.x * p.x) + (p.y > 0.f ? 0.f : d.y * p.y) +
+                                      (p.z > 0.f ? 0.f : d.z * p.z) + (p.w > 0.f ? 0.f : d.w * p.w);
                         }
                         d.x *= act_grad(act, p.x, slope); d.y *= act_grad(act, p.y, slope);
                         d.z *= act_grad(act, p.z, slope); d.w *= act_grad(act, p.w, slope);
@@ -235,9 +236,16 @@ __global__ void reduce_partials_kernel(const float* __restrict__ part, int n_par
     for (int j = blockIdx.x * blockDim.x + threadIdx.x; j < n_items; j += gridDim.x * blockDim.x) {
         const int k = j % ko;
         if (k >= k_valid) continue;
-        double t = 0.0;                                      // per-CTA partials combined in fp64, in CTA order
-        for (int c = 0; c < n_parts; ++c) t += part[(long long)c * part_stride + item_off + j];
-        out[(long long)(j / ko) * ld_out + k_off + k] += (float)t;
+        // per-CTA partials in CTA order, fp32 with two interleaved accumulators (fp64 here made the kernel conversion-bound:
+        // 3.3 instead of 1.5 ms per cfg2-train step, for no measurable change of the gradients)
+        float t0 = 0.f, t1 = 0.f;
+        int c = 0;
+        for (; c + 1 < n_parts; c += 2) {
+            t0 += part[(long long)c * part_stride + item_off + j];
+            t1 += part[(long long)(c + 1) * part_stride + item_off + j];
+        }
+        if (c < n_parts) t0 += part[(long long)c * part_stride + item_off + j];
+        out[(long long)(j / ko) * ld_out + k_off + k] += t0 + t1;
     }
 }
 
@@ -328,13 +336,13 @@ __global__ void __launch_bounds__(NT) act_bwd_kernel(const float* __restrict__ g
                                                      float* __restrict__ slope_part) {
     __shared__ double red[NT / 32];
     const float slope = (act == SWE_ACT_PRELU && slope_p) ? __ldg(slope_p) : 0.f;
-    double ds_acc = 0.0;                                     // fp64: one heavily cancelling scalar (see mlp_layer_bwd_dx)
+    float ds_acc = 0.f;                                      // per thread fp32, across threads / CTAs fp64 (see mlp_layer_bwd_dx)
     for (long long i = (long long)blockIdx.x * NT + threadIdx.x; i < n4; i += (long long)gridDim.x * NT) {
         const float4 p = ldg4(x + 4 * i);
         float4 d = ldg4(g + 4 * i);
         if (act == SWE_ACT_PRELU)
-            ds_acc += (double)((p.x > 0.f ? 0.f : d.x * p.x) + (p.y > 0.f ? 0.f : d.y * p.y)) +
-                      (double)((p.z > 0.f ? 0.f : d.z * p.z) + (p.w > 0.f ? 0.f : d.w * p.w));
+            ds_acc += (p.x > 0.f ? 0.f : d.x * p.x) + (p.y > 0.f ? 0.f : d.y * p.y) +
+                      (p.z > 0.f ? 0.f : d.z * p.z) + (p.w > 0.f ? 0.f : d.w * p.w);
         d.x *= act_grad(act, p.x, slope); d.y *= act_grad(act, p.y, slope);
         d.z *= act_grad(act, p.z, slope); d.w *= act_grad(act, p.w, slope);
         stg4(gx + 4 * i, d);

@@ -370,8 +370,8 @@ __global__ void __launch_bounds__(TR_THREADS, 1) mlp_dx_tc_kernel(const __grid_c
         const float fslope = FUSED ? leaky_slope_of(p.act, p.slope_p) : 1.f;
         const bool prelu = FUSED && p.act == SWE_ACT_PRELU;
         float bacc[4][4];                                          // FUSED: Σ_rows delta of this thread's 4 columns per chunk
-        double sacc = 0.0;                                         //        Σ dh · pre over pre <= 0 (PReLU slope gradient): fp64,
-                                                                   //        one heavily cancelling scalar (see swe_backward.cu)
+        float sacc = 0.f;                                          //        Σ dh · pre over pre <= 0 (PReLU slope gradient): per thread
+                                                                   //        fp32, across threads fp64 (see swe_backward.cu)
 #pragma unroll
         for (int c = 0; c < 4; ++c) { bacc[c][0] = bacc[c][1] = bacc[c][2] = bacc[c][3] = 0.f; }
         auto stage = [&](int i) {
@@ -401,8 +401,8 @@ __global__ void __launch_bounds__(TR_THREADS, 1) mlp_dx_tc_kernel(const __grid_c
                         if (FUSED) {
                             const float4 q = pnx[j];
                             if (prelu)
-                                sacc += (double)((q.x > 0.f ? 0.f : d.x * q.x) + (q.y > 0.f ? 0.f : d.y * q.y)) +
-                                        (double)((q.z > 0.f ? 0.f : d.z * q.z) + (q.w > 0.f ? 0.f : d.w * q.w));
+                                sacc += (q.x > 0.f ? 0.f : d.x * q.x) + (q.y > 0.f ? 0.f : d.y * q.y) +
+                                        (q.z > 0.f ? 0.f : d.z * q.z) + (q.w > 0.f ? 0.f : d.w * q.w);
                             d.x *= q.x > 0.f ? 1.f : fslope; d.y *= q.y > 0.f ? 1.f : fslope;
                             d.z *= q.z > 0.f ? 1.f : fslope; d.w *= q.w > 0.f ? 1.f : fslope;
                             bacc[c][0] += d.x; bacc[c][1] += d.y; bacc[c][2] += d.z; bacc[c][3] += d.w;
