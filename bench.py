@@ -315,18 +315,15 @@ def run_ours(args):
             # the next simulation on the same partitioned mesh: inputs from pinned host memory into the runner's buffers
             # (plan, peer arena and captured step are reused, as rollout_test's runner cache does on one GPU)
             r_e2e.rebind(host_p)
-            preds = r_e2e.run()
-            out_host.copy_(preds[:, owned_rows], non_blocking=True)
+            r_e2e.run(out_host=out_host)                # owned rows of every step -> pinned host while the next step runs
             torch.cuda.synchronize()
     else:
         def e2e_call():
             ta = time.perf_counter()
             g = host_p.to(dev, non_blocking=True)
             torch.cuda.synchronize(); tb = time.perf_counter()
-            pred = rollout_test(model, g)
+            rollout_test(model, g, out_host=out_host)  # every step's predictions -> pinned host while the next step runs
             torch.cuda.synchronize(); tc_ = time.perf_counter()
-            out_host.copy_(pred.permute(2, 0, 1), non_blocking=True)
-            torch.cuda.synchronize()
             if os.environ.get("BENCH_E2E_DEBUG"):
                 print(f"e2e: h2d {1e3 * (tb - ta):.1f} ms, rollout_test {1e3 * (tc_ - tb):.1f} ms, d2h {1e3 * (time.perf_counter() - tc_):.1f} ms",
                       file=sys.stderr)
@@ -417,9 +414,11 @@ def run_ours(args):
             "clocks": clocks,
             "e2e": {"value": e2e_value, "unit": "node-steps/s", "h2d_bytes_per_step": h2d // K, "d2h_bytes_per_step": n_out * 8,
                     "what": ("PartitionedRollout.rebind(pinned local graph) + run(): node inputs, boundary series and edge attributes "
-                             "host -> device, K captured steps with halo exchange, owned predictions -> pinned host (partitioning, "
-                             "plan and peer arena built once per mesh); median of 3 calls") if partitioned else
-                            "rollout_test(model, host_graph): pinned host graph -> device, K steps, predictions -> pinned host; the runner "
+                             "host -> device, K captured steps with halo exchange, owned predictions of every step -> pinned host on a side "
+                             "stream while the next step runs (run(out_host=...)); partitioning, plan and peer arena built once per "
+                             "mesh; median of 3 calls") if partitioned else
+                            "rollout_test(model, graph, out_host=pinned): pinned host graph -> device, K steps, every step's predictions -> pinned "
+                            "host on a side stream while the next step runs; the runner "
                             "(plan, workspaces, captured step) is cached per mesh under a content hash of the topology; median of 3 calls"},
             "gpu_launches": per_step_launches * K,
             "roofline": roof,

@@ -518,24 +518,53 @@ class PartitionedRollout:
             torch.cuda.synchronize()
             self.halo.dist.barrier(group=self.halo.group)
 
-    def run(self, n_steps: Optional[int] = None):
+    def _stream_out(self, out_host, step: int):
+        """Device -> host copy of the OWNED rows of prediction slot `step` (one contiguous range per scale) on a side
+        stream, ordered after the kernels issued so far: it overlaps the next step (training/train.py:RolloutRunner)."""
+        main = torch.cuda.current_stream()
+        if getattr(self, "_copy_stream", None) is None:
+            self._copy_stream = torch.cuda.Stream(device=self.preds.device)
+        ev = torch.cuda.Event()
+        ev.record(main)
+        self._copy_stream.wait_event(ev)
+        with torch.cuda.stream(self._copy_stream):
+            off = 0
+            for s_ in range(self.part.num_scales):
+                lo, cnt = int(self.part.scale_lo[s_]), int(self.part.n_owned[s_])
+                out_host[step, off:off + cnt].copy_(self.preds[step, lo:lo + cnt], non_blocking=True)
+                off += cnt
+
+    def run(self, n_steps: Optional[int] = None, out_host: Optional[torch.Tensor] = None):
+        """out_host: optional pinned host tensor ``[T, n_owned_rows, 2]`` receiving the owned rows (the order of
+        ``part.owned_rows``) of every step while the next one runs."""
         n = self.T - self.done if n_steps is None else int(n_steps)
         if n < 0 or self.done + n > self.T:
             raise ValueError(f"rollout of {self.T} steps: {self.done} done, {n} more requested (call reset() first)")
+        if out_host is not None:
+            want = (self.T, int(len(self.part.owned_rows)), int(self.preds.shape[-1]))
+            if not (out_host.is_pinned() and out_host.dtype == torch.float32 and out_host.is_contiguous()
+                    and tuple(out_host.shape) == want):
+                raise ValueError(f"out_host must be a pinned contiguous float32 tensor of shape {want}")
         done = 0
         if self.use_cuda_graph and self._graph is None and n > 1:
             self._one_step()                     # eager: lazy packing / allocation happen here
             done = 1
+            if out_host is not None:
+                self._stream_out(out_host, self.done)
             g = torch.cuda.CUDAGraph()
             torch.cuda.synchronize()
             with torch.cuda.graph(g):
                 self._one_step()
             self._graph = g
-        for _ in range(done, n):
+        for j in range(done, n):
             if self._graph is not None:
                 self._graph.replay()
             else:
                 self._one_step()
+            if out_host is not None:
+                self._stream_out(out_host, self.done + j)
+        if out_host is not None:
+            torch.cuda.current_stream().wait_stream(self._copy_stream)
         self.done += n
         return self.preds
 

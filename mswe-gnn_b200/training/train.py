@@ -208,9 +208,31 @@ class RolloutRunner:
             self._graph = None
         return True
 
-    def run(self, n_steps: Optional[int] = None):
+    def _stream_out(self, out_host, step: int, slices=None):
+        """Queue the device -> host copy of prediction slot `step` on the runner's copy stream, ordered after the kernels
+        issued so far: the copy of step t overlaps the computation of step t + 1 (the slots are written once)."""
+        main = torch.cuda.current_stream()
+        if getattr(self, "_copy_stream", None) is None:
+            self._copy_stream = torch.cuda.Stream(device=self.preds.device)
+        ev = torch.cuda.Event()
+        ev.record(main)
+        self._copy_stream.wait_event(ev)
+        with torch.cuda.stream(self._copy_stream):
+            if slices is None:
+                out_host[step].copy_(self.preds[step], non_blocking=True)
+            else:
+                for (dst_lo, src_lo, cnt) in slices:
+                    out_host[step, dst_lo:dst_lo + cnt].copy_(self.preds[step, src_lo:src_lo + cnt], non_blocking=True)
+
+    def run(self, n_steps: Optional[int] = None, out_host: Optional[torch.Tensor] = None):
         """Advance `n_steps` (default: all remaining) steps; returns the prediction buffer
-        ``[T, N, 2]`` (slot t holds step t)."""
+        ``[T, N, 2]`` (slot t holds step t).  out_host: optional PINNED host tensor ``[T, N, 2]``; every step's slot is
+        copied into it on a side stream while the next step runs (complete when this call's stream work has finished:
+        the current stream waits for the copies before run() returns)."""
+        if out_host is not None:
+            if not (out_host.is_pinned() and out_host.dtype == torch.float32 and tuple(out_host.shape) == tuple(self.preds.shape)
+                    and out_host.is_contiguous()):
+                raise ValueError(f"out_host must be a pinned contiguous float32 tensor of shape {tuple(self.preds.shape)}")
         n = self.T - self.done if n_steps is None else int(n_steps)
         if n < 0 or self.done + n > self.T:
             # the decode kernel writes slot `step` of preds and apply_bc reads BC[..., step]: going past T would run
@@ -227,6 +249,8 @@ class RolloutRunner:
                 self.model._xs_stamp = None
             self._one_step()                     # eager: lazy packing / allocation happen here
             done = 1
+            if out_host is not None:
+                self._stream_out(out_host, self.done)
             ws = self.model._ws.get((self.plan.key, self.plan.n_nodes))
             if ws is not None:
                 ws["_static_owner"] = self._token
@@ -236,23 +260,31 @@ class RolloutRunner:
                 self._one_step()
             self._graph = g
             self._graph_stamp = self._replay_stamp()
-        for _ in range(done, n):
+        for j in range(done, n):
             if self._graph is not None:
                 self._graph.replay()
             else:
                 self._one_step()
+            if out_host is not None:
+                self._stream_out(out_host, self.done + j)
+        if out_host is not None:
+            torch.cuda.current_stream().wait_stream(self._copy_stream)
         self.done += n
         return self.preds
 
 
 @torch.no_grad()
-def rollout_test(model, batch, use_cuda_graph: Optional[bool] = None):
+def rollout_test(model, batch, use_cuda_graph: Optional[bool] = None, out_host: Optional[torch.Tensor] = None):
     '''
     Tests a model and returns the rollout prediction ``[N, 2, T]`` (reference
     ``training/train.py:67-95``).
     ------
     model: GNN or MSGNN from ``mswe_gnn_b200.models.gnn``
     batch: a single graph (``Data``) or several graphs stacked in a ``Batch``
+    out_host: optional pinned host tensor ``[T, N, 2]`` (step-major, the runner's own layout) that receives the
+        predictions step by step while the rollout is still running (device -> host copies on a side stream, ordered
+        before the end of the call's stream work) — what an evaluation loop that wants the result on the host
+        passes instead of calling ``.cpu()`` on the returned tensor
     '''
     temp = adapt_batch_device(batch) if _is_batch(batch) else batch.clone()
     dynamic_vars = model.previous_t * model.NUM_WATER_VARS
@@ -267,14 +299,14 @@ def rollout_test(model, batch, use_cuda_graph: Optional[bool] = None):
         key = (id(model), _topology_hash(temp), int(final_step), tuple(temp.x.shape), str(temp.x.device), use_cuda_graph)
         hit = _RUNNER_CACHE.get(key)
         if hit is not None and hit.model is model and hit.rebind(temp):
-            return hit.run().clone().permute(1, 2, 0)              # (a copy: the runner's buffer is rewritten by the next call)
+            return hit.run(out_host=out_host).clone().permute(1, 2, 0)   # (a copy: the runner's buffer is rewritten by the next call)
     runner = RolloutRunner(model, temp, final_step, use_cuda_graph)
     if key is not None:
         if len(_RUNNER_CACHE) >= 2:
             _RUNNER_CACHE.pop(next(iter(_RUNNER_CACHE)))
         _RUNNER_CACHE[key] = runner
-        return runner.run().clone().permute(1, 2, 0)
-    preds = runner.run()
+        return runner.run(out_host=out_host).clone().permute(1, 2, 0)
+    preds = runner.run(out_host=out_host)
     return preds.permute(1, 2, 0)
 
 

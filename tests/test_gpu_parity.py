@@ -294,3 +294,24 @@ def test_rollout_test_reuses_runner_for_same_topology_with_new_values():
     for a, b in zip(warm, cold):
         assert torch.equal(a, b)
     assert not torch.equal(warm[0], warm[1])                         # the variants really differ, and the results are copies
+
+
+def test_rollout_test_streams_predictions_to_pinned_host():
+    """rollout_test(..., out_host=pinned [T, N, 2]) fills the host buffer step by step on a side stream: same bits as the
+    returned device tensor, on the first call (eager step + capture) and on a cached-runner call; a wrong buffer is refused."""
+    from mswe_gnn_b200.training.train import rollout_test
+    from mswe_gnn_b200.utils.synthetic import make_tri_mesh
+    ctor = dict(num_node_features=8, num_edge_features=1, num_scales=3, previous_t=3, **REF_CONFIG_MODELS)
+    m = build_model(dict(model="MSGNN", ctor=ctor), device=DEV)
+    d = make_tri_mesh(24, 20, 3, seed=4, rollout_steps=5).to(DEV)
+    N, T = d.x.shape[0], d.y.shape[-1]
+    host = torch.full((T, N, 2), float("nan")).pin_memory()
+    for _ in range(2):
+        host.fill_(float("nan"))
+        pred = rollout_test(m, d, out_host=host)                       # [N, 2, T]
+        torch.cuda.synchronize()
+        assert torch.equal(host, pred.permute(2, 0, 1).cpu())
+    with pytest.raises(ValueError):
+        rollout_test(m, d, out_host=torch.empty(T, N, 2))              # not pinned
+    with pytest.raises(ValueError):
+        rollout_test(m, d, out_host=torch.empty(T + 1, N, 2).pin_memory())

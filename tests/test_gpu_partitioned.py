@@ -35,8 +35,12 @@ def _worker(rank, world, port, steps, mesh_kw, out, transport="staged"):
         model = MSGNN(**CTOR).to(dev)
         g = make_tri_mesh(24, 16, 3, rollout_steps=steps, seed=5, **mesh_kw)
         pr = PartitionedRollout(model, g, steps, dev, transport=transport)
-        pr.run()
+        # the owned rows of every step also stream to a pinned host buffer while the next step runs (run(out_host=...))
+        host = torch.full((steps, len(pr.part.owned_rows), 2), float("nan")).pin_memory()
+        pr.run(out_host=host)
+        torch.cuda.synchronize()
         preds, gids = pr.owned_predictions()
+        assert torch.equal(host, preds.cpu())
         out[rank] = (preds.cpu().numpy(), gids, pr.halo.n_exchanges)
         pr.close()
         if rank == 0:
