@@ -222,15 +222,22 @@ __global__ void __launch_bounds__(N_THREADS, 1) edge_gate_tc16_kernel(const __gr
         // the two groups start half a tile period apart, so that one gathers (LSU, conversion ALU, layer-0 MMAs) while the
         // other runs its epilogues (TMEM, ALU) instead of both doing the same thing at the same time
         if (g == 1 && n_g > 0 && p.stagger_ns > 0) __nanosleep(p.stagger_ns);
+        // endpoint (src for threads 0-127, dst for 128-255) of this thread's edge of tile j_: fetched one tile ahead, while the
+        // epilogue chain of the tile before runs (it used to cost ~1.5 k cycles at the head of every tile)
+        auto endpoint_of = [&](int j_) -> int32_t {
+            if (j_ >= n_g) return 0;
+            long long e = ((long long)blockIdx.x + (long long)(g + 2 * j_) * gridDim.x) * TILE + (tg & 127);
+            if (e >= p.n_edges) e = p.n_edges - 1;
+            return tg < 128 ? __ldg(p.src + e) : __ldg(p.dst + e);
+        };
+        int32_t next_id = endpoint_of(0);
 #pragma unroll 1
         for (int j = 0; j < n_g; ++j) {
             const long long tile = (long long)blockIdx.x + (long long)(g + 2 * j) * gridDim.x;
             const long long e0 = tile * TILE;
             // ---------------------------------------------------------------- endpoints of the tile
             {
-                long long e = e0 + (tg & 127);
-                if (e >= p.n_edges) e = p.n_edges - 1;
-                ids[tg] = tg < 128 ? __ldg(p.src + e) : __ldg(p.dst + e);
+                ids[tg] = next_id;
                 group_sync(g);
             }
             G_STAMP(j, 0);
@@ -298,6 +305,7 @@ __global__ void __launch_bounds__(N_THREADS, 1) edge_gate_tc16_kernel(const __gr
 #pragma unroll
                 for (int u = 0; u < 4; ++u) atomicMax(rowmax + rr + 32 * u, __float_as_uint(m[u]) & 0x7fffffffu);
             }
+            next_id = endpoint_of(j + 1);                                // consumed at the head of the next tile
             G_STAMP(j, 1);
             const bool dump = p.dbg != nullptr && blockIdx.x == 0 && g == 0 && j == 0;
             float inv_scale = 1.f;                                       // 2^-e of the row's current A operand
