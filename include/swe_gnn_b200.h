@@ -176,6 +176,13 @@ int swe_edge_gate_tc16_fwd(const float* xs, const float* xd_src, const float* xd
                            const void* image_tf32, int32_t k1, const int32_t* act3, const float* const* slope3,
                            int32_t normalize, float* s_out, float* dbg, int32_t* flag_ws, void* stream);
 
+/* Row linear out[row_lo + r, :] = x[row_lo + r, :] · Wᵀ for r < n_rows (x, out: [*, 64] fp32; no bias, no activation): the
+ * o_0 = x_d W_0ᵀ at the head of every SWEGNN call (models/gnn.py:401-402) as a STREAMING kernel — whole 128-row tiles
+ * enter a 3-deep shared-memory ring by cp.async.bulk, fp16 hi/lo operands with a per-row power-of-two scale, 12
+ * tcgen05.mma per tile (same arithmetic contract as swe_propagate_hop_tc16_fwd's filter: rel 1e-5 of fp32).
+ * w_image: swe_hop_tc16_pack of W [64, 64]. */
+int swe_row_linear_tc16(const float* x, int64_t row_lo, int64_t n_rows, const void* w_image, float* out, void* stream);
+
 /* Decomposed first layer of the edge MLP: W1·[x_s[r]|x_s[c]|x_d[r]|x_d[c]|a] = P_src[r] + P_dst[c] + E·a with
  *   P_src[n] = A·x_s[n] + C·x_d[n]   (role 0),   P_dst[n] = B·x_s[n] + D·x_d[n]   (role 1; xd NULL drops D·x_d),
  * evaluated once per NODE (2·128² MAC) instead of once per edge.  swe_gate_partials_tc writes one table

@@ -268,6 +268,12 @@ def rowmlp_backend() -> str:
     return os.environ.get("MSWE_ROWMLP", "tc")
 
 
+def rowlin_backend() -> str:
+    """'tc16' (default): o_0 = x_d W_0ᵀ by the streaming kernel swe_row_linear_tc16; 'tc': by swe_row_mlp_tc (3xTF32)."""
+    import os
+    return os.environ.get("MSWE_ROWLIN", "tc16")
+
+
 class RowMlpTC:
     """tcgen05 image of a ``make_mlp`` stack for ``swe_row_mlp_tc``.
 
@@ -346,7 +352,24 @@ class RowMlpTC:
         d.out_rows = lib.ptr(out_rows)
         lib.row_mlp_tc(d)
 
+    def image16(self):
+        """kind='linear': the fp16 hi/lo image of the single layer for the streaming kernel (swe_row_linear_tc16)."""
+        w = self.linears[0].weight
+        stamp = (w.data_ptr(), w._version)
+        if stamp != getattr(self, "_stamp16", None):
+            if getattr(self, "_img16", None) is None or self._img16.device != w.device:
+                self._img16 = torch.empty(lib.hop_tc16_image_bytes(), dtype=torch.uint8, device=w.device)
+            with torch.no_grad():
+                wd = w.detach().contiguous()
+                lib.hop_tc16_pack(wd, float(wd.abs().max()), self._img16)
+            self._stamp16 = stamp
+        return self._img16
+
     def linear(self, x_rows, row_lo, n_rows, out_rows):
+        if (self.kind == "linear" and self.linears[0].bias is None and self.acts[0] is None and rowlin_backend() == "tc16"
+                and x_rows.shape[1] == 64 and out_rows.shape[1] == 64):
+            lib.row_linear_tc16(x_rows, row_lo, n_rows, self.image16(), out_rows)
+            return
         d = lib.SweRowMlp()
         d.x_rows, d.act_in = lib.ptr(x_rows), 0
         d.row_lo, d.n_rows = row_lo, n_rows

@@ -83,6 +83,7 @@ SIGNATURES = {
     "swe_gate_tc16_pack": (C.c_int, [_p, _i32, _p, _p, _p, _p, _p, C.POINTER(C.c_float), _p, _p]),
     "swe_edge_gate_tc16_fwd": (C.c_int, [_p, _p, _p, _p, _p, _p, _i64, _p, _p, _i32, C.POINTER(C.c_int32),
                                          C.POINTER(C.c_void_p), _i32, _p, _p, _p, _p]),
+    "swe_row_linear_tc16": (C.c_int, [_p, _i64, _i64, _p, _p, _p]),
     "swe_gate_partials_tc": (C.c_int, [_p, _p, _i32, _i32, _p, _i32, _i32, _p, _p]),
     "swe_edge_gate_tc_dec_fwd": (C.c_int, [_p, _p, _p, _p, _p, _i64, _p, _i32, C.POINTER(C.c_int32), C.POINTER(C.c_void_p),
                                            _i32, _p, _p]),
@@ -299,6 +300,12 @@ def edge_gate_tc16_fwd(xs, xd_src, xd_dst, a, src, dst, n_edges, image16, image_
                                          None if image_tf32 is None else image_tf32.data_ptr(), k1, act3, slope3,
                                          int(normalize), ptr(s_out), ptr(dbg), ptr(flag_ws, torch.int32), _stream()),
            "swe_edge_gate_tc16_fwd")
+
+
+def row_linear_tc16(x, row_lo, n_rows, w_image, out):
+    """out[row_lo + r] = x[row_lo + r] · Wᵀ (swe_row_linear_tc16; w_image: hop_tc16_pack of W)."""
+    _check(load().swe_row_linear_tc16(ptr(x), int(row_lo), int(n_rows), w_image.data_ptr(), ptr(out), _stream()),
+           "swe_row_linear_tc16")
 
 
 def edge_gate_tc_fwd_listed(xs, xd_src, xd_dst, a, src, dst, n_edges, image, k1, acts, slopes, normalize, s_out, tile_list):

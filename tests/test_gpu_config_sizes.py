@@ -165,11 +165,14 @@ def test_row_mlp_tc_encoder_stage_vs_fp64(n_rows):
     assert e < 1e-5, e
 
 
-@pytest.mark.parametrize("n_rows", [1, 128, 129, 40000])
-def test_row_mlp_tc_linear_stage_vs_fp64(n_rows):
-    """o_0 = x_d W_0^T (models/gnn.py:401-402) on tcgen05 (3xTF32) against fp64: rel-L2 <= 1e-5."""
+@pytest.mark.parametrize("backend", ["tc16", "tc"])
+@pytest.mark.parametrize("n_rows", [1, 128, 129, 40000, 148 * 128 * 3 + 5])
+def test_row_mlp_tc_linear_stage_vs_fp64(n_rows, backend, monkeypatch):
+    """o_0 = x_d W_0^T (models/gnn.py:401-402) on tcgen05 against fp64: rel-L2 <= 1e-5.  'tc16': the streaming kernel
+    swe_row_linear_tc16 (fp16 hi/lo, per-row scale, cp.async.bulk ring); 'tc': swe_row_mlp_tc (3xTF32)."""
     import torch.nn as nn
     from mswe_gnn_b200.engine import RowMlpTC
+    monkeypatch.setenv("MSWE_ROWLIN", backend)
     torch.manual_seed(6)
     lin = nn.Linear(64, 64, bias=False).to(DEV)
     rm = RowMlpTC([lin], [None], "linear")
@@ -178,4 +181,28 @@ def test_row_mlp_tc_linear_stage_vs_fp64(n_rows):
     rm.linear(x, 3, n_rows, out)
     ref = x[3:3 + n_rows].double().cpu() @ lin.weight.detach().double().cpu().T
     assert rel_l2(out[3:3 + n_rows].cpu(), ref) < 1e-5
+    assert float((out[3:3 + n_rows].cpu().double() - ref).abs().max()) < 2e-5 * float(ref.abs().max())
     assert bool(torch.isnan(out[:3]).all()) and bool(torch.isnan(out[3 + n_rows:]).all())      # guard rows untouched
+
+
+def test_row_linear_tc16_rows_of_any_magnitude_and_determinism():
+    """Per-row power-of-two scaling: rows of 1e-20 .. 1e20 and all-zero rows keep the 1e-5 bound row by row; two runs
+    give the same bits."""
+    import torch.nn as nn
+    from mswe_gnn_b200.engine import RowMlpTC
+    torch.manual_seed(7)
+    lin = nn.Linear(64, 64, bias=False).to(DEV)
+    rm = RowMlpTC([lin], [None], "linear")
+    n = 5000
+    x = torch.randn(n, 64, device=DEV) * torch.logspace(-20, 20, n, device=DEV)[:, None]
+    x[::7] = 0.0
+    out = torch.empty(n, 64, device=DEV)
+    rm.linear(x, 0, n, out)
+    ref = x.double().cpu() @ lin.weight.detach().double().cpu().T
+    err = (out.cpu().double() - ref).norm(dim=1)
+    den = ref.norm(dim=1)
+    assert bool((err <= 1e-5 * den + 1e-300).all()), float((err / den.clamp_min(1e-300)).max())
+    assert bool((out[::7] == 0).all())
+    out2 = torch.empty_like(out)
+    rm.linear(x, 0, n, out2)
+    assert torch.equal(out, out2)

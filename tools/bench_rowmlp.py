@@ -57,7 +57,10 @@ for be in ("tc", "ffma"):
     if be == "tc":
         print(be, "  static only: %.3f ms" % t(lambda: m._tc_static.encode(x, 0, 2, True, (1, 6), None, 0, N, xs)))
         print(be, "  dynamic only: %.3f ms" % t(lambda: m._tc_dynamic.encode(x, 2, 6, False, (0, 0), None, 0, N, xd)))
-        print(be, "W0: %.3f ms" % t(lambda: la.w0_tc.linear(h, 0, N, xs)))
+        os.environ["MSWE_ROWLIN"] = "tc"
+        print(be, "W0 (swe_row_mlp_tc, 3xTF32): %.3f ms" % t(lambda: la.w0_tc.linear(h, 0, N, xs)))
+        os.environ["MSWE_ROWLIN"] = "tc16"
+        print(be, "W0 (swe_row_linear_tc16, streaming): %.3f ms" % t(lambda: la.w0_tc.linear(h, 0, N, xs)))
     else:
         print(be, "W0: %.3f ms" % t(lambda: lib.node_linear_fwd(h, 0, N, la.filters.tensors()[0], xs, 64)))
     print(be, "decode head: %.3f ms" % t(lambda: m._decode(h, "tanh", m.gnn_activation, x, plan, pred, None, 0, xn)))
