@@ -241,6 +241,15 @@ typedef struct swe_rowmlp {
 } swe_rowmlp_t;
 int swe_row_mlp_tc(const swe_rowmlp_t* desc, void* stream);
 
+/* The two-layer shapes of swe_row_mlp_tc (node encoders: raw rows of 8 floats -> 64 -> 64 -> 64; decoder: rows -> 64 -> 64 ->
+ * head) as a STREAMING kernel with fp16 hi/lo operands (per-row power-of-two scale, 12 MMAs per layer, layer-1 operand
+ * in TMEM, inputs through a shared-memory ring filled by asynchronous copies several tiles ahead).  Same descriptor;
+ * img16[0], img16[1] = swe_hop_tc16_pack images of the two [64, 64] matrices (desc->img is not read).  Returns
+ * SWE_E_UNSUPP for shapes it does not cover (n_tc != 2, activations outside none / relu / leakyrelu / prelu in the
+ * layers or the head — tanh is accepted as the decoder's input activation —, raw rows that are not 8 aligned floats);
+ * the caller then uses swe_row_mlp_tc. */
+int swe_row_mlp_tc16(const swe_rowmlp_t* desc, const void* const* img16, void* stream);
+
 /* out[dst_lo + i] = x[dst_lo + i] · Wᵀ for i < n_rows.  Replaces models/gnn.py:401-402
  * (filter_matrix[0]).  wt is the packed (k-major) F×F weight. */
 int swe_node_linear_fwd(const float* x, int32_t row_lo, int32_t n_rows, const float* wt, float* out,

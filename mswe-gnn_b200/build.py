@@ -18,7 +18,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB_NAME = "libswe_gnn_b200.so"
 LIB_PATH = os.path.join(CSRC, LIB_NAME)
-SOURCES = ["swe_plan.cu", "swe_forward.cu", "swe_backward.cu", "swe_gate_tc.cu", "swe_gate_tc16.cu", "swe_hop_tc.cu", "swe_hop_tc16.cu", "swe_rowmlp_tc.cu", "swe_rowlin_tc16.cu", "swe_train_tc.cu", "swe_halo.cu", "swe_train_step.cu", "swe_dataset.cu"]
+SOURCES = ["swe_plan.cu", "swe_forward.cu", "swe_backward.cu", "swe_gate_tc.cu", "swe_gate_tc16.cu", "swe_hop_tc.cu", "swe_hop_tc16.cu", "swe_rowmlp_tc.cu", "swe_rowlin_tc16.cu", "swe_rowmlp_tc16.cu", "swe_train_tc.cu", "swe_halo.cu", "swe_train_step.cu", "swe_dataset.cu"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
     "-Xcompiler", "-fPIC", "--expt-relaxed-constexpr", "-Xptxas", "-v",

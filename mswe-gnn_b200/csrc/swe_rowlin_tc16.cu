@@ -39,6 +39,7 @@ constexpr size_t SMEM = 1024 + IN_STAGES * IN_TILE + 2 * (size_t)A_SLOT + W_IMAG
 
 struct Params {
     const float* x; float* out;
+    uint32_t zero_mask;                      // 0 at run time, opaque to the compiler (see the ring-slot release)
     long long row_lo, n_rows;
     const unsigned char* w_img;
 };
@@ -108,7 +109,16 @@ __global__ void __launch_bounds__(THREADS, 1) row_linear_tc16_kernel(const __gri
                 const int r = g + 16 * k;
                 x[k] = r < rows ? *reinterpret_cast<const float4*>(src + r * F + q4) : make_float4(0.f, 0.f, 0.f, 0.f);
             }
-            mbar_arrive(&bar->in_empty[s]);                             // the values are in registers
+            // the slot goes back to the loader only when the reads have RETURNED: the arrive's address depends on the values
+            // (an arrive issued right behind the LDS could overtake them; see swe_rowmlp_tc16.cu)
+            {
+                uint32_t dep = 0u, zero;
+#pragma unroll
+                for (int k = 0; k < 8; ++k)
+                    dep |= __float_as_uint(x[k].x) | __float_as_uint(x[k].y) | __float_as_uint(x[k].z) | __float_as_uint(x[k].w);
+                asm volatile("and.b32 %0, %1, %2;" : "=r"(zero) : "r"(dep), "r"(p.zero_mask));
+                asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&bar->in_empty[s]) + zero) : "memory");
+            }
             // per-row power-of-two scale (max |x'| in [2^13, 2^14)); the row's 16 lanes agree on the maximum
             float sc[8];
 #pragma unroll
@@ -227,7 +237,7 @@ extern "C" int swe_row_linear_tc16(const float* x, int64_t row_lo, int64_t n_row
     SWE_REQUIRE(aligned16(x) && aligned16(out) && aligned16(w_image), SWE_E_ALIGN, "row_linear_tc16: unaligned buffer");
     if (n_rows == 0) return 0;
     rowlin::Params p;
-    p.x = x; p.out = out; p.row_lo = row_lo; p.n_rows = n_rows; p.w_img = (const unsigned char*)w_image;
+    p.x = x; p.out = out; p.zero_mask = 0u; p.row_lo = row_lo; p.n_rows = n_rows; p.w_img = (const unsigned char*)w_image;
     cudaError_t e = cudaFuncSetAttribute(rowlin::row_linear_tc16_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rowlin::SMEM);
     if (e != cudaSuccess) { set_error("row_linear_tc16 smem opt-in (%zu B): %s", rowlin::SMEM, cudaGetErrorString(e)); return (int)e; }
     const long long n_tiles = (n_rows + rowlin::TILE - 1) / rowlin::TILE;

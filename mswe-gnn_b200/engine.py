@@ -268,6 +268,13 @@ def rowmlp_backend() -> str:
     return os.environ.get("MSWE_ROWMLP", "tc")
 
 
+def rowmlp16_backend() -> str:
+    """Which two-layer row MLPs run on the fp16 streaming kernel swe_row_mlp_tc16: '1' all, 'enc' the encoders only
+    (default: the decoder's head is faster on the 16 row warps of swe_row_mlp_tc), 'dec' the decoder only, '0' none."""
+    import os
+    return os.environ.get("MSWE_ROWMLP16", "enc")
+
+
 def rowlin_backend() -> str:
     """'tc16' (default): o_0 = x_d W_0ᵀ by the streaming kernel swe_row_linear_tc16; 'tc': by swe_row_mlp_tc (3xTF32)."""
     import os
@@ -350,6 +357,29 @@ class RowMlpTC:
         d.row_lo, d.n_rows = row_lo, n_rows
         self._fill_tc(d, [1, 2])
         d.out_rows = lib.ptr(out_rows)
+        self._launch(d)
+
+    def images16(self):
+        """fp16 hi/lo images (swe_hop_tc16_pack) of the tensor-core layers for the streaming kernel swe_row_mlp_tc16."""
+        tl = self.tc_layers()
+        stamp = tuple((l.weight.data_ptr(), l.weight._version) for l in tl)
+        if stamp != getattr(self, "_stamp16s", None):
+            dev = tl[0].weight.device
+            if getattr(self, "_img16s", None) is None or self._img16s.device != dev:
+                self._img16s = torch.empty(len(tl), lib.hop_tc16_image_bytes(), dtype=torch.uint8, device=dev)
+            with torch.no_grad():
+                for i, l in enumerate(tl):
+                    wd = l.weight.detach().contiguous()
+                    lib.hop_tc16_pack(wd, float(wd.abs().max()), self._img16s[i])
+            self._stamp16s = stamp
+        return [self._img16s[i] for i in range(len(tl))]
+
+    def _launch(self, d):
+        """Two-layer stacks go to the fp16 streaming kernel where it covers the shape (MSWE_ROWMLP16=0: never)."""
+        mode = rowmlp16_backend()
+        if d.n_tc == 2 and (mode == "1" or (mode == "enc" and not d.head) or (mode == "dec" and d.head)) \
+                and lib.row_mlp_tc16(d, self.images16()):
+            return
         lib.row_mlp_tc(d)
 
     def image16(self):
@@ -399,7 +429,7 @@ class RowMlpTC:
         d.step_ptr = None if step_ptr is None else lib.ptr(step_ptr, torch.int32)
         d.pred_step_stride = pred_stride
         d.x_next = None if x_next is None else lib.ptr(x_next)
-        lib.row_mlp_tc(d)
+        self._launch(d)
 
 
 def hop_backend() -> str:

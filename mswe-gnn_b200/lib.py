@@ -83,6 +83,7 @@ SIGNATURES = {
     "swe_gate_tc16_pack": (C.c_int, [_p, _i32, _p, _p, _p, _p, _p, C.POINTER(C.c_float), _p, _p]),
     "swe_edge_gate_tc16_fwd": (C.c_int, [_p, _p, _p, _p, _p, _p, _i64, _p, _p, _i32, C.POINTER(C.c_int32),
                                          C.POINTER(C.c_void_p), _i32, _p, _p, _p, _p]),
+    "swe_row_mlp_tc16": (C.c_int, [C.POINTER(SweRowMlp), C.POINTER(C.c_void_p), _p]),
     "swe_row_linear_tc16": (C.c_int, [_p, _i64, _i64, _p, _p, _p]),
     "swe_gate_partials_tc": (C.c_int, [_p, _p, _i32, _i32, _p, _i32, _i32, _p, _p]),
     "swe_edge_gate_tc_dec_fwd": (C.c_int, [_p, _p, _p, _p, _p, _i64, _p, _i32, C.POINTER(C.c_int32), C.POINTER(C.c_void_p),
@@ -300,6 +301,16 @@ def edge_gate_tc16_fwd(xs, xd_src, xd_dst, a, src, dst, n_edges, image16, image_
                                          None if image_tf32 is None else image_tf32.data_ptr(), k1, act3, slope3,
                                          int(normalize), ptr(s_out), ptr(dbg), ptr(flag_ws, torch.int32), _stream()),
            "swe_edge_gate_tc16_fwd")
+
+
+def row_mlp_tc16(desc, imgs16) -> bool:
+    """swe_row_mlp_tc16; False when the shape is not covered by the fp16 streaming kernel (caller falls back)."""
+    arr = (C.c_void_p * 2)(*[t.data_ptr() for t in imgs16])
+    rc = load().swe_row_mlp_tc16(C.byref(desc), arr, _stream())
+    if rc == -3:                                           # SWE_E_UNSUPP
+        return False
+    _check(rc, "swe_row_mlp_tc16")
+    return True
 
 
 def row_linear_tc16(x, row_lo, n_rows, w_image, out):

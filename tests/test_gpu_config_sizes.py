@@ -141,12 +141,14 @@ def _prelu64(x, a):
     return torch.where(x > 0, x, a * x)
 
 
+@pytest.mark.parametrize("kernel16", ["1", "0"])
 @pytest.mark.parametrize("n_rows", [1, 127, 128, 129, 40000])
-def test_row_mlp_tc_encoder_stage_vs_fp64(n_rows):
+def test_row_mlp_tc_encoder_stage_vs_fp64(n_rows, kernel16, monkeypatch):
     """Encoder stack (Linear(8 -> 64) + PReLU on CUDA cores, two 64 -> 64 tcgen05 layers + PReLU; reference
     models/models.py:121-146, gnn.py:284-294) against fp64 from the same fp32 inputs: rel-L2 <= 1e-5 per stack."""
     import torch.nn as nn
     from mswe_gnn_b200.engine import RowMlpTC
+    monkeypatch.setenv("MSWE_ROWMLP16", kernel16)        # "1": fp16 streaming kernel (swe_row_mlp_tc16), "0": swe_row_mlp_tc
     torch.manual_seed(5)
     seq = nn.Sequential(nn.Linear(8, 64), nn.PReLU(), nn.Linear(64, 64), nn.PReLU(), nn.Linear(64, 64), nn.PReLU()).to(DEV)
     with torch.no_grad():

@@ -1,5 +1,6 @@
-"""tcgen05 row-MLP kernel (encoders, filter_matrix[0], decoder head; F = 64) against the exact-fp32 CUDA-core
-kernels on identical inputs.  The 64->64 layers are 3xTF32 (fp32 accumulation): per layer ~1e-6 relative."""
+"""tcgen05 row-MLP kernels (encoders, filter_matrix[0], decoder head; F = 64) against the exact-fp32 CUDA-core
+kernels on identical inputs.  The 64->64 layers are 3xTF32 (swe_row_mlp_tc) or fp16 hi/lo with per-row scaling
+(swe_row_mlp_tc16, swe_row_linear_tc16), fp32 accumulation: per layer ~1e-6 relative."""
 import os
 
 import pytest
@@ -27,8 +28,10 @@ def _with_backend(name, fn):
             os.environ["MSWE_ROWMLP"] = old
 
 
+@pytest.mark.parametrize("rm16", ["enc", "1", "0"])                # which two-layer stacks run on swe_row_mlp_tc16 (engine.rowmlp16_backend)
 @pytest.mark.parametrize("nx,ny", [(16, 8), (320, 320)])          # the second: ~21 tiles per CTA in every pipeline
-def test_msgnn_forward_tc_row_mlps_match_ffma(nx, ny):
+def test_msgnn_forward_tc_row_mlps_match_ffma(nx, ny, rm16, monkeypatch):
+    monkeypatch.setenv("MSWE_ROWMLP16", rm16)
     ctor = dict(num_node_features=8, num_edge_features=1, num_scales=4, previous_t=3, **REF_CONFIG_MODELS)
     m = MSGNN(**ctor).to(DEV)
     d = make_tri_mesh(nx, ny, 4, seed=3).to(DEV)
