@@ -44,7 +44,7 @@ struct __align__(8) Bar {
     uint64_t st_full, st_empty;
 };
 
-constexpr size_t SMEM = 1024 + 2 * (size_t)A_SLOT + 2 * W_IMAGE + IN_BYTES + STAGE_BYTES + 4 * TILE * 4 +
+constexpr size_t SMEM = 1024 + 2 * (size_t)A_SLOT + 2 * W_IMAGE + IN_BYTES + STAGE_BYTES + 6 * TILE * 4 +
                         (8 * 64 + 64 + 128 + 128 + 8) * 4 + sizeof(Bar) + 16;
 
 struct Params {
@@ -93,8 +93,11 @@ __global__ void __launch_bounds__(THREADS, 1) row_mlp_tc16_kernel(const __grid_c
     unsigned char* w_tile = a_slots + 2 * (size_t)A_SLOT;                 // layer l at + l * 16 KB
     unsigned char* in_ring = w_tile + 2 * W_IMAGE;
     float* stage = reinterpret_cast<float*>(in_ring + IN_BYTES);          // [128][68]
-    float* s_inv0 = stage + TILE * STAGE_LD;                              // [2][128] descale of D0 rows
-    float* s_inv1 = s_inv0 + 2 * TILE;                                    // [2][128] descale of D1 rows
+    // [4][128] descale of D0 rows, indexed by tile & 3: without the stage hand-over (HEAD) nothing keeps the converters from
+    // running two tiles ahead of the epilogue that reads it; slot i & 3 is rewritten for tile i + 4, whose operand store
+    // waits for the MMAs of tile i + 2, which were issued after the epilogue of tile i released its accumulator
+    float* s_inv0 = stage + TILE * STAGE_LD;
+    float* s_inv1 = s_inv0 + 4 * TILE;                                    // [2][128] descale of D1 rows (epilogue-private)
     float* s_wf = s_inv1 + 2 * TILE;                                      // [8][64] first-layer weights by absolute raw column
     float* s_bf = s_wf + 8 * 64;                                          // [64]
     float* s_bias = s_bf + 64;                                            // [2][64]
@@ -168,7 +171,7 @@ __global__ void __launch_bounds__(THREADS, 1) row_mlp_tc16_kernel(const __grid_c
         const int chunk = q >> 3, piece = q & 7;
         const uint32_t a_sub = ((uint32_t)(q & 1)) * 8u;
         const float w_descale0 = *reinterpret_cast<const float*>(p.img[0] + W_IMAGE);
-        const Leaky a_f = leaky_of(p.act_first, p.slope_first), a_in = leaky_of(p.act_in, nullptr), a_h = leaky_of(p.act_head, p.slope_head);
+        const Leaky a_f = leaky_of(p.act_first, p.slope_first), a_in = leaky_of(p.act_in, nullptr);
         float4 wf[8];                                                   // this lane's 4 output columns of the first layer
         float bf[4] = {0.f, 0.f, 0.f, 0.f};
         if (RAW_IN) {
@@ -177,77 +180,15 @@ __global__ void __launch_bounds__(THREADS, 1) row_mlp_tc16_kernel(const __grid_c
 #pragma unroll
             for (int c = 0; c < 4; ++c) bf[c] = s_bf[q4 + c];
         }
-        // head constants of this lane (swe_rowmlp_tc.cu)
-        const int n_static_raw = p.n_cols - 2 * p.previous_t;
-        float4 wh0 = make_float4(0.f, 0.f, 0.f, 0.f), wh1 = wh0;
-        float res_w0 = 0.f, res_w1 = 0.f, bh0 = 0.f, bh1 = 0.f;
-        if (HEAD) {
-            wh0 = *reinterpret_cast<const float4*>(s_wh + q4); wh1 = *reinterpret_cast<const float4*>(s_wh + 64 + q4);
-            const int rel = q - n_static_raw;
-            if (rel >= 0 && q < p.n_cols && p.res_mode != 0) {
-                const int t = rel >> 1, jv = rel & 1;
-                const float w = p.res_mode == 1 ? __ldg(p.res_w + t) : p.res_mode == 2 ? __ldg(p.res_w + 2 * t + jv)
-                                : (t == p.previous_t - 1 ? 1.f : 0.f);
-                if (jv) res_w1 = w; else res_w0 = w;
-            }
-            if (p.b_head) { bh0 = __ldg(p.b_head); bh1 = __ldg(p.b_head + 1); }
-        }
-        auto write_out = [&](int j) {
+        auto write_out = [&](int j) {                                   // ROW output only (the head runs in the epilogue warps)
             const long long r0 = tile_row0(j);
-            if (!HEAD) {
+            {
                 mbar_wait(&bar->st_full, (uint32_t)j & 1);
 #pragma unroll
                 for (int k = 0; k < 8; ++k) {
                     const int r = g + 16 * k;
                     const float4 d = *reinterpret_cast<const float4*>(stage + r * STAGE_LD + q4);
                     if (r0 + r < p.n_rows) stg4(p.out_rows + (p.row_lo + r0 + r) * F + q4, d);
-                }
-            } else {
-                // decoder head: lane c (< n_cols <= 16) of a row's 16 lanes owns input column c of that row
-                float* pred_step = q < 2 ? p.pred + (p.step_ptr ? (long long)(*p.step_ptr) * p.pred_step_stride : 0) : nullptr;
-#pragma unroll 1
-                for (int kh = 0; kh < 8; kh += 4) {
-                    float xr[4];
-                    long long orow[4];
-#pragma unroll
-                    for (int k = 0; k < 4; ++k) {
-                        const long long row = r0 + g + 16 * (kh + k);
-                        xr[k] = 0.f; orow[k] = 0;
-                        if (row < p.n_rows) {
-                            const long long node = p.row_lo + row;
-                            orow[k] = p.head_perm ? p.head_perm[node] : node;
-                            if (q < p.n_cols) xr[k] = p.x0[orow[k] * p.n_cols + q];
-                        }
-                    }
-                    if (kh == 0) mbar_wait(&bar->st_full, (uint32_t)j & 1);
-#pragma unroll
-                    for (int k = 0; k < 4; ++k) {
-                        const int r = g + 16 * (kh + k);
-                        const long long row = r0 + r;
-                        const float4 d = *reinterpret_cast<const float4*>(stage + r * STAGE_LD + q4);
-                        float y0 = d.x * wh0.x + d.y * wh0.y + d.z * wh0.z + d.w * wh0.w;
-                        float y1 = d.x * wh1.x + d.y * wh1.y + d.z * wh1.z + d.w * wh1.w;
-                        float c0 = xr[k] * res_w0, c1 = xr[k] * res_w1;       // residual (models/models.py:50-77)
-#pragma unroll
-                        for (int off = 8; off >= 1; off >>= 1) {
-                            y0 += __shfl_xor_sync(0xffffffffu, y0, off);
-                            y1 += __shfl_xor_sync(0xffffffffu, y1, off);
-                            c0 += __shfl_xor_sync(0xffffffffu, c0, off);
-                            c1 += __shfl_xor_sync(0xffffffffu, c1, off);
-                        }
-                        const float shifted = __shfl_down_sync(0xffffffffu, xr[k], 2, 16);   // column c + 2 of the same row
-                        y0 = fmaxf(leaky_do(a_h, y0 + bh0) + c0, 0.f);
-                        y1 = fmaxf(leaky_do(a_h, y1 + bh1) + c1, 0.f);
-                        const float oh = (fabsf(y0) > p.eps) ? y0 : 0.f;                    // h · [|h| > eps]
-                        const float oq = (y0 != 0.f) ? y1 : 0.f;                             // q · [h != 0] (un-thresholded h)
-                        if (row < p.n_rows) {
-                            if (q < 2) pred_step[orow[k] * 2 + q] = q ? oq : oh;
-                            if (p.x_next && q < p.n_cols) {
-                                const float v = q < n_static_raw ? xr[k] : (q < p.n_cols - 2 ? shifted : (q == p.n_cols - 2 ? oh : oq));
-                                p.x_next[orow[k] * p.n_cols + q] = v;
-                            }
-                        }
-                    }
                 }
             }
             mbar_arrive(&bar->st_empty);
@@ -314,9 +255,13 @@ __global__ void __launch_bounds__(THREADS, 1) row_mlp_tc16_kernel(const __grid_c
                 uint32_t sb = 267u - (__float_as_uint(m) >> 23);
                 sb = sb > 253u ? 253u : sb;
                 sc[k] = __uint_as_float(sb << 23);
-                if (q == 0) s_inv0[slot * TILE + g + 16 * k] = __uint_as_float((254u - sb) << 23) * w_descale0;
             }
             mbar_wait(&bar->a_empty[slot], (((uint32_t)i >> 1) & 1) ^ 1);
+            if (q == 0) {
+#pragma unroll
+                for (int k = 0; k < 8; ++k)                              // 2^-e = 1 / sc exactly: exponent 254 - biased exponent of sc
+                    s_inv0[(i & 3) * TILE + g + 16 * k] = __uint_as_float((254u << 23) - __float_as_uint(sc[k])) * w_descale0;
+            }
             unsigned char* base = a_slots + (size_t)slot * A_SLOT + (size_t)chunk * 2 * A_TILE;
 #pragma unroll
             for (int k = 0; k < 8; ++k) {
@@ -329,10 +274,10 @@ __global__ void __launch_bounds__(THREADS, 1) row_mlp_tc16_kernel(const __grid_c
             }
             fence_proxy_async_smem();
             mbar_arrive(&bar->a_full[slot]);
-            if (i >= 2) write_out(i - 2);
+            if (!HEAD && i >= 2) write_out(i - 2);
         }
-        if (n_my >= 2) write_out(n_my - 2);
-        if (n_my >= 1) write_out(n_my - 1);
+        if (!HEAD && n_my >= 2) write_out(n_my - 2);
+        if (!HEAD && n_my >= 1) write_out(n_my - 1);
     } else if (warp < CONV_WARPS + EPI_WARPS) {
         // =====================================================================================
         // epilogue warps (thread = TMEM lane = row):  E0(0) ; for i: { E0(i + 1) ; E1(i) }
@@ -343,12 +288,16 @@ __global__ void __launch_bounds__(THREADS, 1) row_mlp_tc16_kernel(const __grid_c
         const float w_descale1 = *reinterpret_cast<const float*>(p.img[1] + W_IMAGE);
         const float bias0_max = s_misc[0];
         float* my_row = stage + row * STAGE_LD;
+        const Leaky a_h = leaky_of(p.act_head, p.slope_head);
+        const int n_static_raw = p.n_cols - 2 * p.previous_t;
+        float bh0 = 0.f, bh1 = 0.f;
+        if (HEAD && p.b_head) { bh0 = __ldg(p.b_head); bh1 = __ldg(p.b_head + 1); }
         // X1 = act_0(D0 descaled + b_0) -> row scale -> fp16 hi/lo -> TMEM operand of layer 1
         auto e0 = [&](int i) {
             const uint32_t b = (uint32_t)i & 1, bph = ((uint32_t)i >> 1) & 1;
             mbar_wait(&bar->d0_full[b], bph);
             tc_fence_after_sync();
-            const float dsc = s_inv0[b * TILE + row];
+            const float dsc = s_inv0[(i & 3) * TILE + row];
             // pass 1: an upper bound of the row's largest |activation| (|act(v)| <= max(1, |slope|) (|D| dsc + max |b|))
             float m = 0.f;
 #pragma unroll 1
@@ -389,28 +338,94 @@ __global__ void __launch_bounds__(THREADS, 1) row_mlp_tc16_kernel(const __grid_c
             if (i + 1 < n_my) e0(i + 1);
             if (i < 0) continue;
             const uint32_t b = (uint32_t)i & 1, bph = ((uint32_t)i >> 1) & 1;
+            // head: this row's inputs (original row number through the permutation, then its n_cols <= 16 input columns) are
+            // requested before the wait for the accumulator
+            float hx[16];
+            long long horow = 0;
+            if (HEAD) {
+#pragma unroll
+                for (int c = 0; c < 16; ++c) hx[c] = 0.f;
+                const long long grow = tile_row0(i) + row;
+                if (grow < p.n_rows) {
+                    const long long node = p.row_lo + grow;
+                    horow = p.head_perm ? p.head_perm[node] : node;
+                    const float* xr = p.x0 + horow * p.n_cols;
+#pragma unroll
+                    for (int c = 0; c < 16; ++c) if (c < p.n_cols) hx[c] = __ldg(xr + c);
+                }
+            }
             mbar_wait(&bar->d1_full[b], bph);
             tc_fence_after_sync();
             const float dsc = s_inv1[b * TILE + row];
-            mbar_wait(&bar->st_empty, ((uint32_t)i & 1) ^ 1);           // stage written out (tile i - 1)
+            if (!HEAD) {
+                mbar_wait(&bar->st_empty, ((uint32_t)i & 1) ^ 1);       // stage written out (tile i - 1)
 #pragma unroll 1
-            for (int hf = 0; hf < 2; ++hf) {
-                uint32_t v[32];
-                tmem_ld32(lane_addr + C_D1 + b * 64 + hf * 32, v);
-                tmem_wait_ld();
+                for (int hf = 0; hf < 2; ++hf) {
+                    uint32_t v[32];
+                    tmem_ld32(lane_addr + C_D1 + b * 64 + hf * 32, v);
+                    tmem_wait_ld();
 #pragma unroll
-                for (int j = 0; j < 32; j += 4) {
-                    float4 r;
-                    r.x = leaky_do(a1, fmaf(__uint_as_float(v[j]), dsc, s_bias[64 + hf * 32 + j]));
-                    r.y = leaky_do(a1, fmaf(__uint_as_float(v[j + 1]), dsc, s_bias[64 + hf * 32 + j + 1]));
-                    r.z = leaky_do(a1, fmaf(__uint_as_float(v[j + 2]), dsc, s_bias[64 + hf * 32 + j + 2]));
-                    r.w = leaky_do(a1, fmaf(__uint_as_float(v[j + 3]), dsc, s_bias[64 + hf * 32 + j + 3]));
-                    *reinterpret_cast<float4*>(my_row + hf * 32 + j) = r;
+                    for (int j = 0; j < 32; j += 4) {
+                        float4 r;
+                        r.x = leaky_do(a1, fmaf(__uint_as_float(v[j]), dsc, s_bias[64 + hf * 32 + j]));
+                        r.y = leaky_do(a1, fmaf(__uint_as_float(v[j + 1]), dsc, s_bias[64 + hf * 32 + j + 1]));
+                        r.z = leaky_do(a1, fmaf(__uint_as_float(v[j + 2]), dsc, s_bias[64 + hf * 32 + j + 2]));
+                        r.w = leaky_do(a1, fmaf(__uint_as_float(v[j + 3]), dsc, s_bias[64 + hf * 32 + j + 3]));
+                        *reinterpret_cast<float4*>(my_row + hf * 32 + j) = r;
+                    }
+                }
+            } else {
+                // decoder head in the thread that owns the row: 64 -> 2 dot products straight from the accumulator, residual,
+                // ReLU, dry mask, prediction and shifted window (models/gnn.py:339-348, models/models.py:50-91,
+                // utils/dataset.py:508-529) — no stage, no hand-over
+                float y0 = 0.f, y1 = 0.f;
+#pragma unroll 1
+                for (int hf = 0; hf < 2; ++hf) {
+                    uint32_t v[32];
+                    tmem_ld32(lane_addr + C_D1 + b * 64 + hf * 32, v);
+                    tmem_wait_ld();
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) {
+                        const float t = leaky_do(a1, fmaf(__uint_as_float(v[j]), dsc, s_bias[64 + hf * 32 + j]));
+                        y0 = fmaf(t, s_wh[hf * 32 + j], y0);
+                        y1 = fmaf(t, s_wh[64 + hf * 32 + j], y1);
+                    }
+                }
+                const long long grow = tile_row0(i) + row;
+                if (grow < p.n_rows) {
+                    float c0 = 0.f, c1 = 0.f;
+                    if (p.res_mode != 0) {
+                        // column c of the inputs contributes to variable (c - n_static) & 1 of time step (c - n_static) >> 1
+                        // (static register indices: a runtime index would put hx in local memory)
+#pragma unroll
+                        for (int c = 0; c < 16; ++c) {
+                            const int rel = c - n_static_raw;
+                            if (rel >= 0 && c < p.n_cols) {
+                                const int t = rel >> 1, jv = rel & 1;
+                                const float w = p.res_mode == 1 ? __ldg(p.res_w + t) : p.res_mode == 2 ? __ldg(p.res_w + 2 * t + jv)
+                                                : (t == p.previous_t - 1 ? 1.f : 0.f);
+                                if (jv) c1 = fmaf(hx[c], w, c1); else c0 = fmaf(hx[c], w, c0);
+                            }
+                        }
+                    }
+                    y0 = fmaxf(leaky_do(a_h, y0 + bh0) + c0, 0.f);
+                    y1 = fmaxf(leaky_do(a_h, y1 + bh1) + c1, 0.f);
+                    const float oh = (fabsf(y0) > p.eps) ? y0 : 0.f;     // h · [|h| > eps]
+                    const float oq = (y0 != 0.f) ? y1 : 0.f;              // q · [h != 0] (un-thresholded h)
+                    float* pr = p.pred + (p.step_ptr ? (long long)(*p.step_ptr) * p.pred_step_stride : 0) + horow * 2;
+                    *reinterpret_cast<float2*>(pr) = make_float2(oh, oq);
+                    if (p.x_next) {
+                        float* xn = p.x_next + horow * p.n_cols;
+#pragma unroll
+                        for (int c = 0; c < 16; ++c)
+                            if (c < p.n_cols)
+                                xn[c] = c < n_static_raw ? hx[c] : (c < p.n_cols - 2 ? hx[c + 2 < 16 ? c + 2 : 15] : (c == p.n_cols - 2 ? oh : oq));
+                    }
                 }
             }
             tc_fence_before_sync();
             mbar_arrive(&bar->d1_free[b]);
-            mbar_arrive(&bar->st_full);
+            if (!HEAD) mbar_arrive(&bar->st_full);
         }
     } else if (warp == CONV_WARPS + EPI_WARPS) {
         // =====================================================================================

@@ -269,10 +269,10 @@ def rowmlp_backend() -> str:
 
 
 def rowmlp16_backend() -> str:
-    """Which two-layer row MLPs run on the fp16 streaming kernel swe_row_mlp_tc16: '1' all, 'enc' the encoders only
-    (default: the decoder's head is faster on the 16 row warps of swe_row_mlp_tc), 'dec' the decoder only, '0' none."""
+    """Which two-layer row MLPs run on the fp16 streaming kernel swe_row_mlp_tc16: '1' all (default), 'enc' the encoders
+    only, 'dec' the decoder only, '0' none (swe_row_mlp_tc)."""
     import os
-    return os.environ.get("MSWE_ROWMLP16", "enc")
+    return os.environ.get("MSWE_ROWMLP16", "1")
 
 
 def rowlin_backend() -> str:

@@ -41,6 +41,9 @@ def test_msgnn_forward_tc_row_mlps_match_ffma(nx, ny, rm16, monkeypatch):
         b = _with_backend("ffma", lambda: m(d))
         m._edge_cache = None                                         # (the encoded edge features are cached per backend run)
         a2 = _with_backend("tc", lambda: m(d))
+        for _ in range(4 if nx >= 320 else 1):                       # the pipelines are timing-sensitive: several repeats
+            m._edge_cache = None
+            assert torch.equal(a, _with_backend("tc", lambda: m(d)))
     assert torch.equal(a, a2)                                        # deterministic
     assert rel_l2(a, b) < 2e-5, rel_l2(a, b)
     assert_close_masked(a, b, 2e-4, 2e-5, "tc vs ffma row MLPs")
