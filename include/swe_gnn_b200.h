@@ -217,6 +217,13 @@ int swe_propagate_hop_tc16_fwd(const float* o_src, const float* o_dst, const flo
                                const int32_t* src, int32_t dst_lo, int32_t n_dst, const void* w_image,
                                int32_t with_gradient, int32_t upwind, const float* addend, int32_t act,
                                const float* slope, float* agg_out, float* out, void* stream);
+/* s-ring edition of the fp16 hop (same image, same contract, bit-identical results): every gather warp owns 8 contiguous
+ * nodes of a tile and streams their run of gate rows s_p (CSR order: one contiguous run, 768 of the node's 1280 bytes)
+ * into its own shared-memory buffers with cp.async.bulk one tile ahead; rowptr two tiles and src ids one tile ahead. */
+int swe_propagate_hop_tc16s_fwd(const float* o_src, const float* o_dst, const float* s, const int32_t* rowptr,
+                                const int32_t* src, int32_t dst_lo, int32_t n_dst, const void* w_image,
+                                int32_t with_gradient, int32_t upwind, const float* addend, int32_t act,
+                                const float* slope, float* agg_out, float* out, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
  * Row MLPs on tcgen05 (F = 64): encoders (models/gnn.py:281-294), filter_matrix[0] (gnn.py:401-402) and the decoder

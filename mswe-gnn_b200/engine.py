@@ -617,9 +617,9 @@ class SweGnnLauncher:
             raise NotImplementedError("multi-hop propagation needs source and destination in the same node set")
         bufs = [tmp_b, tmp_a] if o_src is tmp_a else [tmp_a, tmp_b]
         hb = hop_backend()
-        use_tc = m.with_filter_matrix and self.F == 64 and FP == 64 and hb in ("tc", "tc16")
-        Wtc = (self.filters.tc16_images() if hb == "tc16" else self.filters.tc_images()) if use_tc else None
-        hop_tc = lib.propagate_hop_tc16_fwd if hb == "tc16" else lib.propagate_hop_tc_fwd
+        use_tc = m.with_filter_matrix and self.F == 64 and FP == 64 and hb in ("tc", "tc16", "tc16s")
+        Wtc = (self.filters.tc16_images() if hb in ("tc16", "tc16s") else self.filters.tc_images()) if use_tc else None
+        hop_tc = {"tc16": lib.propagate_hop_tc16_fwd, "tc16s": lib.propagate_hop_tc16s_fwd}.get(hb, lib.propagate_hop_tc_fwd)
         for k in range(K):
             last = k == K - 1
             dst_buf = out if last else bufs[k % 2]

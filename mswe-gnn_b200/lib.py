@@ -95,6 +95,7 @@ SIGNATURES = {
     "swe_hop_tc16_image_bytes": (_sz, []),
     "swe_hop_tc16_pack": (C.c_int, [_p, _f32, _p, _p]),
     "swe_propagate_hop_tc16_fwd": (C.c_int, [_p, _p, _p, _p, _p, _i32, _i32, _p, _i32, _i32, _p, _i32, _p, _p, _p, _p]),
+    "swe_propagate_hop_tc16s_fwd": (C.c_int, [_p, _p, _p, _p, _p, _i32, _i32, _p, _i32, _i32, _p, _i32, _p, _p, _p, _p]),
     "swe_node_linear_fwd": (C.c_int, [_p, _i32, _i32, _p, _p, _i32, _p]),
     "swe_propagate_hop_fwd": (C.c_int, [_p, _p, _p, _p, _p, _i32, _i32, _p, _i32, _i32, _p, _i32, _p, _p, _i32, _p]),
     "swe_pool_mean_fwd": (C.c_int, [_p, _p, _p, _i32, _i32, _p, _i32, _p]),
@@ -423,6 +424,15 @@ def propagate_hop_tc16_fwd(o_src, o_dst, s, rowptr, src, dst_lo, n_dst, w_image,
                                              dst_lo, n_dst, w_image.data_ptr(), int(with_gradient), int(upwind), ptr(addend),
                                              act, ptr(slope), ptr(agg_out), ptr(out), _stream()),
            "swe_propagate_hop_tc16_fwd")
+
+
+def propagate_hop_tc16s_fwd(o_src, o_dst, s, rowptr, src, dst_lo, n_dst, w_image, with_gradient, upwind, addend, act,
+                            slope, agg_out, out):
+    """s-ring edition of the fp16 hop (gate rows streamed by cp.async.bulk; same image, bit-identical results)."""
+    _check(load().swe_propagate_hop_tc16s_fwd(ptr(o_src), ptr(o_dst), ptr(s), ptr(rowptr, torch.int32), ptr(src, torch.int32),
+                                              dst_lo, n_dst, w_image.data_ptr(), int(with_gradient), int(upwind), ptr(addend),
+                                              act, ptr(slope), ptr(agg_out), ptr(out), _stream()),
+           "swe_propagate_hop_tc16s_fwd")
 
 
 def pool_mean_fwd(x, rowptr, fine, coarse_lo, n_coarse, out, F):

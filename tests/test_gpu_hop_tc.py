@@ -15,10 +15,10 @@ def _csr(ei, n):
     return lib.csr_build(ei[0].contiguous(), ei[1].contiguous(), None, 0, n, 0, n)
 
 
-BACKEND = ["tc"]          # "tc": 3xTF32 (swe_hop_tc.cu), "tc16": fp16 hi/lo splits (swe_hop_tc16.cu); set by the fixture below
+BACKEND = ["tc"]          # "tc": 3xTF32 (swe_hop_tc.cu), "tc16": fp16 hi/lo splits (swe_hop_tc16.cu), "tc16s": + s-ring; set by the fixture below
 
 
-@pytest.fixture(autouse=True, params=["tc", "tc16"])
+@pytest.fixture(autouse=True, params=["tc", "tc16", "tc16s"])
 def _backend(request):
     BACKEND[0] = request.param
     yield
@@ -32,10 +32,10 @@ def _run_both(o, s, rowptr, src, n, W, with_grad, addend, act, slope, dst_lo=0, 
     out = torch.zeros_like(o)
     agg = torch.zeros_like(o)
     lib.propagate_hop_fwd(o, o, s, rowptr, src, dst_lo, n_dst, wt, with_grad, 0, addend, act, slope, ref, 64)
-    if BACKEND[0] == "tc16":
+    if BACKEND[0] in ("tc16", "tc16s"):
         img = torch.empty(lib.hop_tc16_image_bytes(), dtype=torch.uint8, device=DEV)
         lib.hop_tc16_pack(W.contiguous(), float(W.abs().max()), img)
-        lib.propagate_hop_tc16_fwd(o, o, s, rowptr, src, dst_lo, n_dst, img, with_grad, 0, addend, act, slope, agg, out)
+        (lib.propagate_hop_tc16s_fwd if BACKEND[0] == "tc16s" else lib.propagate_hop_tc16_fwd)(o, o, s, rowptr, src, dst_lo, n_dst, img, with_grad, 0, addend, act, slope, agg, out)
     else:
         img = torch.empty(lib.hop_tc_image_bytes(), dtype=torch.uint8, device=DEV)
         lib.hop_tc_pack(W.contiguous(), img)
@@ -111,3 +111,40 @@ def test_hop_tc_rows_of_any_magnitude(mag):
     err = (out.double() - ref.double()).norm(dim=1) / ref.double().norm(dim=1).clamp_min(1e-300)
     assert bool(torch.isfinite(out).all())
     assert float(err.max()) < 5e-6, float(err.max())           # per ROW, not per tile
+
+
+def test_hop_tc16s_bit_identical_to_tc16():
+    """The s-ring edition changes how the gate rows reach the gather warps (cp.async.bulk into per-warp buffers, src ids
+    and rowptr staged ahead), not the arithmetic or its order: equal bits on a mesh, on hubs that overflow the pass
+    buffers (in-degree > 3 on a pass's four nodes) and the 32-id staging, and on isolated nodes."""
+    if BACKEND[0] != "tc16s":
+        pytest.skip("one run is enough")
+    torch.manual_seed(11)
+    d = make_single_scale_mesh(97, 53, seed=4)
+    n = d.x.shape[0]
+    hubs = torch.tensor([5, 130, 131, 132, 133, 1000, n - 1])
+    hub_edges = torch.stack([torch.randint(0, n, (len(hubs) * 57,)), hubs.repeat_interleave(57)])
+    keep = (d.edge_index[1] % 41) != 7                        # nodes 7, 48, 89, ... lose all their edges
+    ei = torch.cat([d.edge_index[:, keep], hub_edges], 1).to(DEV)
+    e = ei.shape[1]
+    rowptr, src, dst, eid = _csr(ei, n)
+    o = torch.randn(n, 64, device=DEV)
+    s = torch.randn(e, 64, device=DEV) / 4
+    W = torch.randn(64, 64, device=DEV) / 8
+    img = torch.empty(lib.hop_tc16_image_bytes(), dtype=torch.uint8, device=DEV)
+    lib.hop_tc16_pack(W.contiguous(), float(W.abs().max()), img)
+    add = torch.randn(n, 64, device=DEV)
+    slope = torch.tensor([0.25], device=DEV)
+    for with_grad, addend, act in [(1, None, 0), (0, add, 1), (1, add, 3)]:
+        a, b = torch.zeros_like(o), torch.zeros_like(o)
+        agg_a, agg_b = torch.zeros_like(o), torch.zeros_like(o)
+        lib.propagate_hop_tc16_fwd(o, o, s, rowptr, src, 0, n, img, with_grad, 0, addend, act, slope, agg_a, a)
+        lib.propagate_hop_tc16s_fwd(o, o, s, rowptr, src, 0, n, img, with_grad, 0, addend, act, slope, agg_b, b)
+        torch.cuda.synchronize()
+        assert torch.equal(agg_a, agg_b)
+        assert torch.equal(a, b)
+    # repeated launches give the same bits (buffer hand-over races would show here)
+    for _ in range(5):
+        lib.propagate_hop_tc16s_fwd(o, o, s, rowptr, src, 0, n, img, 1, 0, add, 3, slope, agg_b, b)
+    torch.cuda.synchronize()
+    assert torch.equal(a, b)

@@ -22,11 +22,13 @@ def run(which):
         lib.propagate_hop_fwd(o, o, s, rowptr, src, 0, n, None, 1, 0, None, 0, None, out, 64)
     elif which == "ffma":
         lib.propagate_hop_fwd(o, o, s, rowptr, src, 0, n, wt, 1, 0, None, 0, None, out, 64)
+    elif which == "tc16s":
+        lib.propagate_hop_tc16s_fwd(o, o, s, rowptr, src, 0, n, img16, 1, 0, None, 0, None, None, out)
     elif which == "tc16":
         lib.propagate_hop_tc16_fwd(o, o, s, rowptr, src, 0, n, img16, 1, 0, None, 0, None, None, out)
     else:
         lib.propagate_hop_tc_fwd(o, o, s, rowptr, src, 0, n, img, 1, 0, None, 0, None, None, out)
-for which in os.environ.get("WHICH", "nofilter,ffma,tc,tc16").split(","):
+for which in os.environ.get("WHICH", "nofilter,ffma,tc,tc16,tc16s").split(","):
     for _ in range(3): run(which)
     torch.cuda.synchronize()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -53,3 +55,18 @@ if os.environ.get("TRACE"):
     for tile in range(2, 9):
         for r, name in enumerate(["gather", "epilogue", "mma"]):
             print(tile, name, " ".join(f"{ev[r][e]}={int(t[r, tile, e]) - t0}" for e in range(len(ev[r]))))
+
+if os.environ.get("TRACE16S"):
+    import ctypes as C
+    l = lib.load()
+    l.swe_hop_tc16s_set_trace.restype = None
+    l.swe_hop_tc16s_set_trace.argtypes = [C.c_void_p]
+    trace = torch.zeros(16 * 16, dtype=torch.int64, device=DEV)
+    l.swe_hop_tc16s_set_trace(trace.data_ptr())
+    lib.propagate_hop_tc16s_fwd(o, o, s, rowptr, src, 0, n, img16, 1, 0, None, 0, None, None, out)
+    torch.cuda.synchronize()
+    t = trace.cpu().view(16, 16)
+    t0 = int(t[2, 0])
+    names = ["start", "ids", "p0_iss", "p0_full", "p0_acc", "a_empty", "prev_out", "p1_iss", "p1_full", "p1_acc", "end"]
+    for tile in range(2, 10):
+        print(tile, " ".join(f"{names[e]}={int(t[tile, e]) - t0}" for e in range(len(names))))
