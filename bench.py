@@ -707,7 +707,7 @@ def profile_kernels(runner, alg):
     from mswe_gnn_b200 import lib
     records = []
     orig = {}
-    names = ["row_mlp_tc", "row_mlp_tc16", "row_linear_tc16", "node_encode_fwd", "edge_gate_fwd", "edge_gate_tc_fwd", "edge_gate_tc16_fwd", "propagate_hop_tc16_fwd", "edge_gate_tc_dec_fwd", "gate_partials_tc", "edge_gate_tc_stat_fwd",
+    names = ["row_mlp_tc", "row_mlp_tc16", "row_linear_tc16", "node_encode_fwd", "edge_gate_fwd", "edge_gate_tc_fwd", "edge_gate_tc16_fwd", "propagate_hop_tc16_fwd", "propagate_hop_tc16s_fwd", "edge_gate_tc_dec_fwd", "gate_partials_tc", "edge_gate_tc_stat_fwd",
              "gate_static_partials_tc", "node_linear_fwd", "propagate_hop_fwd", "propagate_hop_tc_fwd", "pool_mean_fwd",
              "decode_head_fwd", "edge_encode_fwd", "apply_bc", "step_advance", "halo_exchange", "pack_rows"]
 
@@ -721,7 +721,7 @@ def profile_kernels(runner, alg):
             r = fn(*a, **k)
             e1.record()
             meta = None
-            if name in ("propagate_hop_fwd", "propagate_hop_tc_fwd", "propagate_hop_tc16_fwd"):
+            if name in ("propagate_hop_fwd", "propagate_hop_tc_fwd", "propagate_hop_tc16_fwd", "propagate_hop_tc16s_fwd"):
                 meta = ("hop", int(a[6]), a[7] is not None)          # n_dst, has filter
             elif name in ("edge_gate_fwd", "edge_gate_tc_fwd", "edge_gate_tc16_fwd"):
                 meta = ("gate", int(a[6]), a[3] is not None)         # n_edges, has edge features

@@ -433,11 +433,13 @@ class RowMlpTC:
 
 
 def hop_backend() -> str:
-    """'tc' (tcgen05 filter as 3xTF32, default for F = 64), 'tc16' (fp16 hi/lo splits: half the MMAs and half the operand
-    bytes, but the row-max shuffles and conversions land on the gather warps, which — not the tensor pipe — bound this
-    kernel: 0.414 vs 0.348 ms at cfg3 level 0) or 'ffma' (exact-fp32 CUDA cores)."""
+    """'tc16s' (default for F = 64: fp16 hi/lo filter on tcgen05, gate rows streamed into per-warp shared-memory buffers by
+    cp.async.bulk — 0.301 ms at cfg3 level 0 = 0.67 of the copy peak), 'tc' (3xTF32 filter, per-thread loads: 0.346 ms),
+    'tc16' (fp16 hi/lo filter, per-thread loads: 0.411 ms) or 'ffma' (exact-fp32 CUDA cores).  'tc16s' stages at most 12
+    edges per 4 nodes and 32 per 8; blocks beyond that (hubs) run one edge at a time, so graphs whose in-degrees exceed
+    3 as a rule are better served by 'tc'."""
     import os
-    return os.environ.get("MSWE_HOP", "tc")
+    return os.environ.get("MSWE_HOP", "tc16s")
 
 
 _STATIC_TOKEN = None
