@@ -383,9 +383,16 @@ constexpr size_t HOP_TC16S_SMEM = 1024 + (size_t)HOP_A_SLOT + HOP_W_IMAGE + HOP_
                                   (size_t)HOP_GATHER_WARPS * 2 * SR_BUF + HOP_GATHER_WARPS * sizeof(SrWarp) + sizeof(HopBarriers) + 16;
 static_assert(HOP_GATHER_WARPS * SR_NODES == HOP_TILE, "8 nodes per gather warp");
 
+#ifndef SR_PREFETCH
+#define SR_PREFETCH 1
+#endif
+__device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
+__device__ __forceinline__ void prefetch_l1(const void* p) { asm volatile("prefetch.global.L1 [%0];" ::"l"(p)); }
+
 struct HopTc16sParams {
     HopTcParams h;
     unsigned zero_mask;                        // 0 (a value the compiler cannot fold: see the buffer release)
+    int pf_dist, pf_l1;                        // prefetch distance in tiles (0: off), 1: into L1 instead of L2
 };
 
 __device__ __forceinline__ void bulk_g2s_u32(uint32_t smem_dst, const void* gmem_src, uint32_t bytes, uint64_t* bar) {
@@ -702,6 +709,24 @@ __global__ void __launch_bounds__(HOP_THREADS, 1) hop_tc16s_kernel(const __grid_
             tc_fence_before_sync();
             mbar_arrive(&bar->d_empty[dslot]);
             mbar_arrive(&bar->st_full);
+#if SR_PREFETCH
+            // These warps sleep for most of a tile: they pull the rows tile i+2 will gather (its own o[c] rows and its
+            // sources) into L2 — every pass of the gather warps waited for at least one first-touch row from DRAM
+            if (pp.pf_dist > 0 && i + pp.pf_dist < n_my) {
+                const int row0n = ((int)blockIdx.x + (i + pp.pf_dist) * (int)gridDim.x) * HOP_TILE;
+                const int rowsn = min(HOP_TILE, p.n_dst - row0n);
+                const int tid = lq * 32 + lane;
+                if (p.o_dst && tid < rowsn) {
+                    const float* r = p.o_dst + ((long long)p.dst_lo + row0n + tid) * HF;
+                    if (pp.pf_l1) { prefetch_l1(r); prefetch_l1(r + 32); } else { prefetch_l2(r); prefetch_l2(r + 32); }
+                }
+                const int e0 = __ldg(p.rowptr + row0n), e1 = __ldg(p.rowptr + row0n + rowsn);
+                for (int e = e0 + tid; e < e1; e += HOP_EPI_WARPS * 32) {
+                    const float* r = p.o_src + (long long)__ldg(p.src + e) * HF;
+                    if (pp.pf_l1) { prefetch_l1(r); prefetch_l1(r + 32); } else { prefetch_l2(r); prefetch_l2(r + 32); }
+                }
+            }
+#endif
         }
     }
     tc_fence_before_sync();
@@ -770,6 +795,8 @@ extern "C" int swe_propagate_hop_tc16s_fwd(const float* o_src, const float* o_ds
     p.act = act; p.slope = slope; p.out = out; p.agg_out = agg_out;
     p.trace = g_tc16s_trace; g_tc16s_trace = nullptr;
     pp.zero_mask = 0u;
+    { static int pd = -1, pl = 0; if (pd < 0) { const char* e1 = getenv("MSWE_HOP_PF_DIST"); pd = e1 ? atoi(e1) : 3; const char* e2 = getenv("MSWE_HOP_PF_L1"); pl = e2 ? atoi(e2) : 0; }
+      pp.pf_dist = pd; pp.pf_l1 = pl; }
     void (*kern)(const tch::HopTc16sParams) = with_gradient ? (upwind ? tch::hop_tc16s_kernel<true, true, false> : tch::hop_tc16s_kernel<true, false, false>)
                                                              : tch::hop_tc16s_kernel<false, false, false>;
     if (p.trace && with_gradient && !upwind) kern = tch::hop_tc16s_kernel<true, false, true>;
