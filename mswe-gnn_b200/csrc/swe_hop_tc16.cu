@@ -663,6 +663,32 @@ __global__ void __launch_bounds__(HOP_THREADS, 1) hop_tc16s_kernel(const __grid_
         const uint32_t idesc = make_idesc_f16(HOP_TILE, HF);
         const uint32_t a_u32 = smem_u32(a_slots), w_u32 = smem_u32(w_tile);
         float* my_row = stage + (lq * 32 + lane) * HOP_STAGE_LD;
+        // These warps sleep for most of a tile: they pull the rows a later tile will gather (its own o[c] rows, its sources,
+        // its addend rows) into L2 — every pass of the gather warps waited for at least one first-touch row from DRAM
+        auto prefetch_tile = [&](int t) {
+            if (t >= n_my) return;
+            const int row0n = ((int)blockIdx.x + t * (int)gridDim.x) * HOP_TILE;
+            const int rowsn = min(HOP_TILE, p.n_dst - row0n);
+            const int tid = lq * 32 + lane;
+            if (tid < rowsn) {
+                if (p.o_dst) {
+                    const float* r = p.o_dst + ((long long)p.dst_lo + row0n + tid) * HF;
+                    if (pp.pf_l1) { prefetch_l1(r); prefetch_l1(r + 32); } else { prefetch_l2(r); prefetch_l2(r + 32); }
+                }
+                if (p.addend) {
+                    const float* r = p.addend + ((long long)p.dst_lo + row0n + tid) * HF;
+                    prefetch_l2(r); prefetch_l2(r + 32);
+                }
+            }
+            const int e0 = __ldg(p.rowptr + row0n), e1 = __ldg(p.rowptr + row0n + rowsn);
+            for (int e = e0 + tid; e < e1; e += HOP_EPI_WARPS * 32) {
+                const float* r = p.o_src + (long long)__ldg(p.src + e) * HF;
+                if (pp.pf_l1) { prefetch_l1(r); prefetch_l1(r + 32); } else { prefetch_l2(r); prefetch_l2(r + 32); }
+            }
+        };
+#if SR_PREFETCH
+        for (int t = 1; t < pp.pf_dist; ++t) prefetch_tile(t);           // (tile 0 is being gathered already; the loop takes over at pf_dist)
+#endif
 #pragma unroll 1
         for (int i = 0; i < n_my; ++i) {
             const int dslot = i & 1;
@@ -710,22 +736,7 @@ __global__ void __launch_bounds__(HOP_THREADS, 1) hop_tc16s_kernel(const __grid_
             mbar_arrive(&bar->d_empty[dslot]);
             mbar_arrive(&bar->st_full);
 #if SR_PREFETCH
-            // These warps sleep for most of a tile: they pull the rows tile i+2 will gather (its own o[c] rows and its
-            // sources) into L2 — every pass of the gather warps waited for at least one first-touch row from DRAM
-            if (pp.pf_dist > 0 && i + pp.pf_dist < n_my) {
-                const int row0n = ((int)blockIdx.x + (i + pp.pf_dist) * (int)gridDim.x) * HOP_TILE;
-                const int rowsn = min(HOP_TILE, p.n_dst - row0n);
-                const int tid = lq * 32 + lane;
-                if (p.o_dst && tid < rowsn) {
-                    const float* r = p.o_dst + ((long long)p.dst_lo + row0n + tid) * HF;
-                    if (pp.pf_l1) { prefetch_l1(r); prefetch_l1(r + 32); } else { prefetch_l2(r); prefetch_l2(r + 32); }
-                }
-                const int e0 = __ldg(p.rowptr + row0n), e1 = __ldg(p.rowptr + row0n + rowsn);
-                for (int e = e0 + tid; e < e1; e += HOP_EPI_WARPS * 32) {
-                    const float* r = p.o_src + (long long)__ldg(p.src + e) * HF;
-                    if (pp.pf_l1) { prefetch_l1(r); prefetch_l1(r + 32); } else { prefetch_l2(r); prefetch_l2(r + 32); }
-                }
-            }
+            if (pp.pf_dist > 0) prefetch_tile(i + pp.pf_dist);
 #endif
         }
     }

@@ -214,6 +214,10 @@ def ptr(t: Optional[torch.Tensor], dtype=torch.float32) -> Optional[int]:
         raise TypeError(f"expected {dtype}, got {t.dtype}")
     if not t.is_contiguous():
         raise ValueError("tensor must be contiguous")
+    if t.device.index != torch.cuda.current_device():
+        # every launch goes to the current device's stream (_stream): a tensor of another device would be an illegal address
+        raise RuntimeError(f"tensor on {t.device} but the current CUDA device is {torch.cuda.current_device()}: "
+                           "call torch.cuda.set_device / use `with torch.cuda.device(...)` around the call")
     return t.data_ptr()
 
 
