@@ -619,6 +619,8 @@ class SweGnnLauncher:
             raise NotImplementedError("multi-hop propagation needs source and destination in the same node set")
         bufs = [tmp_b, tmp_a] if o_src is tmp_a else [tmp_a, tmp_b]
         hb = hop_backend()
+        if hb == "tc16s" and es.max_block4 > 12:
+            hb = "tc"                  # in-degrees beyond the s-ring kernel's staging (not a dual mesh): per-thread loads
         use_tc = m.with_filter_matrix and self.F == 64 and FP == 64 and hb in ("tc", "tc16", "tc16s")
         Wtc = (self.filters.tc16_images() if hb in ("tc16", "tc16s") else self.filters.tc_images()) if use_tc else None
         hop_tc = {"tc16": lib.propagate_hop_tc16_fwd, "tc16s": lib.propagate_hop_tc16s_fwd}.get(hb, lib.propagate_hop_tc_fwd)

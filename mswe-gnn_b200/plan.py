@@ -36,11 +36,22 @@ class EdgeSet:
     # transposed view (grouped by src, stable in CSR position) — built lazily for the backward pass
     t_rowptr: Optional[torch.Tensor] = None
     t_pos: Optional[torch.Tensor] = None
+    # largest number of edges of 4 consecutive destinations (the s-ring hop stages 12 per such block; -1: unknown)
+    max_block4: int = -1
 
 
 def _build_edge_set(row, col, node_map, dst_lo, n_dst, src_lo, src_hi) -> EdgeSet:
     rowptr, src, dst, eid = lib.csr_build(row.contiguous(), col.contiguous(), node_map, dst_lo, n_dst, src_lo, src_hi)
-    return EdgeSet(rowptr, src, dst, eid, int(row.numel()), dst_lo, n_dst, src_lo, src_hi)
+    es = EdgeSet(rowptr, src, dst, eid, int(row.numel()), dst_lo, n_dst, src_lo, src_hi)
+    if n_dst > 0:
+        # blocks as the s-ring hop cuts them: 4 destinations starting at multiples of 4 (one host read per edge set, once
+        # per topology)
+        idx = torch.arange(0, n_dst + 4, 4, device=rowptr.device).clamp_(max=n_dst)
+        rp = rowptr[idx.long()]
+        es.max_block4 = int((rp[1:] - rp[:-1]).max()) if rp.numel() > 1 else 0
+    else:
+        es.max_block4 = 0
+    return es
 
 
 @dataclass
