@@ -86,7 +86,7 @@ def _csr_of(d):
     return n, rowptr, src, dst, eid
 
 
-@pytest.mark.parametrize("backend", ["tc", "tc16"])
+@pytest.mark.parametrize("backend", ["tc", "tc16", "tc16s"])
 @pytest.mark.parametrize("act,addend", [(0, False), ("tanh", True), ("prelu", False)])
 def test_hop_tc_stage_vs_fp64(act, addend, backend):
     """out[c] = act(o[c] + (sum_p s_p * (o[c] - o[src_p])) W^T + addend[c]) (models/gnn.py:428-443) in fp64 from the
@@ -105,10 +105,11 @@ def test_hop_tc_stage_vs_fp64(act, addend, backend):
     slope = torch.tensor([0.25], device=DEV) if act == "prelu" else None
     out = torch.empty(n, 64, device=DEV)
     code = ACT_CODES[act] if isinstance(act, str) else 0
-    if backend == "tc16":
+    if backend in ("tc16", "tc16s"):
         img = torch.empty(lib.hop_tc16_image_bytes(), dtype=torch.uint8, device=DEV)
         lib.hop_tc16_pack(W.contiguous(), float(W.abs().max()), img)
-        lib.propagate_hop_tc16_fwd(o, o, s, rowptr, src, 0, n, img, True, False, add, code, slope, None, out)
+        (lib.propagate_hop_tc16s_fwd if backend == "tc16s" else lib.propagate_hop_tc16_fwd)(
+            o, o, s, rowptr, src, 0, n, img, True, False, add, code, slope, None, out)
     else:
         img = torch.empty(lib.hop_tc_image_bytes(), dtype=torch.uint8, device=DEV)
         lib.hop_tc_pack(W.contiguous(), img)

@@ -148,3 +148,22 @@ def test_hop_tc16s_bit_identical_to_tc16():
         lib.propagate_hop_tc16s_fwd(o, o, s, rowptr, src, 0, n, img, 1, 0, add, 3, slope, agg_b, b)
     torch.cuda.synchronize()
     assert torch.equal(a, b)
+
+
+def test_edge_set_block_bound_selects_the_hop():
+    """plan.EdgeSet.max_block4 (edges of 4 consecutive destinations, as the s-ring hop cuts its passes) is what
+    engine.SweGnnLauncher.run reads to keep graphs beyond the staging on the per-thread-load hop."""
+    if BACKEND[0] != "tc16s":
+        pytest.skip("one run is enough")
+    from mswe_gnn_b200.plan import _build_edge_set
+    d = make_single_scale_mesh(40, 31, seed=2)
+    n = d.x.shape[0]
+    ei = d.edge_index.to(DEV)
+    es = _build_edge_set(ei[0], ei[1], None, 0, n, 0, n)
+    deg = torch.bincount(ei[1], minlength=n)
+    blocks = torch.nn.functional.pad(deg, (0, (-n) % 4)).view(-1, 4).sum(1)
+    assert es.max_block4 == int(blocks.max()) <= 12                    # a dual mesh: in-degree <= 3
+    hub = torch.stack([torch.arange(20, device=DEV), torch.full((20,), 7, device=DEV)])
+    ei2 = torch.cat([ei, hub], 1)
+    es2 = _build_edge_set(ei2[0].contiguous(), ei2[1].contiguous(), None, 0, n, 0, n)
+    assert es2.max_block4 > 12
