@@ -364,7 +364,10 @@ __global__ void __launch_bounds__(HOP_THREADS, 1) hop_tc16_kernel(const __grid_c
 //   * per pass one buffer of SR_CAP edges (3 KB), refilled for the next tile as soon as the pass has read it;
 //   * the warp's 9 rowptr values are fetched two tiles ahead, its src ids one tile ahead (cp.async, 4 B per lane),
 //     so the only global round trip left on a pass's chain is the gather of the o rows;
-//   * edges beyond a buffer's capacity (in-degree > 3 on all four nodes of a pass) come from global memory as before.
+//   * a pass whose rows exceed the staging (more than 12 edges on its four nodes, or more than 32 on the warp's eight:
+//     never on a dual mesh) is not staged at all and runs one edge at a time from global memory; engine.py keeps edge
+//     sets like that on hop_tc_kernel (plan.EdgeSet.max_block4);
+//   * the four epilogue warps, idle for most of a tile, prefetch.global.L2 the rows tile i+3 will touch.
 // Same arithmetic, same order: bit-identical to hop_tc16_kernel.
 // =================================================================================================================
 constexpr int SR_NODES = 8;                    // nodes per warp and tile
