@@ -238,14 +238,20 @@ __global__ void reduce_partials_kernel(const float* __restrict__ part, int n_par
         if (k >= k_valid) continue;
         // per-CTA partials in CTA order, fp32 with two interleaved accumulators (fp64 here made the kernel conversion-bound:
         // 3.3 instead of 1.5 ms per cfg2-train step, for no measurable change of the gradients)
-        float t0 = 0.f, t1 = 0.f;
+        // eight interleaved accumulators (a fixed order: partial c goes to accumulator c mod 8): the loop is a chain of dependent
+        // loads, and with two accumulators a launch over ~150-300 partials was pure latency (~100 such launches per training step)
+        float t[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+        const float* pj = part + item_off + j;
         int c = 0;
-        for (; c + 1 < n_parts; c += 2) {
-            t0 += part[(long long)c * part_stride + item_off + j];
-            t1 += part[(long long)(c + 1) * part_stride + item_off + j];
+        for (; c + 7 < n_parts; c += 8) {
+            float v[8];
+#pragma unroll
+            for (int u = 0; u < 8; ++u) v[u] = pj[(long long)(c + u) * part_stride];
+#pragma unroll
+            for (int u = 0; u < 8; ++u) t[u] += v[u];
         }
-        if (c < n_parts) t0 += part[(long long)c * part_stride + item_off + j];
-        out[(long long)(j / ko) * ld_out + k_off + k] += t0 + t1;
+        for (int u = 0; c < n_parts; ++c, ++u) t[u] += pj[(long long)c * part_stride];
+        out[(long long)(j / ko) * ld_out + k_off + k] += ((t[0] + t[1]) + (t[2] + t[3])) + ((t[4] + t[5]) + (t[6] + t[7]));
     }
 }
 
